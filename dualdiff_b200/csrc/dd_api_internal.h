@@ -1,0 +1,10 @@
+// internal declarations shared by the .cu translation units
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/dualdiff_b200.h"
+
+namespace dd {
+int gemm_run(const dd_gemm_args* a, cudaStream_t stream);
+void count_launch(int n = 1);
+}  // namespace dd

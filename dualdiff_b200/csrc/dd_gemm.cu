@@ -1,0 +1,410 @@
+// dualdiff_b200 — tcgen05 / TMEM / TMA GEMM core (sm_100a).
+//
+// One persistent, warp-specialised kernel computes
+//     out[m, n] = epilogue( sum_{tap, k} A[m + shift(tap), k] * W[n, tap*K + k] )
+// which covers, on the DualDiff denoising path:
+//   * Linear / 1x1 conv   (taps = 1)                         diffusers Attention.to_q/k/v/out,
+//                                                            FeedForward, Transformer2DModel.proj_in/out,
+//                                                            ResnetBlock2D.conv_shortcut, ControlNet zero convs
+//   * 3x3 stride-1 conv as implicit GEMM (taps = 9)          ResnetBlock2D.conv1/conv2, Upsample2D.conv,
+//                                                            conv_out.  The activation is stored in a
+//                                                            zero-haloed "padded pixel" layout
+//                                                            [img][H+1][W+1][C], so tap (kh,kw) is the same
+//                                                            2-D TMA box shifted by (kh-1)*(W+1)+(kw-1) rows.
+//   * channel concat of two sources along K (skip connections of the up blocks) without torch.cat.
+// Epilogues (fused): +bias[n], +per-image vector (time-embedding), +residual(s), GEGLU, fp32/bf16 out,
+// padded-pixel -> compact-row scatter for the conv mode.
+//
+// Roles: warp0 = TMA producer, warp1 = UMMA issuer (+TMEM alloc), warps2-5 = epilogue (TMEM -> regs -> HBM).
+// Pipelines: smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "dd_api_internal.h"
+#include "dd_common.cuh"
+
+namespace dd {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+static constexpr int GEMM_THREADS = 192;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmDev {
+  int M, N, K, K1, taps;
+  int conv_H, conv_W;  // conv mode (taps == 9): image geometry of the padded layout
+  int m_tiles, n_tiles, stages;
+  // epilogue
+  void* out;
+  long long out_ld;
+  int out_f32;
+  const float* bias;
+  const float* rowvec;
+  int rowvec_ld;
+  int rows_per_img;
+  const bf16* res1;
+  long long res1_ld;
+  const bf16* res2;
+  long long res2_ld;
+  int geglu;
+  int n_store;  // number of valid output columns (N, or N/2 for GEGLU)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int ACC_COLS = (BN < 32) ? 32 : BN;      // columns per accumulator buffer
+  constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
+  __shared__ uint32_t tmem_ptr_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const uint32_t full_bar = smem_u32(&bars[0]);
+  const uint32_t empty_bar = smem_u32(&bars[8]);
+  const uint32_t tfull_bar = smem_u32(&bars[16]);
+  const uint32_t tempty_bar = smem_u32(&bars[18]);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr_smem;
+
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int iters = p.taps * kchunks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int pitch = p.conv_W + 1;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      uint32_t it_global = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM;
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int it = 0; it < iters; ++it, ++it_global) {
+          const int s = it_global % stages;
+          const uint32_t ph = (it_global / stages) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+          const int tap = it / kchunks;
+          const int kc = (it - tap * kchunks) * BK;
+          int arow = m0;
+          if (p.taps == 9) arow += (tap / 3 - 1) * pitch + (tap % 3 - 1);
+          const uint32_t sA = smem_base + s * STAGE_BYTES;
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          if (kc < p.K1)
+            tma_load_2d(sA, &tmA, full_bar + 8 * s, kc, arow);
+          else
+            tma_load_2d(sA, &tmA2, full_bar + 8 * s, kc - p.K1, arow);
+          tma_load_2d(sB, &tmB, full_bar + 8 * s, tap * p.K + kc, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- UMMA issuer --------------------------------
+    if (lane == 0) {
+      uint32_t it_global = 0;
+      uint32_t local_tile = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+        const uint32_t as = local_tile & 1;
+        const uint32_t aph = (local_tile >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+        for (int it = 0; it < iters; ++it, ++it_global) {
+          const int s = it_global % stages;
+          const uint32_t ph = (it_global / stages) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA = smem_base + s * STAGE_BYTES;
+          const uint32_t sB = sA + A_STAGE_BYTES;
+          const uint64_t dA = umma_smem_desc(sA, 16, 1024, 2);
+          const uint64_t dB = umma_smem_desc(sB, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
+            umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * s);  // frees the smem slot when these UMMAs retire
+        }
+        umma_commit(tfull_bar + 8 * as);  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps ------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t local_tile = 0;
+    const int HW1 = (p.conv_H + 1) * pitch;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+      const int m0 = (tile / p.n_tiles) * BM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const uint32_t as = local_tile & 1;
+      const uint32_t aph = (local_tile >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      bool valid = m < p.M;
+      long long orow = m;
+      if (p.taps == 9) {
+        const int img = m / HW1;
+        const int rem = m - img * HW1;
+        const int hp = rem / pitch;
+        const int wp = rem - hp * pitch;
+        valid = valid && (hp < p.conv_H) && (wp < p.conv_W);
+        orow = ((long long)img * p.conv_H + hp) * p.conv_W + wp;
+      }
+      const float* rv = nullptr;
+      if (p.rowvec != nullptr && valid) rv = p.rowvec + (orow / p.rows_per_img) * (long long)p.rowvec_ld;
+      const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+
+      if (p.geglu) {
+        // tile columns [0, BN/2) = value half, [BN/2, BN) = gate half (weights are packed that way)
+        constexpr int HALF = BN / 2;
+        const int nout0 = (n0 / BN) * HALF;
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t a[32], g[32];
+          tmem_ld_32x32(tmem_acc + c, a);
+          tmem_ld_32x32(tmem_acc + HALF + c, g);
+          tmem_ld_wait();
+          if (valid) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + orow * p.out_ld + nout0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                float v0 = __uint_as_float(a[j + e]), v1 = __uint_as_float(a[j + e + 1]);
+                float g0 = __uint_as_float(g[j + e]), g1 = __uint_as_float(g[j + e + 1]);
+                if (p.bias) {
+                  v0 += p.bias[n0 + c + j + e];
+                  v1 += p.bias[n0 + c + j + e + 1];
+                  g0 += p.bias[n0 + HALF + c + j + e];
+                  g1 += p.bias[n0 + HALF + c + j + e + 1];
+                }
+                pk[e >> 1] = pack_bf16(v0 * gelu_erf_f(g0), v1 * gelu_erf_f(g1));
+              }
+              if (nout0 + c + j + 8 <= p.n_store)
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t a[32];
+          if (BN >= 32 || c == 0) tmem_ld_32x32(tmem_acc + c, a);
+          tmem_ld_wait();
+          const int nb = n0 + c;
+          if (valid && nb < p.n_store) {
+            if (nb + 32 <= p.n_store) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j + e]);
+                if (p.bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb + j);
+                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + nb + j + 4);
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (rv) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(rv + nb + j);
+                  const float4 b1 = *reinterpret_cast<const float4*>(rv + nb + j + 4);
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (p.res1) {
+                  const uint4 r = *reinterpret_cast<const uint4*>(p.res1 + orow * p.res1_ld + nb + j);
+                  float2 t;
+                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+                }
+                if (p.res2) {
+                  const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow * p.res2_ld + nb + j);
+                  float2 t;
+                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+                }
+                if (p.out_f32) {
+                  float* o = reinterpret_cast<float*>(p.out) + orow * p.out_ld + nb + j;
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+                  bf16* o = reinterpret_cast<bf16*>(p.out) + orow * p.out_ld + nb + j;
+                  *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+              }
+            } else {
+              // ragged right edge (N not a multiple of 32): scalar path
+              for (int j = 0; j < 32 && nb + j < p.n_store; ++j) {
+                float v = __uint_as_float(a[j]);
+                if (p.bias) v += p.bias[nb + j];
+                if (rv) v += rv[nb + j];
+                if (p.res1) v += __bfloat162float(p.res1[orow * p.res1_ld + nb + j]);
+                if (p.res2) v += __bfloat162float(p.res2[orow * p.res2_ld + nb + j]);
+                if (p.out_f32)
+                  reinterpret_cast<float*>(p.out)[orow * p.out_ld + nb + j] = v;
+                else
+                  reinterpret_cast<bf16*>(p.out)[orow * p.out_ld + nb + j] = __float2bfloat16(v);
+              }
+            }
+          }
+        }
+      }
+      // release the accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                       GemmDev p, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+  int stages = (200 * 1024) / STAGE_BYTES;
+  if (stages > 8) stages = 8;
+  const int iters = p.taps * ((p.K + BK - 1) / BK);
+  if (stages > iters && iters >= 2) stages = iters;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024 - 2048));
+    attr_done = true;
+  }
+  p.m_tiles = (p.M + BM - 1) / BM;
+  p.n_tiles = (p.N + BN - 1) / BN;
+  int grid = p.m_tiles * p.n_tiles;
+  const int sms = num_sms();
+  if (grid > sms) grid = sms;
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, p);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int pick_bn(int N, int geglu, int force) {
+  if (force > 0) return force;
+  if (geglu) return 256;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  // choose the tile width that wastes the fewest columns, preferring wide tiles (less smem traffic / flop)
+  const int cands[] = {256, 192, 160, 128};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const int tiles = (N + bn - 1) / bn;
+    const double waste = (double)tiles * bn / N;           // >= 1
+    const double smem_pen = (8192.0 / bn + 64.0) / 96.0;   // relative smem bytes per MMA cycle
+    const double cost = waste * (0.75 + 0.25 * smem_pen);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
+  DD_CHECK(a != nullptr, -1, "dd_gemm: null args");
+  DD_CHECK(a->M > 0 && a->N > 0 && a->K > 0, -1, "dd_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  DD_CHECK(a->taps == 1 || a->taps == 9, -1, "dd_gemm: taps must be 1 or 9 (got %d)", a->taps);
+  DD_CHECK(a->K % 8 == 0, -1, "dd_gemm: K=%d must be a multiple of 8 (16-byte TMA rows)", a->K);
+  DD_CHECK(a->a_ld % 8 == 0 && a->w_ld % 8 == 0, -1, "dd_gemm: leading dims must be multiples of 8");
+  DD_CHECK(((uintptr_t)a->a & 15) == 0 && ((uintptr_t)a->w & 15) == 0 && ((uintptr_t)a->out & 15) == 0,
+           -1, "dd_gemm: pointers must be 16-byte aligned");
+  int K1 = a->K;
+  if (a->a2 != nullptr) {
+    K1 = a->k1;
+    DD_CHECK(K1 > 0 && K1 < a->K && K1 % BK == 0, -1, "dd_gemm: dual-source split k1=%d must be a multiple of 64", K1);
+    DD_CHECK(a->a2_ld % 8 == 0 && ((uintptr_t)a->a2 & 15) == 0, -1, "dd_gemm: a2 alignment");
+  }
+  if (a->taps == 9) DD_CHECK(a->conv_h > 0 && a->conv_w > 0, -1, "dd_gemm: conv geometry missing");
+  if (a->geglu) DD_CHECK(a->N % 256 == 0 && !a->out_f32, -1, "dd_gemm: GEGLU needs N %% 256 == 0 and bf16 out");
+  const int n_store = a->geglu ? a->N / 2 : a->N;
+  DD_CHECK(a->out_ld >= n_store, -1, "dd_gemm: out_ld too small");
+  if (n_store % 8 != 0) DD_CHECK(a->res1 == nullptr || true, -1, "unreachable");
+
+  const int bn = pick_bn(a->N, a->geglu, a->force_bn);
+  CUtensorMap tmA, tmA2, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, BM, BK);
+  if (rc) return rc;
+  if (a->a2 != nullptr) {
+    rc = make_tmap_2d_bf16(&tmA2, a->a2, (uint64_t)a->M, (uint64_t)(a->K - K1), (uint64_t)a->a2_ld, BM, BK);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+  }
+  rc = make_tmap_2d_bf16(&tmB, a->w, (uint64_t)a->N, (uint64_t)a->K * a->taps, (uint64_t)a->w_ld, bn, BK);
+  if (rc) return rc;
+
+  GemmDev p;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.K1 = K1; p.taps = a->taps;
+  p.conv_H = a->conv_h; p.conv_W = a->conv_w;
+  p.out = a->out; p.out_ld = a->out_ld; p.out_f32 = a->out_f32;
+  p.bias = a->bias; p.rowvec = a->rowvec; p.rowvec_ld = a->rowvec_ld;
+  p.rows_per_img = a->rows_per_img > 0 ? a->rows_per_img : 1;
+  p.res1 = reinterpret_cast<const bf16*>(a->res1); p.res1_ld = a->res1_ld;
+  p.res2 = reinterpret_cast<const bf16*>(a->res2); p.res2_ld = a->res2_ld;
+  p.geglu = a->geglu; p.n_store = n_store;
+  p.m_tiles = p.n_tiles = p.stages = 0;
+  switch (bn) {
+    case 32: return launch_gemm<32>(tmA, tmA2, tmB, p, stream);
+    case 64: return launch_gemm<64>(tmA, tmA2, tmB, p, stream);
+    case 128: return launch_gemm<128>(tmA, tmA2, tmB, p, stream);
+    case 160: return launch_gemm<160>(tmA, tmA2, tmB, p, stream);
+    case 192: return launch_gemm<192>(tmA, tmA2, tmB, p, stream);
+    case 256: return launch_gemm<256>(tmA, tmA2, tmB, p, stream);
+    default: DD_CHECK(false, -1, "dd_gemm: unsupported tile width %d", bn);
+  }
+  return 0;
+}
+
+}  // namespace dd

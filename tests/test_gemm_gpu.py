@@ -1,0 +1,77 @@
+"""tcgen05 GEMM / implicit-GEMM conv parity (GPU). Reference = torch fp32 on the same bf16-rounded inputs.
+Tolerance: bf16 output rounding -> max-abs <= 2e-2 * max|ref|."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(out, ref):
+    return ((out.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (300, 320, 320, 0), (1400, 320, 320, 160), (1000, 640, 1280, 0),
+    (257, 1280, 768, 256), (129, 960, 320, 192), (77, 64, 768, 0), (50, 32, 128, 0),
+    (4096, 2560, 640, 0), (133, 200, 72, 0),
+])
+def test_linear(M, N, K, bn):
+    from dualdiff_b200 import ops
+    a = _mk((M, K), 1); w = _mk((N, K), 2, K ** -0.5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    out = ops.gemm(a, w, bias=bias, force_bn=bn)
+    ref = a.float() @ w.float().t() + bias
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+def test_epilogue_residual_rowvec_f32():
+    from dualdiff_b200 import ops
+    n_img, T, K, N = 3, 350, 640, 640
+    a = _mk((n_img * T, K), 1); w = _mk((N, K), 2, K ** -0.5)
+    r1 = _mk((n_img * T, N), 4); r2 = _mk((n_img * T, N), 5)
+    rv = torch.randn(n_img, N, generator=torch.Generator().manual_seed(6)).cuda()
+    ref = a.float() @ w.float().t() + r1.float() + r2.float() + rv.repeat_interleave(T, 0)
+    out = ops.gemm(a, w, res1=r1, res2=r2, rowvec=rv, rows_per_img=T)
+    assert _rel(out, ref) < 1e-2
+    out32 = ops.gemm(a, w, res1=r1, res2=r2, rowvec=rv, rows_per_img=T, out_f32=True)
+    assert out32.dtype == torch.float32 and _rel(out32, ref) < 2e-3
+
+
+def test_dual_source_concat():
+    from dualdiff_b200 import ops
+    M, K1, K2, N = 700, 640, 320, 320
+    a1 = _mk((M, K1), 1); a2 = _mk((M, K2), 2); w = _mk((N, K1 + K2), 3, (K1 + K2) ** -0.5)
+    out = ops.gemm(a1, w, a2=a2)
+    ref = torch.cat([a1, a2], 1).float() @ w.float().t()
+    assert _rel(out, ref) < 1e-2
+
+
+def test_geglu():
+    from dualdiff_b200 import ops, packing
+    M, C = 500, 320
+    a = _mk((M, C), 1); w = _mk((8 * C, C), 2, C ** -0.5)
+    b = torch.randn(8 * C, generator=torch.Generator().manual_seed(3)).cuda()
+    wp, bp = packing.pack_geglu(w, b)
+    out = ops.gemm(a, wp, bias=bp, geglu=True)
+    proj = a.float() @ w.float().t() + b
+    v, g = proj.chunk(2, -1)
+    ref = v * F.gelu(g)
+    assert out.shape == (M, 4 * C) and _rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("n,H,W,ci,co", [(2, 28, 50, 320, 320), (3, 14, 25, 640, 1280), (2, 7, 13, 1280, 1280),
+                                         (5, 4, 7, 128, 64), (1, 28, 50, 320, 4)])
+def test_conv3x3_implicit_gemm(n, H, W, ci, co):
+    from dualdiff_b200 import ops, packing
+    x = _mk((n, H, W, ci), 1)
+    w = _mk((co, ci, 3, 3), 2, (9 * ci) ** -0.5)
+    bias = torch.randn(co, generator=torch.Generator().manual_seed(3)).cuda()
+    out = ops.gemm(packing.to_padded(x), packing.pack_conv3x3(w), bias=bias, taps=9, conv_hw=(H, W), n_img=n)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
