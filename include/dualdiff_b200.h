@@ -26,11 +26,16 @@ extern "C" {
 #endif
 
 #define DD_VERSION 100
+#if defined(__GNUC__)
+#define DD_API __attribute__((visibility("default")))
+#else
+#define DD_API
+#endif
 
-int dd_version(void);
-const char* dd_last_error(void);
+DD_API int dd_version(void);
+DD_API const char* dd_last_error(void);
 /* number of kernels launched by this library since load (bench.py `gpu_launches`) */
-long long dd_launch_count(void);
+DD_API long long dd_launch_count(void);
 
 /* ---- GEMM / implicit-GEMM convolution on tcgen05 tensor cores ------------------------------------
  * out = epilogue( A[M, K(*taps)] x W[N, taps*K]^T )
@@ -59,7 +64,7 @@ typedef struct dd_gemm_args {
                          column groups per 256-wide tile (dd pack_geglu in dualdiff_b200/packing.py) */
   int force_bn;       /* 0 = auto tile width; testing hook                                        */
 } dd_gemm_args;
-int dd_gemm(const dd_gemm_args* args, void* stream);
+DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 
 #ifdef __cplusplus
 }
