@@ -30,6 +30,43 @@ class GemmArgs(C.Structure):
     ]
 
 
+class GroupNormArgs(C.Structure):
+    _fields_ = [
+        ("x1", _vp), ("x2", _vp), ("out", _vp), ("stats", _vp), ("gamma", _vp), ("beta", _vp),
+        ("x1_ld", _ll), ("x2_ld", _ll), ("out_ld", _ll),
+        ("n_img", _i), ("h", _i), ("w", _i), ("c1", _i), ("c2", _i), ("groups", _i),
+        ("eps", _f), ("silu", _i), ("padded_out", _i),
+    ]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [("x", _vp), ("out", _vp), ("gamma", _vp), ("beta", _vp), ("x_ld", _ll), ("out_ld", _ll),
+                ("rows", _i), ("c", _i), ("eps", _f)]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("v", _vp), ("out", _vp), ("kv_map", _vp),
+        ("q_ld", _ll), ("k_ld", _ll), ("v_ld", _ll), ("out_ld", _ll),
+        ("q_cols", _i), ("k_cols", _i), ("v_cols", _i),
+        ("q_col0", _i), ("k_col0", _i), ("v_col0", _i),
+        ("q_head_stride", _i), ("k_head_stride", _i), ("v_head_stride", _i),
+        ("n_img", _i), ("n_kv_img", _i), ("heads", _i), ("head_dim", _i), ("lq", _i), ("lk", _i), ("n_src", _i),
+        ("scale", _f),
+    ]
+
+
+class ToPaddedArgs(C.Structure):
+    _fields_ = [("src", _vp), ("out", _vp), ("stride_outer", _ll), ("stride_view", _ll), ("stride_c", _ll),
+                ("stride_h", _ll), ("n_outer", _i), ("n_view", _i), ("c", _i), ("h", _i), ("w", _i), ("cp", _i),
+                ("src_f32", _i)]
+
+
+class LinearF32Args(C.Structure):
+    _fields_ = [("x", _vp), ("w", _vp), ("b", _vp), ("y", _vp), ("y16", _vp), ("x_ld", _ll), ("y_ld", _ll),
+                ("y16_ld", _ll), ("M", _i), ("N", _i), ("K", _i), ("act", _i)]
+
+
 _lib = None
 
 
@@ -54,7 +91,10 @@ def lib():
 
 # every symbol include/dualdiff_b200.h declares (tests/test_abi.py checks the list against the header)
 EXPORTS = [
-    "dd_version", "dd_last_error", "dd_launch_count", "dd_gemm",
+    "dd_version", "dd_last_error", "dd_launch_count", "dd_gemm", "dd_groupnorm", "dd_layernorm", "dd_attention",
+    "dd_nchw_to_padded", "dd_im2col_s2", "dd_upsample_pad", "dd_pad_rows", "dd_linear_f32",
+    "dd_timestep_embedding", "dd_fourier_embed", "dd_box_features", "dd_silu_to_bf16", "dd_add_bf16",
+    "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step",
 ]
 
 

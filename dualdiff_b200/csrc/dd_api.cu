@@ -88,4 +88,13 @@ int dd_gemm(const dd_gemm_args* args, void* stream) {
   if (rc == 0) dd::count_launch();
   return rc;
 }
+int dd_groupnorm(const dd_groupnorm_args* args, void* stream) {
+  return dd::groupnorm_run(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int dd_layernorm(const dd_layernorm_args* args, void* stream) {
+  return dd::layernorm_run(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int dd_attention(const dd_attention_args* args, void* stream) {
+  return dd::attention_run(args, reinterpret_cast<cudaStream_t>(stream));
+}
 }

@@ -6,5 +6,8 @@
 
 namespace dd {
 int gemm_run(const dd_gemm_args* a, cudaStream_t stream);
+int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream);
+int layernorm_run(const dd_layernorm_args* a, cudaStream_t stream);
+int attention_run(const dd_attention_args* a, cudaStream_t stream);
 void count_launch(int n = 1);
 }  // namespace dd

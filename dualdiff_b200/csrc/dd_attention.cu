@@ -1,0 +1,303 @@
+// dualdiff_b200 — flash-style fused attention on tcgen05 / TMEM / TMA (sm_100a).
+//
+// One kernel serves the four attentions of the DualDiff step:
+//   self        (diffusers BasicTransformerBlock.attn1,  networks/blocks.py:166-172)
+//   text-cross  (attn2, keys = [camera token | 77 text tokens | box tokens], blocks.py:182-188)
+//   cross-view  (attn4, networks/blocks.py:190-222): each view attends to its two ring neighbours; the two
+//               softmax-attentions are computed back to back and SUMMED in the epilogue, so the reference's
+//               torch.cat of 12 (view, neighbour) pairs, the duplicated projections and the CPU-mask gather
+//               disappear (out = A_left + A_right; to_out then adds 2*b_o, see packing.py)
+//   SFA         (networks/txt_con_fusion.py:110-177): 320-ch condition feature map queries the 77 text tokens.
+//
+// CTA = (128 query rows, one head, one image).  S = Q K^T and O_tile = P V run on the tensor cores with
+// fp32 accumulators in TMEM; the 128 softmax threads own one query row each (TMEM lane == row), so the online
+// softmax needs no shuffles.  K/V tiles arrive by TMA through a 2-stage mbarrier ring; V is consumed as an
+// MN-major UMMA operand straight from its row-major [key, dv] layout (no transpose pass).
+#include "dd_api_internal.h"
+#include "dd_common.cuh"
+
+namespace dd {
+
+static constexpr int ATT_BM = 128;
+static constexpr int ATT_BN = 128;
+static constexpr int ATT_THREADS = 160;     // 4 softmax warps + 1 TMA/UMMA warp
+static constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 64 bf16 (one SWIZZLE_128B column chunk)
+
+struct AttnDev {
+  int Lq, Lk, n_src, n_kv_tiles;
+  const int* kv_map;  // [n_img * n_src] kv image per (query image, source) or nullptr (identity)
+  float scale_log2e;
+  bf16* out;
+  long long out_ld;
+  int q_col0, k_col0, v_col0, q_hs, k_hs, v_hs, o_hs;
+};
+
+template <int DQK, int DV, int DVP, int STAGES>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
+  constexpr int QCH = (DQK + 63) / 64;
+  constexpr int VCH = (DVP + 63) / 64;
+  constexpr int KV_STAGE_BYTES = (QCH + VCH) * CHUNK_BYTES;
+  constexpr int TMEM_COLS = (128 + DVP <= 256) ? 256 : 512;
+  constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+  constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, DVP, 0, 1);  // B (=V) is MN-major
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sKV = sQ + QCH * CHUNK_BYTES;
+  const uint32_t sP = sKV + STAGES * KV_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t bars[10];
+  __shared__ uint32_t tmem_ptr_smem;
+  const uint32_t q_full = smem_u32(&bars[0]);
+  const uint32_t s_full = smem_u32(&bars[1]);
+  const uint32_t p_full = smem_u32(&bars[2]);
+  const uint32_t o_full = smem_u32(&bars[3]);
+  const uint32_t kv_full = smem_u32(&bars[4]);   // [STAGES]
+  const uint32_t kv_empty = smem_u32(&bars[6]);  // [STAGES]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(kv_full + 8 * s, 1);
+      mbar_init(kv_empty + 8 * s, 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr_smem;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+  const int total = p.n_src * p.n_kv_tiles;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      // Q tile (once)
+      mbar_arrive_expect_tx(q_full, QCH * CHUNK_BYTES);
+      for (int c = 0; c < QCH; ++c)
+        tma_load_3d(sQ + c * CHUNK_BYTES, &tmQ, q_full, p.q_col0 + head * p.q_hs + c * 64, q_tile * ATT_BM, img);
+      auto produce = [&](int g) {
+        const int s = g % STAGES;
+        const uint32_t ph = (g / STAGES) & 1;
+        mbar_wait(kv_empty + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(kv_full + 8 * s, KV_STAGE_BYTES);
+        const int src = g / p.n_kv_tiles, jt = g - src * p.n_kv_tiles;
+        const int kv_img = p.kv_map ? p.kv_map[img * p.n_src + src] : img;
+        const uint32_t sK = sKV + s * KV_STAGE_BYTES;
+        const uint32_t sV = sK + QCH * CHUNK_BYTES;
+        for (int c = 0; c < QCH; ++c)
+          tma_load_3d(sK + c * CHUNK_BYTES, &tmK, kv_full + 8 * s, p.k_col0 + head * p.k_hs + c * 64, jt * ATT_BN, kv_img);
+        for (int c = 0; c < VCH; ++c)
+          tma_load_3d(sV + c * CHUNK_BYTES, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs + c * 64, jt * ATT_BN, kv_img);
+      };
+      produce(0);
+      mbar_wait(q_full, 0);
+      for (int g = 0; g < total; ++g) {
+        const int s = g % STAGES;
+        const uint32_t ph = (g / STAGES) & 1;
+        mbar_wait(kv_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sK = sKV + s * KV_STAGE_BYTES;
+        const uint32_t sV = sK + QCH * CHUNK_BYTES;
+        // S = Q K^T  (both operands K-major, 64-column swizzle chunks)
+#pragma unroll
+        for (int kk = 0; kk < DQK / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+          umma_bf16(tmem_S, umma_smem_desc(sQ + off, 16, 1024, 2), umma_smem_desc(sK + off, 16, 1024, 2), IDESC_S,
+                    kk != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (STAGES > 1 && g + 1 < total) produce(g + 1);
+        mbar_wait(p_full, g & 1);
+        tc_fence_after();
+        // O_tile = P V : A = P (K-major, 2 chunks of 64 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          const uint32_t offP = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+          const uint32_t offV = kk * 16 * 128;  // 16 key rows of 128 B
+          umma_bf16(tmem_O, umma_smem_desc(sP + offP, 16, 1024, 2),
+                    umma_smem_desc(sV + offV, CHUNK_BYTES, 1024, 2), IDESC_O, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(o_full);
+        if (STAGES == 1 && g + 1 < total) produce(g + 1);
+      }
+    }
+  } else {
+    // ------------------------------- softmax / accumulate / epilogue -------------------------------
+    const int row = threadIdx.x;  // == TMEM lane
+    const int q_row = q_tile * ATT_BM + row;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const float sl2 = p.scale_log2e;
+    bf16* orow = p.out + ((long long)img * p.Lq + q_row) * p.out_ld + head * p.o_hs;
+    const uint32_t p_row_base = sP + row * 128;
+    const uint32_t xr = (uint32_t)(row & 7);
+    int g = 0;
+    for (int src = 0; src < p.n_src; ++src) {
+      float m = -INFINITY, l = 0.f;
+      float o[DVP];
+#pragma unroll
+      for (int i = 0; i < DVP; ++i) o[i] = 0.f;
+      for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        const int key0 = jt * ATT_BN;
+        // pass 1: row max over the valid keys
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_S + lane_sel + c, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+        }
+        const float m_new = fmaxf(m, mx * sl2);
+        const float alpha = exp2f(m - m_new);
+        float lsum = 0.f;
+        // pass 2: p = exp2(s*scale*log2e - m_new), write bf16 P into the swizzled K-major A tile
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_S + lane_sel + c, sv);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float p0 = (key0 + c + j < p.Lk) ? exp2f(__uint_as_float(sv[j]) * sl2 - m_new) : 0.f;
+            float p1 = (key0 + c + j + 1 < p.Lk) ? exp2f(__uint_as_float(sv[j + 1]) * sl2 - m_new) : 0.f;
+            lsum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+          }
+          const uint32_t chunk_base = p_row_base + (c >> 6) * CHUNK_BYTES;
+          const uint32_t u0 = (uint32_t)((c & 63) >> 3);  // first 16-byte unit of this 32-key group
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t addr = chunk_base + (((u0 + u) ^ xr) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                         "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                         : "memory");
+          }
+        }
+        l = l * alpha + lsum;
+        m = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        // accumulate this tile's O contribution
+        mbar_wait(o_full, g & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DVP; c += 16) {
+          uint32_t ov[16];
+          tmem_ld_32x16(tmem_O + lane_sel + c, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[c + j] = o[c + j] * alpha + __uint_as_float(ov[j]);
+        }
+        tc_fence_before();
+      }
+      if (q_row < p.Lq) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int c = 0; c < DV; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = o[c + e] * inv;
+          if (src > 0) {
+            const uint4 r = *reinterpret_cast<const uint4*>(orow + c);
+            float2 t;
+            t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+            t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+            t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+            t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+          }
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int DQK, int DV, int DVP, int STAGES>
+static int launch_attn(const dd_attention_args* a, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                       const CUtensorMap& tmV, AttnDev p, cudaStream_t stream) {
+  constexpr int QCH = (DQK + 63) / 64, VCH = (DVP + 63) / 64;
+  constexpr size_t smem = (size_t)QCH * CHUNK_BYTES + (size_t)STAGES * (QCH + VCH) * CHUNK_BYTES + 2 * CHUNK_BYTES + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DD_CUDA(cudaFuncSetAttribute(attn_tcgen05_kernel<DQK, DV, DVP, STAGES>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((a->lq + ATT_BM - 1) / ATT_BM, a->heads, a->n_img);
+  attn_tcgen05_kernel<DQK, DV, DVP, STAGES><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  DD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attention_run(const dd_attention_args* a, cudaStream_t stream) {
+  DD_CHECK(a != nullptr, -1, "dd_attention: null args");
+  DD_CHECK(a->n_img > 0 && a->heads > 0 && a->lq > 0 && a->lk > 0, -1, "dd_attention: bad shape");
+  DD_CHECK(a->head_dim == 40 || a->head_dim == 80 || a->head_dim == 160, -1,
+           "dd_attention: head_dim %d unsupported (40, 80, 160 = SDv1.5 levels)", a->head_dim);
+  DD_CHECK(a->n_src == 1 || a->n_src == 2, -1, "dd_attention: n_src must be 1 or 2");
+  DD_CHECK(a->n_src == 1 || a->kv_map != nullptr, -1, "dd_attention: kv_map required for n_src == 2");
+  DD_CHECK(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->out_ld % 8 == 0, -1,
+           "dd_attention: leading dims must be multiples of 8");
+  DD_CHECK(a->n_kv_img > 0, -1, "dd_attention: n_kv_img missing");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  rc = make_tmap_3d_bf16(&tmQ, a->q, (uint64_t)a->q_cols, (uint64_t)a->lq, (uint64_t)a->n_img, (uint64_t)a->q_ld,
+                         (uint64_t)a->lq * a->q_ld, 64, ATT_BM, 1);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tmK, a->k, (uint64_t)a->k_cols, (uint64_t)a->lk, (uint64_t)a->n_kv_img, (uint64_t)a->k_ld,
+                         (uint64_t)a->lk * a->k_ld, 64, ATT_BN, 1);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tmV, a->v, (uint64_t)a->v_cols, (uint64_t)a->lk, (uint64_t)a->n_kv_img, (uint64_t)a->v_ld,
+                         (uint64_t)a->lk * a->v_ld, 64, ATT_BN, 1);
+  if (rc) return rc;
+  AttnDev p;
+  p.Lq = a->lq; p.Lk = a->lk; p.n_src = a->n_src; p.n_kv_tiles = (a->lk + ATT_BN - 1) / ATT_BN;
+  p.kv_map = a->kv_map;
+  p.scale_log2e = a->scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld;
+  p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
+  p.q_hs = a->q_head_stride; p.k_hs = a->k_head_stride; p.v_hs = a->v_head_stride; p.o_hs = a->head_dim;
+  switch (a->head_dim) {
+    case 40:
+      DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
+               "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
+      return launch_attn<48, 40, 48, 2>(a, tmQ, tmK, tmV, p, stream);
+    case 80: return launch_attn<80, 80, 80, 2>(a, tmQ, tmK, tmV, p, stream);
+    case 160: return launch_attn<160, 160, 160, 1>(a, tmQ, tmK, tmV, p, stream);
+  }
+  return -1;
+}
+
+}  // namespace dd

@@ -1,0 +1,265 @@
+// dualdiff_b200 — bandwidth-bound normalisation kernels (sm_100a).
+//   * GroupNorm(32) [+ SiLU] over channels-last activations, optional channel-concat of two sources
+//     (up-block skip connections), output either compact rows or the zero-haloed padded-pixel layout the
+//     3x3 implicit-GEMM conv consumes.  Replaces diffusers ResnetBlock2D.norm1/norm2 + SiLU,
+//     Transformer2DModel.norm and conv_norm_out (unet_2d_condition_multiview.py:519-521).
+//   * LayerNorm over the channel dim of token rows (blocks.py:163,177,192,225).
+// fp32 statistics, bf16 I/O, 16-byte vector accesses, warp-shuffle reductions.
+#include "dd_api_internal.h"
+#include "dd_common.cuh"
+
+namespace dd {
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm pass 1: per (image, channel) sum and sum of squares -> stats[img][C][2] (fp32, pre-zeroed)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384)
+gn_stats_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
+                long long ld2, int C, int HW, int rows_per_cta, float* __restrict__ stats) {
+  const int img = blockIdx.y;
+  const int tpr = C >> 3;                    // threads per row (8 channels each)
+  const int rpi = blockDim.x / tpr;          // rows per iteration
+  const int lane_c = threadIdx.x % tpr;
+  const int sub = threadIdx.x / tpr;
+  if (sub >= rpi) return;
+  const int c0 = lane_c * 8;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(HW, r_begin + rows_per_cta);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  const bool from1 = c0 < C1;
+  const bf16* base = from1 ? x1 + c0 : x2 + (c0 - C1);
+  const long long ld = from1 ? ld1 : ld2;
+  for (int r = r_begin + sub; r < r_end; r += rpi) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + r) * ld);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16(w[e]);
+      s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+      s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+    }
+  }
+  float* o = stats + ((long long)img * C + c0) * 2;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(o + 2 * e, s[e]);
+    atomicAdd(o + 2 * e + 1, q[e]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm pass 2: normalise + affine (+ SiLU), write compact or padded layout
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384)
+gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
+                long long ld2, int C, int H, int W, int groups, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ stats, int silu, int padded, bf16* __restrict__ out,
+                long long out_ld, int rows_per_cta) {
+  extern __shared__ float sm[];  // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  const int img = blockIdx.y;
+  const int cpg = C / groups;
+  const int HW = H * W;
+  // per-group mean / rstd from the per-channel sums (one warp-level pass over the channels)
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    const float* st = stats + ((long long)img * C + g * cpg) * 2;
+    for (int c = 0; c < cpg; ++c) {
+      s += st[2 * c];
+      q += st[2 * c + 1];
+    }
+    const float inv_n = 1.f / (float)(cpg * HW);
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    for (int c = 0; c < cpg; ++c) {
+      const int ch = g * cpg + c;
+      const float ga = gamma[ch] * rstd;
+      scale[ch] = ga;
+      shift[ch] = beta[ch] - mean * ga;
+    }
+  }
+  __syncthreads();
+  const int tpr = C >> 3;
+  const int rpi = blockDim.x / tpr;
+  const int lane_c = threadIdx.x % tpr;
+  const int sub = threadIdx.x / tpr;
+  if (sub >= rpi) return;
+  const int c0 = lane_c * 8;
+  const bool from1 = c0 < C1;
+  const bf16* base = from1 ? x1 + c0 : x2 + (c0 - C1);
+  const long long ld = from1 ? ld1 : ld2;
+  const int Wp = W + 1;
+  const int rows_img = padded ? (H + 1) * Wp : HW;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(rows_img, r_begin + rows_per_cta);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = scale[c0 + e];
+    sh[e] = shift[c0 + e];
+  }
+  for (int r = r_begin + sub; r < r_end; r += rpi) {
+    int src = r;
+    bool live = true;
+    if (padded) {
+      const int hp = r / Wp, wp = r - hp * Wp;
+      live = (hp < H) && (wp < W);
+      src = hp * W + wp;
+    }
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (live) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + src) * ld);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        float a = f.x * sc[2 * e] + sh[2 * e];
+        float b = f.y * sc[2 * e + 1] + sh[2 * e + 1];
+        if (silu) {
+          a = silu_f(a);
+          b = silu_f(b);
+        }
+        pk[e] = pack_bf16(a, b);
+      }
+      o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    *reinterpret_cast<uint4*>(out + ((long long)img * rows_img + r) * out_ld + c0) = o;
+  }
+}
+
+int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
+  DD_CHECK(a != nullptr, -1, "dd_groupnorm: null args");
+  const int C = a->c1 + a->c2;
+  DD_CHECK(a->n_img > 0 && a->h > 0 && a->w > 0 && C > 0, -1, "dd_groupnorm: bad shape");
+  DD_CHECK(C % 8 == 0 && a->c1 % 8 == 0, -1, "dd_groupnorm: channels must be multiples of 8 (C=%d c1=%d)", C, a->c1);
+  DD_CHECK(C % a->groups == 0, -1, "dd_groupnorm: C=%d not divisible by groups=%d", C, a->groups);
+  DD_CHECK(C <= 2048 * 8 && (C >> 3) <= 256 * 4, -1, "dd_groupnorm: C=%d too large", C);
+  DD_CHECK(a->c2 == 0 || a->x2 != nullptr, -1, "dd_groupnorm: x2 missing");
+  const int HW = a->h * a->w;
+  int tpr = C >> 3;
+  int threads = 256;
+  if (tpr > 256) threads = ((tpr + 31) / 32) * 32;  // C up to 2560 -> 320 threads
+  DD_CHECK(threads <= 384, -1, "dd_groupnorm: C=%d too large (max 3072)", C);
+  DD_CUDA(cudaMemsetAsync(a->stats, 0, sizeof(float) * 2 * (size_t)a->n_img * C, stream));
+  const int rpi = threads / tpr;
+  int rows_per_cta = rpi * 8;
+  {
+    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, a->n_img);
+    gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1,
+                                                  reinterpret_cast<const bf16*>(a->x2), a->x2_ld, C, HW,
+                                                  rows_per_cta, a->stats);
+    DD_CUDA(cudaGetLastError());
+  }
+  {
+    const int rows_img = a->padded_out ? (a->h + 1) * (a->w + 1) : HW;
+    rows_per_cta = rpi * 16;
+    dim3 grid((rows_img + rows_per_cta - 1) / rows_per_cta, a->n_img);
+    const size_t smem = sizeof(float) * 2 * C;
+    gn_apply_kernel<<<grid, threads, smem, stream>>>(
+        reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1, reinterpret_cast<const bf16*>(a->x2),
+        a->x2_ld, C, a->h, a->w, a->groups, a->eps, a->gamma, a->beta, a->stats, a->silu, a->padded_out,
+        reinterpret_cast<bf16*>(a->out), a->out_ld, rows_per_cta);
+    DD_CUDA(cudaGetLastError());
+  }
+  count_launch(2);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 1280 -> <= 5 x uint4 per lane)
+// ---------------------------------------------------------------------------------------------------
+template <int VPL>  // uint4 vectors per lane
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ out, long long out_ld,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int C,
+                 float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const bf16* xr = x + (long long)warp * x_ld;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        v[i][2 * e] = f.x;
+        v[i][2 * e + 1] = f.y;
+        s += f.x + f.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  bf16* orow = out + (long long)warp * out_ld;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        pk[e] = pack_bf16((v[i][2 * e] - mean) * rstd * g[2 * e] + b[2 * e],
+                          (v[i][2 * e + 1] - mean) * rstd * g[2 * e + 1] + b[2 * e + 1]);
+      *reinterpret_cast<uint4*>(orow + vi * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+int layernorm_run(const dd_layernorm_args* a, cudaStream_t stream) {
+  DD_CHECK(a != nullptr && a->rows > 0 && a->c > 0, -1, "dd_layernorm: bad args");
+  DD_CHECK(a->c % 8 == 0 && a->c <= 2048, -1, "dd_layernorm: C=%d must be a multiple of 8 and <= 2048", a->c);
+  const int nvec = a->c >> 3;
+  const int vpl = (nvec + 31) / 32;
+  const int threads = 256;
+  const int grid = (int)(((long long)a->rows * 32 + threads - 1) / threads);
+  const bf16* x = reinterpret_cast<const bf16*>(a->x);
+  bf16* out = reinterpret_cast<bf16*>(a->out);
+#define DD_LN(V)                                                                                         \
+  layernorm_kernel<V><<<grid, threads, 0, stream>>>(x, a->x_ld, out, a->out_ld, a->gamma, a->beta, a->rows, \
+                                                    a->c, a->eps)
+  if (vpl <= 1) DD_LN(1);
+  else if (vpl == 2) DD_LN(2);
+  else if (vpl == 3) DD_LN(3);
+  else if (vpl <= 5) DD_LN(5);
+  else DD_LN(8);
+#undef DD_LN
+  DD_CUDA(cudaGetLastError());
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace dd

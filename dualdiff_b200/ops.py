@@ -76,3 +76,199 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
         _req(rowvec, torch.float32, "rowvec")
     check(_lib.lib().dd_gemm(C.byref(args), _stream()), "dd_gemm")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+from ._lib import AttentionArgs, GroupNormArgs, LayerNormArgs, LinearF32Args, ToPaddedArgs  # noqa: E402
+
+_L = C.c_longlong
+_I = C.c_int
+
+
+def groupnorm(x1, gamma, beta, *, n_img, hw, x2=None, eps=1e-5, silu=True, padded_out=False, groups=32,
+              out=None, stats=None):
+    """GroupNorm(32) [+SiLU] over compact channels-last rows; x2 = second channel source (skip concat)."""
+    _req(x1, torch.bfloat16, "x1")
+    H, W = hw
+    c1 = x1.shape[1]
+    c2 = x2.shape[1] if x2 is not None else 0
+    C_ = c1 + c2
+    assert x1.shape[0] == n_img * H * W
+    rows = padded_rows(n_img, H, W) if padded_out else n_img * H * W
+    if out is None:
+        out = torch.empty((rows, C_), device=x1.device, dtype=torch.bfloat16)
+    if stats is None:
+        stats = torch.empty((n_img * C_ * 2,), device=x1.device, dtype=torch.float32)
+    a = GroupNormArgs()
+    a.x1 = _ptr(x1); a.x2 = _ptr(x2); a.out = _ptr(out); a.stats = _ptr(stats)
+    a.gamma = _ptr(gamma); a.beta = _ptr(beta)
+    a.x1_ld = x1.stride(0); a.x2_ld = x2.stride(0) if x2 is not None else 0; a.out_ld = out.stride(0)
+    a.n_img = n_img; a.h = H; a.w = W; a.c1 = c1; a.c2 = c2; a.groups = groups
+    a.eps = eps; a.silu = 1 if silu else 0; a.padded_out = 1 if padded_out else 0
+    check(_lib.lib().dd_groupnorm(C.byref(a), _stream()), "dd_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _req(x, torch.bfloat16, "x")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    a = LayerNormArgs()
+    a.x = _ptr(x); a.out = _ptr(out); a.gamma = _ptr(gamma); a.beta = _ptr(beta)
+    a.x_ld = x.stride(0); a.out_ld = out.stride(0); a.rows = rows; a.c = c; a.eps = eps
+    check(_lib.lib().dd_layernorm(C.byref(a), _stream()), "dd_layernorm")
+    return out
+
+
+def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_col0=0, v_col0=0,
+              q_hs=None, k_hs=None, v_hs=None, kv_map=None, n_src=1, n_kv_img=None, scale=None,
+              q_cols=None, k_cols=None, v_cols=None):
+    """q: [n_img*lq, *], k/v: [n_kv_img*lk, *] bf16 (may be column views of one fused projection output)."""
+    _req(q, torch.bfloat16, "q")
+    hs_qk = 48 if head_dim == 40 else head_dim
+    q_hs = hs_qk if q_hs is None else q_hs
+    k_hs = hs_qk if k_hs is None else k_hs
+    v_hs = head_dim if v_hs is None else v_hs
+    n_kv_img = n_img if n_kv_img is None else n_kv_img
+    if out is None:
+        out = torch.empty((n_img * lq, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = AttentionArgs()
+    a.q = _ptr(q); a.k = _ptr(k); a.v = _ptr(v); a.out = _ptr(out); a.kv_map = _ptr(kv_map)
+    a.q_ld = q.stride(0); a.k_ld = k.stride(0); a.v_ld = v.stride(0); a.out_ld = out.stride(0)
+    a.q_cols = q.shape[1] if q_cols is None else q_cols
+    a.k_cols = k.shape[1] if k_cols is None else k_cols
+    a.v_cols = v.shape[1] if v_cols is None else v_cols
+    a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0
+    a.q_head_stride = q_hs; a.k_head_stride = k_hs; a.v_head_stride = v_hs
+    a.n_img = n_img; a.n_kv_img = n_kv_img; a.heads = heads; a.head_dim = head_dim
+    a.lq = lq; a.lk = lk; a.n_src = n_src
+    a.scale = float(head_dim) ** -0.5 if scale is None else scale
+    check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")
+    return out
+
+
+def nchw_to_padded(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_view, stride_c, stride_h, out=None):
+    assert src.is_cuda and src.dtype in (torch.float32, torch.bfloat16)
+    n = n_outer * n_view
+    if out is None:
+        out = torch.empty((padded_rows(n, h, w), cp), device=src.device, dtype=torch.bfloat16)
+    a = ToPaddedArgs()
+    a.src = _ptr(src); a.out = _ptr(out)
+    a.stride_outer = stride_outer; a.stride_view = stride_view; a.stride_c = stride_c; a.stride_h = stride_h
+    a.n_outer = n_outer; a.n_view = n_view; a.c = c; a.h = h; a.w = w; a.cp = cp
+    a.src_f32 = 1 if src.dtype == torch.float32 else 0
+    check(_lib.lib().dd_nchw_to_padded(C.byref(a), _stream()), "dd_nchw_to_padded")
+    return out
+
+
+def im2col_s2(x, *, n_img, hw, out=None):
+    _req(x, torch.bfloat16, "x")
+    H, W = hw
+    c = x.shape[1]
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((n_img * ho * wo, 9 * c), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().dd_im2col_s2(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s2")
+    return out, (ho, wo)
+
+
+def upsample_pad(x, *, n_img, hw, hw2, out=None):
+    _req(x, torch.bfloat16, "x")
+    H, W = hw
+    H2, W2 = hw2
+    c = x.shape[1]
+    if out is None:
+        out = torch.empty((padded_rows(n_img, H2, W2), c), device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().dd_upsample_pad(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, H2, W2, _stream()),
+          "dd_upsample_pad")
+    return out
+
+
+def pad_rows(x, *, n_img, hw, out=None):
+    return upsample_pad(x, n_img=n_img, hw=hw, hw2=hw, out=out)
+
+
+def linear_f32(x, w, b=None, *, act=0, out=None, out16=None, want_f32=True):
+    _req(x, torch.float32, "x")
+    _req(w, torch.float32, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and w.is_contiguous()
+    if out is None and want_f32:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    a = LinearF32Args()
+    a.x = _ptr(x); a.w = _ptr(w); a.b = _ptr(b); a.y = _ptr(out); a.y16 = _ptr(out16)
+    a.x_ld = x.stride(0); a.y_ld = out.stride(0) if out is not None else 0
+    a.y16_ld = out16.stride(0) if out16 is not None else 0
+    a.M = M; a.N = N; a.K = K; a.act = act
+    check(_lib.lib().dd_linear_f32(C.byref(a), _stream()), "dd_linear_f32")
+    return out if out is not None else out16
+
+
+def timestep_embedding(t, dim):
+    _req(t, torch.float32, "t")
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
+    check(_lib.lib().dd_timestep_embedding(_ptr(t), _ptr(out), t.shape[0], dim, _stream()), "dd_timestep_embedding")
+    return out
+
+
+def fourier_embed(x, nfreq=4):
+    _req(x, torch.float32, "x")
+    assert x.shape[-1] == 3 and x.is_contiguous()
+    rows = x.numel() // 3
+    out = torch.empty((rows, 3 + 6 * nfreq), device=x.device, dtype=torch.float32)
+    check(_lib.lib().dd_fourier_embed(_ptr(x), _ptr(out), _L(rows), nfreq, _stream()), "dd_fourier_embed")
+    return out
+
+
+def box_features(boxes, classes, masks, class_tokens, null_pos, null_cls, pos_out, cls_out):
+    """boxes [n, P, 3] fp32, classes [n] int64, masks [n] uint8/bool -> pos_out [n, 27P], cls_out [n, 768]"""
+    n, P = boxes.shape[0], boxes.shape[1]
+    m8 = masks.to(torch.uint8).contiguous()
+    check(_lib.lib().dd_box_features(_ptr(boxes), _ptr(classes), _ptr(m8), _ptr(class_tokens), _ptr(null_pos),
+                                     _ptr(null_cls), _ptr(pos_out), _L(pos_out.stride(0)), _ptr(cls_out),
+                                     _L(cls_out.stride(0)), _L(n), P, class_tokens.shape[1], _stream()),
+          "dd_box_features")
+
+
+def silu_to_bf16(x, out=None):
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib.lib().dd_silu_to_bf16(_ptr(x), _ptr(out), _L(x.numel()), _stream()), "dd_silu_to_bf16")
+    return out
+
+
+def add_bf16(a, b, c=None, out=None):
+    _req(a, torch.bfloat16, "a")
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib().dd_add_bf16(_ptr(a), _ptr(b), _ptr(c), _ptr(out), _L(a.numel()), _stream()), "dd_add_bf16")
+    return out
+
+
+def nchw_to_rows(src, out=None):
+    """[n, C, H, W] fp32/bf16 contiguous -> [n*H*W, C] bf16"""
+    assert src.is_cuda and src.is_contiguous()
+    n, c, h, w = src.shape
+    if out is None:
+        out = torch.empty((n * h * w, c), device=src.device, dtype=torch.bfloat16)
+    check(_lib.lib().dd_nchw_to_rows(_ptr(src), 1 if src.dtype == torch.float32 else 0, _ptr(out), n, c, h * w,
+                                     _stream()), "dd_nchw_to_rows")
+    return out
+
+
+def rows_to_nchw(rows, n_img, hw, out_dtype=torch.float32, c=None):
+    H, W = hw
+    c = rows.shape[1] if c is None else c
+    out = torch.empty((n_img, c, H, W), device=rows.device, dtype=out_dtype)
+    check(_lib.lib().dd_rows_to_nchw(_ptr(rows), 1 if rows.dtype == torch.float32 else 0, _L(rows.stride(0)),
+                                     _ptr(out), 1 if out_dtype == torch.float32 else 0, n_img, c, H * W, _stream()),
+          "dd_rows_to_nchw")
+    return out
+
+
+def cfg_sched_step(eps, x, last, m0, m1, coef, *, n_img, c, hw, cfg=True):
+    check(_lib.lib().dd_cfg_sched_step(_ptr(eps), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), n_img, c,
+                                       hw, 1 if cfg else 0, _stream()), "dd_cfg_sched_step")

@@ -66,6 +66,109 @@ typedef struct dd_gemm_args {
 } dd_gemm_args;
 DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 
+/* ---- GroupNorm(32) [+SiLU] ------------------------------------------------------------------------
+ * replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm,
+ * conv_norm_out + conv_act (networks/unet_2d_condition_multiview.py:519-521).
+ * Input: compact channels-last rows [n_img*H*W, c1] (+ optional second source [.., c2], concatenated along
+ * channels = the up-block skip concat).  Output: compact rows, or (padded_out=1) the zero-haloed layout
+ * [n_img][(H+1)][(W+1)][C] that dd_gemm(taps=9) consumes.  stats: fp32 scratch [n_img*C*2]. */
+typedef struct dd_groupnorm_args {
+  const void* x1; const void* x2; void* out; float* stats;
+  const float* gamma; const float* beta;
+  long long x1_ld, x2_ld, out_ld;
+  int n_img, h, w, c1, c2, groups;
+  float eps;
+  int silu, padded_out;
+} dd_groupnorm_args;
+DD_API int dd_groupnorm(const dd_groupnorm_args* args, void* stream);
+
+/* ---- LayerNorm over token rows (networks/blocks.py:163,177,192,225) -------------------------------- */
+typedef struct dd_layernorm_args {
+  const void* x; void* out; const float* gamma; const float* beta;
+  long long x_ld, out_ld;
+  int rows, c;
+  float eps;
+} dd_layernorm_args;
+DD_API int dd_layernorm(const dd_layernorm_args* args, void* stream);
+
+/* ---- fused flash attention on tcgen05 (self / text-cross / cross-view / SFA) -------------------------
+ * replaces xformers.ops.memory_efficient_attention behind diffusers Attention (networks/blocks.py:166-222,
+ * networks/txt_con_fusion.py:156-162).  out[img, row, h*head_dim + c] = sum_src softmax(q k_src^T * scale) v_src.
+ * q/k/v are bf16 row-major matrices [n_img*l, ld]; head h of q lives in columns q_col0 + h*q_head_stride ...
+ * (a fused QKV projection output is addressed in place).  head_dim 40 requires the Q and K heads to be
+ * zero-padded to a 48-column stride (packing.py:pack_qkv).  n_src = 2 with kv_map[img*2 + s] = the two
+ * neighbour images implements the reference's `neighboring_attn_type == "add"` cross-view attention. */
+typedef struct dd_attention_args {
+  const void* q; const void* k; const void* v; void* out;
+  const int* kv_map;          /* device int32 [n_img * n_src] or NULL (kv image == query image) */
+  long long q_ld, k_ld, v_ld, out_ld;
+  int q_cols, k_cols, v_cols; /* logical widths of the q/k/v matrices (TMA bounds)             */
+  int q_col0, k_col0, v_col0;
+  int q_head_stride, k_head_stride, v_head_stride;
+  int n_img, n_kv_img, heads, head_dim, lq, lk, n_src;
+  float scale;
+} dd_attention_args;
+DD_API int dd_attention(const dd_attention_args* args, void* stream);
+
+/* ---- layout / gather kernels feeding the implicit-GEMM convolution ---------------------------------- */
+/* NCHW (fp32 or bf16, arbitrary outer strides) -> padded channels-last bf16 with channel zero-padding to cp.
+ * Image index = outer * n_view + view; source offset = outer*stride_outer + view*stride_view + c*stride_c +
+ * y*stride_h + x.  Used for conv_in on the latents (CFG duplication = stride_outer 0) and for the
+ * 6-way panorama split of the bg condition image (networks/map_embedder.py:116-125). */
+typedef struct dd_to_padded_args {
+  const void* src; void* out;
+  long long stride_outer, stride_view, stride_c, stride_h;
+  int n_outer, n_view, c, h, w, cp;
+  int src_f32;
+} dd_to_padded_args;
+DD_API int dd_nchw_to_padded(const dd_to_padded_args* args, void* stream);
+/* 3x3 stride-2 pad-1 patches of a compact activation -> [n_img*Ho*Wo, 9*C] (diffusers Downsample2D.conv and the
+ * stride-2 convs of ControlNetConditioningEmbedding) */
+DD_API int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
+/* nearest-neighbour resize to (h2, w2) written in the padded layout (diffusers Upsample2D with explicit size,
+ * networks/unet_2d_condition_multiview.py:363-374,500-501): src = floor(dst * in / out) */
+DD_API int dd_upsample_pad(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, int h2, int w2,
+                           void* stream);
+/* compact -> padded copy (no normalisation), for 3x3 convs whose input is not a GroupNorm output */
+DD_API int dd_pad_rows(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
+
+/* ---- small fp32 pieces (time / camera / box embedders; hard part 4: fp32 sin/cos and MLPs) ----------- */
+/* y[M,N] = act(x[M,K] W[N,K]^T + b); act: 0 none, 1 SiLU.  y fp32 (ld y_ld) and/or bf16 copy y16 (ld y16_ld). */
+typedef struct dd_linear_f32_args {
+  const float* x; const float* w; const float* b; float* y; void* y16;
+  long long x_ld, y_ld, y16_ld;
+  int M, N, K, act;
+} dd_linear_f32_args;
+DD_API int dd_linear_f32(const dd_linear_f32_args* args, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[i] = cat[cos(t_i f), sin(t_i f)] fp32 */
+DD_API int dd_timestep_embedding(const float* t, float* out, int n, int dim, void* stream);
+/* networks/embedder.py:5-40: [x, sin(x 2^k), cos(x 2^k)]_{k<nfreq} over the last dim (3) of x[rows,3] */
+DD_API int dd_fourier_embed(const float* x, float* out, long long rows, int nfreq, void* stream);
+/* networks/bbox_embedder.py:180-194: pos = fourier(boxes)*m + null_pos*(1-m); cls = class_tokens[c]*m + null_cls*(1-m) */
+DD_API int dd_box_features(const float* boxes, const long long* classes, const unsigned char* masks,
+                           const float* class_tokens, const float* null_pos, const float* null_cls,
+                           float* pos_out, long long pos_ld, float* cls_out, long long cls_ld,
+                           long long n_box, int n_pts, int cls_dim, void* stream);
+/* out = silu(x) (fp32 -> bf16), n elements */
+DD_API int dd_silu_to_bf16(const float* x, void* out, long long n, void* stream);
+/* out = a + b (+ c) elementwise over bf16, n elements (multiple of 8) */
+DD_API int dd_add_bf16(const void* a, const void* b, const void* c, void* out, long long n, void* stream);
+/* fp32 -> bf16 / bf16 -> fp32 NCHW<->channels-last conversions at the module boundary */
+DD_API int dd_nchw_to_rows(const void* src, int src_f32, void* out, int n_img, int c, int hw, void* stream);
+DD_API int dd_rows_to_nchw(const void* rows, int rows_f32, long long ld, void* out, int out_f32, int n_img, int c,
+                           int hw, void* stream);
+
+/* ---- CFG combine + UniPC/DDIM update, one pass (pipeline/pipeline_bev_controlnet.py:487-499) -------- */
+/* eps: fp32 channels-last [2*n_img*hw, c] (uncond half first) or [n_img*hw, c] when cfg == 0.
+ * State (fp32, NCHW, n_img*c*hw each): x (latents, in/out), last (corrected sample), m0, m1 (x0 history).
+ * coef (device, fp32[16]): {guidance, sigma_t, 1/alpha_t, a_last, a_m0, a_m1, a_x0, a_x, b_xc, b_x0, b_m0, ...}
+ *   x0  = (x - sigma_t*eps) / alpha_t
+ *   xc  = a_x*x + a_last*last + a_m0*m0 + a_m1*m1 + a_x0*x0          (UniC corrector; identity on step 0)
+ *   x'  = b_xc*xc + b_x0*x0 + b_m0*m0                                 (UniP predictor / DDIM)
+ *   then last <- xc, m1 <- m0, m0 <- x0, x <- x'.   Coefficients are computed on the host in fp64. */
+DD_API int dd_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef,
+                             int n_img, int c, int hw, int cfg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

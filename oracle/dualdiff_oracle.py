@@ -1,0 +1,451 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product path (dualdiff_b200/).
+
+A self-contained CPU/fp32 restatement, in functional form over a diffusers-keyed state dict, of the one
+hot path this repo accelerates: a DualDiff denoising step
+    [ControlNet-bg, ControlNet-fg] -> summed residuals -> multi-view UNet -> CFG -> scheduler update.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may
+import it.  Each function cites the reference lines (under /root/reference/MD_txt_con_fusion/magicdrive)
+or, for un-vendored third-party arithmetic (diffusers 0.17.1 / xformers), SURVEY.md Appendix A.
+
+Pinning: the reference ships NO tests, golden vectors or fixtures for this path, and the
+diffusers fork it depends on is not vendored, so the library-level semantics are "parity unpinned" by
+the reference itself.  What IS pinned: `oracle/make_golden.py` runs the reference's own, unmodified
+networks/*.py (imported from /root/reference on top of oracle/shim) on the same seeded weights/inputs and
+this file must reproduce those outputs (tests/test_oracle.py, fixtures in tests/golden/).
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+# configs/dataset/Nuscenes.yaml:27-33
+NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}
+BLOCK_OUT = (320, 640, 1280, 1280)
+HEADS = 8
+GROUPS = 32
+
+
+def _lin(sd: SD, p: str, x, bias=True):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias") if bias else None)
+
+
+def _conv(sd: SD, p: str, x, stride=1, padding=1):
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=stride, padding=padding)
+
+
+def _gn(sd: SD, p: str, x, eps):
+    return F.group_norm(x, GROUPS, sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _ln(sd: SD, p: str, x):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# third-party (diffusers 0.17.1) pieces — SURVEY Appendix A.1
+# ---------------------------------------------------------------------------------------------------
+def timestep_sinusoid(t: torch.Tensor, dim=320):
+    """Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): cat[cos, sin] of t * exp(-ln(1e4) * i / half)."""
+    half = dim // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    e = t[:, None].float() * f[None]
+    return torch.cat([torch.cos(e), torch.sin(e)], dim=-1)
+
+
+def time_embedding(sd: SD, t: torch.Tensor):
+    w1 = sd["time_embedding.linear_1.weight"]
+    e = timestep_sinusoid(t, w1.shape[1]).to(w1.dtype)  # sinusoid always fp32, then cast (unet..multiview.py:404-409)
+    return _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", e)))
+
+
+def mha(q, k, v, heads):
+    """softmax(q k^T / sqrt(d)) v with heads split from the channel dim (Attention + xformers MEA contract)."""
+    b, lq, c = q.shape
+    d = c // heads
+    qh = q.reshape(b, lq, heads, d).transpose(1, 2)
+    kh = k.reshape(b, k.shape[1], heads, d).transpose(1, 2)
+    vh = v.reshape(b, v.shape[1], heads, d).transpose(1, 2)
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
+    o = torch.matmul(s.softmax(-1), vh)
+    return o.transpose(1, 2).reshape(b, lq, c)
+
+
+def attention(sd: SD, p: str, x, ctx=None, out_proj=True):
+    ctx = x if ctx is None else ctx
+    o = mha(_lin(sd, p + ".to_q", x, False), _lin(sd, p + ".to_k", ctx, False), _lin(sd, p + ".to_v", ctx, False), HEADS)
+    return _lin(sd, p + ".to_out.0", o) if out_proj else o
+
+
+def feed_forward(sd: SD, p: str, x):
+    h, gate = _lin(sd, p + ".net.0.proj", x).chunk(2, dim=-1)  # GEGLU: value first, gate second
+    return _lin(sd, p + ".net.2", h * F.gelu(gate))
+
+
+def resnet(sd: SD, p: str, x, emb):
+    h = _conv(sd, p + ".conv1", F.silu(_gn(sd, p + ".norm1", x, 1e-5)))
+    h = h + _lin(sd, p + ".time_emb_proj", F.silu(emb))[:, :, None, None]
+    h = _conv(sd, p + ".conv2", F.silu(_gn(sd, p + ".norm2", h, 1e-5)))
+    if (p + ".conv_shortcut.weight") in sd:
+        x = _conv(sd, p + ".conv_shortcut", x, padding=0)
+    return x + h
+
+
+# ---------------------------------------------------------------------------------------------------
+# networks/blocks.py:144-238 — BasicMultiviewTransformerBlock (multiview=True) / stock block (False)
+# ---------------------------------------------------------------------------------------------------
+def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6):
+    x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x))             # blocks.py:163-172
+    x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), enc)        # blocks.py:175-188
+    if multiview:
+        # blocks.py:190-222.  The reference concatenates 12 (view, neighbour) pairs, runs attn4 once over the
+        # 12B batch, and sums the two neighbour outputs per view *after* to_out (so the bias is added twice).
+        # Algebraically: connector( W_o (A_left + A_right) + 2 b_o ).
+        h = _ln(sd, p + ".norm4", x)
+        bn, T, C = h.shape
+        hv = h.reshape(bn // n_cam, n_cam, T, C)
+        q = _lin(sd, p + ".attn4.to_q", hv, False)
+        k = _lin(sd, p + ".attn4.to_k", hv, False)
+        v = _lin(sd, p + ".attn4.to_v", hv, False)
+        acc = torch.zeros_like(hv)
+        for cam, nbrs in NEIGHBORS.items():
+            for nb in nbrs:
+                acc[:, cam] += mha(q[:, cam], k[:, nb], v[:, nb], HEADS)
+        w_o, b_o = sd[p + ".attn4.to_out.0.weight"], sd[p + ".attn4.to_out.0.bias"]
+        out = F.linear(acc, w_o) + 2.0 * b_o
+        out = _lin(sd, p + ".connector", out).reshape(bn, T, C)                # zero_linear connector, blocks.py:83,220
+        x = x + out
+    x = x + feed_forward(sd, p + ".ff", _ln(sd, p + ".norm3", x))             # blocks.py:225-236
+    return x
+
+
+def transformer_2d(sd: SD, p: str, x, enc, multiview: bool):
+    n, c, h, w = x.shape
+    r = x
+    y = _conv(sd, p + ".proj_in", _gn(sd, p + ".norm", x, 1e-6), padding=0)
+    y = y.permute(0, 2, 3, 1).reshape(n, h * w, c)
+    y = transformer_block(sd, p + ".transformer_blocks.0", y, enc, multiview)
+    y = y.reshape(n, h, w, c).permute(0, 3, 1, 2)
+    return _conv(sd, p + ".proj_out", y, padding=0) + r
+
+
+def _down_path(sd: SD, x, emb, enc, multiview: bool):
+    """3x CrossAttnDownBlock2D + DownBlock2D; returns (x, 12 skips) — Appendix A.1."""
+    skips = [x]
+    for i in range(4):
+        for j in range(2):
+            x = resnet(sd, f"down_blocks.{i}.resnets.{j}", x, emb)
+            if i < 3:
+                x = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", x, enc, multiview)
+            skips.append(x)
+        if i < 3:
+            x = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", x, stride=2, padding=1)
+            skips.append(x)
+    return x, skips
+
+
+def _mid(sd: SD, x, emb, enc, multiview: bool):
+    x = resnet(sd, "mid_block.resnets.0", x, emb)
+    x = transformer_2d(sd, "mid_block.attentions.0", x, enc, multiview)
+    return resnet(sd, "mid_block.resnets.1", x, emb)
+
+
+# ---------------------------------------------------------------------------------------------------
+# networks/unet_2d_condition_multiview.py:327-527
+# ---------------------------------------------------------------------------------------------------
+def unet_forward(sd: SD, sample, timestep, enc, down_res: Optional[List[torch.Tensor]] = None, mid_res=None):
+    n = sample.shape[0]
+    t = torch.as_tensor(timestep).reshape(-1).expand(n) if torch.as_tensor(timestep).numel() == 1 else timestep
+    emb = time_embedding(sd, t)                                                 # :386-411
+    x = _conv(sd, "conv_in", sample)                                            # :443
+    x, skips = _down_path(sd, x, emb, enc, True)                                # :446-462
+    if down_res is not None:
+        skips = [s + r for s, r in zip(skips, down_res)]                        # :464-473
+    x = _mid(sd, x, emb, enc, True)                                             # :476-485
+    if mid_res is not None:
+        x = x + mid_res                                                         # :487-488
+    for i in range(4):                                                          # :491-516
+        for j in range(3):
+            x = torch.cat([x, skips.pop()], dim=1)
+            x = resnet(sd, f"up_blocks.{i}.resnets.{j}", x, emb)
+            if i > 0:
+                x = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", x, enc, True)
+        if i < 3:
+            size = skips[-1].shape[2:]  # forward_upsample_size: explicit target (:363-374,500-501)
+            x = F.interpolate(x, size=tuple(size), mode="nearest")
+            x = _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", x)
+    x = F.silu(_gn(sd, "conv_norm_out", x, 1e-5))                               # :519-521
+    return _conv(sd, "conv_out", x)                                             # :522
+
+
+# ---------------------------------------------------------------------------------------------------
+# networks/embedder.py:5-40, networks/bbox_embedder.py:155-203, unet_addon_rawbox.py:308-361
+# ---------------------------------------------------------------------------------------------------
+def fourier_embed(x, num_freqs=4):
+    """Embedder(include_input, log_sampling): [x, sin(x*2^0), cos(x*2^0), ..., sin(x*2^3), cos(x*2^3)]."""
+    outs = [x]
+    for k in range(num_freqs):
+        f = 2.0 ** k
+        outs += [torch.sin(x * f), torch.cos(x * f)]
+    return torch.cat(outs, dim=-1)
+
+
+def camera_tokens(sd: SD, camera_param):
+    """(b, 6, 3, 7) -> (b, 6, 768): Fourier over each of the 7 length-3 columns, flattened (c d), cam2token."""
+    b, n = camera_param.shape[:2]
+    e = fourier_embed(camera_param.permute(0, 1, 3, 2).reshape(-1, 3))          # rows ordered (b n c)
+    return _lin(sd, "cam2token", e.reshape(b, n, -1))
+
+
+def _box_mlp(sd: SD, pos, cls):
+    e = F.silu(_lin(sd, "bbox_embedder.bbox_proj", pos))
+    e = torch.cat([e, cls], dim=-1)
+    e = F.silu(_lin(sd, "bbox_embedder.second_linear.0", e))
+    e = F.silu(_lin(sd, "bbox_embedder.second_linear.2", e))
+    return _lin(sd, "bbox_embedder.second_linear.4", e)
+
+
+def box_tokens(sd: SD, bboxes, classes, masks):
+    """bboxes (B, L, 8, 3), classes (B, L) int64, masks (B, L) bool -> (B, L, 768).  minmax_normalize False."""
+    B, L = classes.shape
+    m = masks.reshape(-1, 1).float()
+    pos = fourier_embed(bboxes.reshape(B * L, 8, 3)).reshape(B * L, -1)
+    pos = pos * m + sd["bbox_embedder.null_pos_feature"][None] * (1 - m)
+    cls = sd["bbox_embedder._class_tokens"][classes.reshape(-1)]
+    cls = cls * m + sd["bbox_embedder.null_class_feature"][None] * (1 - m)
+    return _box_mlp(sd, pos, cls).reshape(B, L, -1)
+
+
+# networks/txt_con_fusion.py:74-181 — Semantic Fusion Attention
+def sfa(sd: SD, cond, txt, p="txt_con_fusion"):
+    n, c, h, w = cond.shape
+    x = cond.reshape(n, c, h * w).transpose(1, 2)
+    o = mha(_lin(sd, p + ".to_q", x, False), _lin(sd, p + ".to_k", txt, False), _lin(sd, p + ".to_v", txt, False), 8)
+    o = _lin(sd, p + ".to_out.0", o)
+    return o.transpose(1, 2).reshape(n, c, h, w) + cond
+
+
+# networks/map_embedder.py:114-138 — ControlNetConditioningEmbedding (bg branch)
+def cond_embedding(sd: SD, cond, p="controlnet_cond_embedding"):
+    per_w = cond.shape[-1] // 6
+    x = torch.stack([cond[..., i * per_w:(i + 1) * per_w] if i < 5 else cond[..., 5 * per_w:] for i in range(6)], dim=1)
+    x = x.reshape(-1, *x.shape[2:])
+    x = F.silu(_conv(sd, p + ".conv_in", x))
+    for i in range(6):
+        x = F.silu(_conv(sd, f"{p}.blocks.{i}", x, stride=2 if i % 2 == 1 else 1))
+    return _conv(sd, p + ".conv_out", x)
+
+
+# ---------------------------------------------------------------------------------------------------
+# networks/unet_addon_rawbox.py:794-1082 — one ControlNet-style branch (inference path, eval mode)
+# ---------------------------------------------------------------------------------------------------
+def controlnet_forward(sd: SD, sample, timestep, camera_param, bboxes_3d_data, enc_text, controlnet_cond,
+                       use_occ_3d: bool, conditioning_scale: float = 1.0):
+    """sample (b, 6, 4, h, w); timestep (b,); camera_param (b, 6, 3, 7); enc_text (b, 77, 768);
+    bboxes_3d_data {bboxes (b, 6|1, L, 8, 3), classes, masks}; controlnet_cond: bg (b, 3, 8h, 48w) image or
+    fg (b*6, 320, h, w) ORS tensor.  Returns (12 residuals, mid residual, tokens (b*6, 78+L, 768))."""
+    b, n_cam = camera_param.shape[:2]
+    cam = camera_tokens(sd, camera_param)                                       # :832-837
+    txt = enc_text[:, None].expand(b, n_cam, *enc_text.shape[1:])               # use_aug_text False: repeat (:354)
+    enc_cam = torch.cat([cam[:, :, None], txt], dim=2)                          # (b, n, 78, 768)  :355-360
+    bb, cl, mk = bboxes_3d_data["bboxes"], bboxes_3d_data["classes"], bboxes_3d_data["masks"]
+    n_box = bb.shape[1]
+    tok = box_tokens(sd, bb.reshape(-1, *bb.shape[2:]), cl.reshape(-1, cl.shape[-1]), mk.reshape(-1, mk.shape[-1]))
+    if n_box != n_cam:                                                          # view-shared boxes: repeat (:879-883)
+        tok = tok.reshape(b, 1, *tok.shape[1:]).expand(b, n_cam, *tok.shape[1:])
+    else:
+        tok = tok.reshape(b, n_cam, *tok.shape[1:])
+    emb = time_embedding(sd, torch.as_tensor(timestep).reshape(-1))             # :903-929
+    x = sample.reshape(b * n_cam, *sample.shape[2:])                            # :944
+    enc_cam = enc_cam.reshape(b * n_cam, *enc_cam.shape[2:])
+    tok = tok.reshape(b * n_cam, *tok.shape[2:])
+    if emb.shape[0] < x.shape[0]:
+        emb = emb.repeat_interleave(n_cam, dim=0)                               # :951-952
+    x = _conv(sd, "conv_in", x)                                                 # :965
+    cond = controlnet_cond if use_occ_3d else cond_embedding(sd, controlnet_cond)   # :967-970
+    cond = sfa(sd, cond, enc_cam[:, 1:])                                        # :973-978 (camera token dropped)
+    x = x + cond                                                                # :990
+    enc = torch.cat([enc_cam, tok], dim=1)                                      # :1007
+    x, skips = _down_path(sd, x, emb, enc, False)                               # :998-1015
+    x = _mid(sd, x, emb, enc, False)                                            # :1018-1025
+    down = [_conv(sd, f"controlnet_down_blocks.{i}", s, padding=0) * conditioning_scale for i, s in enumerate(skips)]
+    mid = _conv(sd, "controlnet_mid_block", x, padding=0) * conditioning_scale  # :1029-1055
+    return down, mid, enc                                                       # :1066-1082
+
+
+# ---------------------------------------------------------------------------------------------------
+# CFG "uncond" half — unet_addon_rawbox.py:327-335, 671-769 (uncond first, cond second)
+# ---------------------------------------------------------------------------------------------------
+def add_uncond(sd: SD, camera_param, bboxes_3d_data):
+    b, n = camera_param.shape[:2]
+    unc = sd["uncond_cam.weight"][0].reshape(1, 1, 3, 7).expand(b, n, 3, 7)
+    cam = torch.cat([unc, camera_param], dim=0)
+    boxes = {k: torch.cat([torch.zeros_like(v), v], dim=0) for k, v in bboxes_3d_data.items()}
+    return cam, boxes
+
+
+# ---------------------------------------------------------------------------------------------------
+# UniPCMultistepScheduler (diffusers 0.17.1 defaults, bh2, order 2, predict_x0) — SURVEY Appendix A.3
+# ---------------------------------------------------------------------------------------------------
+class UniPC:
+    order = 1
+
+    def __init__(self, num_train=1000, beta_start=0.00085, beta_end=0.012, solver_order=2):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.alpha_t = torch.sqrt(self.alphas_cumprod)
+        self.sigma_t = torch.sqrt(1 - self.alphas_cumprod)
+        self.lambda_t = torch.log(self.alpha_t) - torch.log(self.sigma_t)
+        self.num_train = num_train
+        self.solver_order = solver_order
+
+    def set_timesteps(self, n):
+        import numpy as np
+        ts = np.linspace(0, self.num_train - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        _, idx = np.unique(ts, return_index=True)
+        ts = ts[np.sort(idx)]
+        self.timesteps = torch.from_numpy(ts)
+        self.num_inference_steps = len(ts)
+        self.model_outputs = [None] * self.solver_order
+        self.timestep_list = [None] * self.solver_order
+        self.lower_order_nums = 0
+        self.last_sample = None
+        self.this_order = 1
+
+    def scale_model_input(self, x, t=None):
+        return x
+
+    def _x0(self, eps, t, x):
+        return (x - self.sigma_t[t] * eps) / self.alpha_t[t]
+
+    def _update(self, x, m_list, t_list, t, order, x0_t=None):
+        """shared bh2 core.  predictor: x0_t None; corrector: x0_t = converted output at t, x = last_sample."""
+        s0, m0 = t_list[-1], m_list[-1]
+        lam_t, lam_s0 = self.lambda_t[t], self.lambda_t[s0]
+        alpha_t, sigma_t, sigma_s0 = self.alpha_t[t], self.sigma_t[t], self.sigma_t[s0]
+        h = lam_t - lam_s0
+        hh = -h
+        h_phi_1 = torch.expm1(hh)
+        B_h = torch.expm1(hh)
+        rks, D1s = [], []
+        for i in range(1, order):
+            si, mi = t_list[-(i + 1)], m_list[-(i + 1)]
+            rk = (self.lambda_t[si] - lam_s0) / h
+            rks.append(rk)
+            D1s.append((mi - m0) / rk)
+        rks.append(torch.tensor(1.0))
+        rks = torch.stack(rks)
+        R, bvec = [], []
+        h_phi_k = h_phi_1 / hh - 1
+        fact = 1
+        for i in range(1, order + 1):
+            R.append(torch.pow(rks, i - 1))
+            bvec.append(h_phi_k * fact / B_h)
+            fact *= i + 1
+            h_phi_k = h_phi_k / hh - 1 / fact
+        R, bvec = torch.stack(R), torch.stack(bvec)
+        x_t_ = sigma_t / sigma_s0 * x - alpha_t * h_phi_1 * m0
+        if x0_t is None:  # predictor (multistep_uni_p_bh_update)
+            if len(D1s) > 0:
+                rhos_p = torch.tensor([0.5]) if order == 2 else torch.linalg.solve(R[:-1, :-1], bvec[:-1])
+                pred = sum(r * d for r, d in zip(rhos_p, D1s))
+            else:
+                pred = 0
+            return x_t_ - alpha_t * B_h * pred
+        rhos_c = torch.tensor([0.5]) if order == 1 else torch.linalg.solve(R, bvec)
+        corr = sum(r * d for r, d in zip(rhos_c[:-1], D1s)) if len(D1s) > 0 else 0
+        D1_t = x0_t - m0
+        return x_t_ - alpha_t * B_h * (corr + rhos_c[-1] * D1_t)
+
+    def step(self, eps, t, x):
+        t = int(t)
+        idx = (self.timesteps == t).nonzero()
+        idx = len(self.timesteps) - 1 if len(idx) == 0 else int(idx[0])
+        use_corr = idx > 0 and self.last_sample is not None
+        x0 = self._x0(eps, t, x)
+        if use_corr:
+            x = self._update(self.last_sample, self.model_outputs, self.timestep_list, t, self.this_order, x0_t=x0)
+        prev_t = 0 if idx == len(self.timesteps) - 1 else int(self.timesteps[idx + 1])
+        for i in range(self.solver_order - 1):
+            self.model_outputs[i] = self.model_outputs[i + 1]
+            self.timestep_list[i] = self.timestep_list[i + 1]
+        self.model_outputs[-1] = x0
+        self.timestep_list[-1] = t
+        this_order = min(self.solver_order, len(self.timesteps) - idx)  # lower_order_final
+        self.this_order = min(this_order, self.lower_order_nums + 1)
+        self.last_sample = x
+        prev = self._update(x, self.model_outputs, self.timestep_list, prev_t, self.this_order)
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        return prev
+
+
+class DDIM:
+    """DDIMScheduler(eta=0, set_alpha_to_one=False, steps_offset=1) — Appendix A.3 last line."""
+    order = 1
+
+    def __init__(self, num_train=1000, beta_start=0.00085, beta_end=0.012):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.num_train = num_train
+
+    def set_timesteps(self, n):
+        ratio = self.num_train // n
+        self.timesteps = (torch.arange(0, n) * ratio).flip(0).long() + 1
+        self.num_inference_steps = n
+
+    def scale_model_input(self, x, t=None):
+        return x
+
+    def step(self, eps, t, x):
+        t = int(t)
+        prev_t = t - self.num_train // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        x0 = (x - (1 - a_t).sqrt() * eps) / a_t.sqrt()
+        return a_prev.sqrt() * x0 + (1 - a_prev).sqrt() * eps
+
+
+# ---------------------------------------------------------------------------------------------------
+# pipeline/pipeline_bev_controlnet.py:381-504 — the loop body
+# ---------------------------------------------------------------------------------------------------
+def noise_prediction(sd_unet: SD, sd_bg: SD, sd_fg: SD, latents, t, inputs, guidance_scale=2.0, cfg=True):
+    """latents (B, 6, 4, h, w) -> guided noise prediction (B*6, 4, h, w) plus intermediates."""
+    B, n_cam = latents.shape[:2]
+    lat_in = torch.cat([latents] * 2) if cfg else latents                       # :384-386
+    tt = torch.full((lat_in.shape[0],), int(t), dtype=torch.int64)              # :394,403
+    if cfg:
+        cam_bg, box_bg = add_uncond(sd_bg, inputs["camera_param"], inputs["boxes_bg"])
+        _, box_fg = add_uncond(sd_fg, inputs["camera_param"], inputs["boxes_fg"])
+        # NOTE pipeline:349-375 builds the uncond camera from controlnet.nets[0]... the same tensor feeds both nets
+        cam = cam_bg
+        cond_bg = torch.cat([inputs["cond_bg"]] * 2)
+        cond_fg = torch.cat([inputs["cond_fg"]] * 2)
+        text = inputs["prompt_embeds"]                                          # (2B, 77, 768), uncond first
+    else:
+        cam, box_bg, box_fg = inputs["camera_param"], inputs["boxes_bg"], inputs["boxes_fg"]
+        cond_bg, cond_fg = inputs["cond_bg"], inputs["cond_fg"]
+        text = inputs["prompt_embeds"][B:] if inputs["prompt_embeds"].shape[0] == 2 * B else inputs["prompt_embeds"]
+    d0, m0, enc = controlnet_forward(sd_bg, lat_in, tt, cam, box_bg, text, cond_bg, use_occ_3d=False)   # :405-420
+    d1, m1, _ = controlnet_forward(sd_fg, lat_in, tt, cam, box_fg, text, cond_fg, use_occ_3d=True)
+    down = [a + b for a, b in zip(d0, d1)]                                      # :422-429
+    mid = m0 + m1
+    x = lat_in.reshape(-1, *lat_in.shape[2:])                                   # :470-472
+    eps = unet_forward(sd_unet, x, int(t), enc, down, mid)                      # :476-484 (tokens from branch 0)
+    out = {"eps_raw": eps, "down": down, "mid": mid, "enc": enc}
+    if cfg:
+        e_u, e_c = eps.chunk(2)
+        eps = e_u + guidance_scale * (e_c - e_u)                                # :487-492
+    out["eps"] = eps
+    return out
+
+
+def denoise_step(sd_unet, sd_bg, sd_fg, scheduler, latents, t, inputs, guidance_scale=2.0, cfg=True):
+    out = noise_prediction(sd_unet, sd_bg, sd_fg, latents, t, inputs, guidance_scale, cfg)
+    B, n_cam = latents.shape[:2]
+    flat = latents.reshape(B * n_cam, *latents.shape[2:])
+    prev = scheduler.step(out["eps"], t, flat)                                  # :497-499
+    return prev.reshape(B, n_cam, *prev.shape[1:]), out                         # :504

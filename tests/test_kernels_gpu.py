@@ -1,0 +1,221 @@
+"""Parity of the non-GEMM CUDA kernels against torch fp32 references on the same bf16-rounded inputs (GPU).
+Tolerances (bf16 outputs): max-abs <= 2e-2 * max|ref| unless stated."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(out, ref):
+    return ((out.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6)).item()
+
+
+def _mk(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _heads_pad(x, heads, d, dp):
+    """[rows, heads*d] -> [rows, heads*dp] zero padded per head"""
+    r = x.shape[0]
+    out = x.new_zeros((r, heads, dp))
+    out[:, :, :d] = x.reshape(r, heads, d)
+    return out.reshape(r, heads * dp)
+
+
+def _ref_attn(q, k, v, n, lq, lk, heads, d):
+    qh = q.float().reshape(n, lq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(-1, lk, heads, d).transpose(1, 2)
+    vh = v.float().reshape(-1, lk, heads, d).transpose(1, 2)
+    return qh, kh, vh
+
+
+@pytest.mark.parametrize("d,L,n", [(40, 1400, 2), (40, 200, 3), (80, 350, 2), (160, 91, 3), (160, 28, 2), (80, 1400, 1)])
+def test_self_attention_fused_qkv(d, L, n):
+    from dualdiff_b200 import ops
+    heads, C = 8, 8 * d
+    q = _mk((n * L, C), 1); k = _mk((n * L, C), 2); v = _mk((n * L, C), 3)
+    dp = 48 if d == 40 else d
+    fused = torch.cat([_heads_pad(q, heads, d, dp), _heads_pad(k, heads, d, dp), v], dim=1).contiguous()
+    out = ops.attention(fused, fused, fused, n_img=n, lq=L, lk=L, heads=heads, head_dim=d,
+                        q_col0=0, k_col0=heads * dp, v_col0=2 * heads * dp)
+    qh, kh, vh = _ref_attn(q, k, v, n, L, L, heads, d)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(n * L, C)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("d,L,lk", [(40, 1400, 106), (80, 350, 110), (160, 91, 78), (40, 1400, 77)])
+def test_cross_attention_text(d, L, lk):
+    from dualdiff_b200 import ops
+    n, heads, C = 2, 8, 8 * d
+    q = _mk((n * L, C), 1); k = _mk((n * lk, C), 2); v = _mk((n * lk, C), 3)
+    dp = 48 if d == 40 else d
+    kv = torch.cat([_heads_pad(k, heads, d, dp), v], dim=1).contiguous()
+    out = ops.attention(_heads_pad(q, heads, d, dp), kv, kv, n_img=n, lq=L, lk=lk, heads=heads, head_dim=d,
+                        k_col0=0, v_col0=heads * dp)
+    qh, kh, vh = _ref_attn(q, k, v, n, L, lk, heads, d)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(n * L, C)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("d,L", [(40, 1400), (80, 350), (160, 91)])
+def test_cross_view_attention_two_neighbours(d, L):
+    """networks/blocks.py:190-217 with neighboring_attn_type='add': out_v = A(q_v, kv_left) + A(q_v, kv_right)"""
+    from dualdiff_b200 import ops
+    B, n_cam, heads, C = 2, 6, 8, 8 * d
+    n = B * n_cam
+    nb = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}
+    q = _mk((n * L, C), 1); k = _mk((n * L, C), 2); v = _mk((n * L, C), 3)
+    dp = 48 if d == 40 else d
+    fused = torch.cat([_heads_pad(q, heads, d, dp), _heads_pad(k, heads, d, dp), v], dim=1).contiguous()
+    kv_map = torch.tensor([[b * n_cam + j for j in nb[c]] for b in range(B) for c in range(n_cam)],
+                          dtype=torch.int32).cuda()
+    out = ops.attention(fused, fused, fused, n_img=n, lq=L, lk=L, heads=heads, head_dim=d, q_col0=0,
+                        k_col0=heads * dp, v_col0=2 * heads * dp, kv_map=kv_map, n_src=2)
+    qh, kh, vh = _ref_attn(q, k, v, n, L, L, heads, d)
+    ref = torch.zeros_like(qh)
+    for s in range(2):
+        idx = kv_map[:, s].long()
+        ref += F.scaled_dot_product_attention(qh, kh[idx], vh[idx])
+    ref = ref.transpose(1, 2).reshape(n * L, C)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("n,H,W,c1,c2,padded,silu,eps", [
+    (3, 28, 50, 320, 0, True, True, 1e-5), (2, 14, 25, 640, 0, False, False, 1e-6), (2, 7, 13, 1280, 1280, True, True, 1e-5),
+    (2, 14, 25, 1280, 640, True, True, 1e-5), (2, 28, 50, 640, 320, True, True, 1e-5), (2, 4, 7, 1280, 0, True, True, 1e-5)])
+def test_groupnorm_silu(n, H, W, c1, c2, padded, silu, eps):
+    from dualdiff_b200 import ops, packing
+    x1 = _mk((n * H * W, c1), 1) * 2 + 0.5
+    x2 = _mk((n * H * W, c2), 2) if c2 else None
+    C = c1 + c2
+    gamma = (1 + 0.1 * torch.randn(C, generator=torch.Generator().manual_seed(3))).cuda()
+    beta = (0.1 * torch.randn(C, generator=torch.Generator().manual_seed(4))).cuda()
+    out = ops.groupnorm(x1, gamma, beta, n_img=n, hw=(H, W), x2=x2, eps=eps, silu=silu, padded_out=padded)
+    x = torch.cat([x1, x2], 1) if c2 else x1
+    ref = F.group_norm(x.float().reshape(n, H, W, C).permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    ref = packing.to_padded(ref) if padded else ref.reshape(n * H * W, C)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    if padded:  # halo must be exactly zero
+        o = out.reshape(n, H + 1, W + 1, C)
+        assert o[:, H].abs().max() == 0 and o[:, :, W].abs().max() == 0
+
+
+@pytest.mark.parametrize("rows,C", [(1400, 320), (701, 640), (91, 1280), (5, 1280)])
+def test_layernorm(rows, C):
+    from dualdiff_b200 import ops
+    x = _mk((rows, C), 1) * 3 + 1
+    gamma = (1 + 0.1 * torch.randn(C, generator=torch.Generator().manual_seed(3))).cuda()
+    beta = (0.1 * torch.randn(C, generator=torch.Generator().manual_seed(4))).cuda()
+    out = ops.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert _rel(out, ref) < 1e-2
+
+
+def test_downsample_conv_via_im2col():
+    from dualdiff_b200 import ops, packing
+    n, H, W, ci, co = 2, 28, 50, 320, 320
+    x = _mk((n, H, W, ci), 1); w = _mk((co, ci, 3, 3), 2, (9 * ci) ** -0.5)
+    cols, (ho, wo) = ops.im2col_s2(x.reshape(n * H * W, ci), n_img=n, hw=(H, W))
+    out = ops.gemm(cols, packing.pack_conv3x3(w))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1)
+    assert ref.shape[-2:] == (ho, wo)
+    assert _rel(out, ref.permute(0, 2, 3, 1).reshape(n * ho * wo, co)) < 1e-2
+    # odd sizes: 7x13 -> 4x7
+    x = _mk((n, 7, 13, 64), 3); w = _mk((64, 64, 3, 3), 4, 0.05)
+    cols, (ho, wo) = ops.im2col_s2(x.reshape(n * 91, 64), n_img=n, hw=(7, 13))
+    out = ops.gemm(cols, packing.pack_conv3x3(w))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1)
+    assert (ho, wo) == (4, 7) and _rel(out, ref.permute(0, 2, 3, 1).reshape(n * 28, 64)) < 1e-2
+
+
+@pytest.mark.parametrize("hw,hw2", [((4, 7), (7, 13)), ((7, 13), (14, 25)), ((14, 25), (28, 50)), ((8, 8), (16, 16))])
+def test_upsample_nearest_to_size(hw, hw2):
+    from dualdiff_b200 import ops, packing
+    n, C = 2, 64
+    x = _mk((n, hw[0], hw[1], C), 1)
+    out = ops.upsample_pad(x.reshape(-1, C), n_img=n, hw=hw, hw2=hw2)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=hw2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), packing.to_padded(ref))
+
+
+def test_latent_conv_in():
+    """conv_in 4->320 on fp32 NCHW latents with CFG duplication (stride_outer = 0)"""
+    from dualdiff_b200 import ops, packing
+    n, H, W = 6, 28, 50
+    lat = torch.randn(n, 4, H, W, generator=torch.Generator().manual_seed(1)).cuda()
+    w = _mk((320, 4, 3, 3), 2, 1 / 6.0)
+    wp = torch.zeros(320, 8, 3, 3, dtype=torch.bfloat16, device="cuda"); wp[:, :4] = w
+    pad = ops.nchw_to_padded(lat, n_outer=2, n_view=n, c=4, h=H, w=W, cp=8, stride_outer=0,
+                             stride_view=4 * H * W, stride_c=H * W, stride_h=W)
+    out = ops.gemm(pad, packing.pack_conv3x3(wp), taps=9, conv_hw=(H, W), n_img=2 * n)
+    ref = F.conv2d(torch.cat([lat, lat]).to(torch.bfloat16).float(), w.float(), None, padding=1)
+    assert _rel(out, ref.permute(0, 2, 3, 1).reshape(-1, 320)) < 1e-2
+
+
+def test_small_fp32_pieces():
+    from dualdiff_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(12, 189, generator=g).cuda(); w = torch.randn(768, 189, generator=g).cuda() * 0.05
+    b = torch.randn(768, generator=g).cuda()
+    assert _rel(ops.linear_f32(x, w, b, act=1), F.silu(x @ w.t() + b)) < 1e-5
+    t = torch.tensor([801.0, 0.0, 999.0, 40.0]).cuda()
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).cuda()
+    ref = torch.cat([torch.cos(t[:, None] * f), torch.sin(t[:, None] * f)], -1)
+    assert (ops.timestep_embedding(t, 320) - ref).abs().max() < 2e-4
+    cam = torch.tensor([[1266.4, 0.0, 816.3], [0.3, -2.0, 491.0], [1e-3, 7.5, 1.0]]).cuda()
+    ref = torch.cat([cam] + [fn(cam * 2.0 ** k) for k in range(4) for fn in (torch.sin, torch.cos)], -1)
+    assert (ops.fourier_embed(cam.contiguous()) - ref).abs().max() < 1e-4
+    v = torch.randn(1000, generator=g).cuda() * 3
+    assert _rel(ops.silu_to_bf16(v), F.silu(v)) < 1e-2
+    a_ = _mk((64, 320), 1); b_ = _mk((64, 320), 2); c_ = _mk((64, 320), 3)
+    assert _rel(ops.add_bf16(a_, b_, c_), a_.float() + b_.float() + c_.float()) < 1e-2
+
+
+def test_box_features():
+    from dualdiff_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n, P = 37, 8
+    boxes = (torch.rand(n, P, 3, generator=g) * 100 - 50).cuda()
+    classes = torch.randint(0, 10, (n,), generator=g).cuda()
+    masks = (torch.rand(n, generator=g) < 0.6).cuda()
+    tokens = torch.randn(10, 768, generator=g).cuda()
+    null_pos = torch.randn(27 * P, generator=g).cuda(); null_cls = torch.randn(768, generator=g).cuda()
+    pos = torch.empty(n, 27 * P, device="cuda"); cls = torch.empty(n, 768, device="cuda")
+    ops.box_features(boxes, classes, masks, tokens, null_pos, null_cls, pos, cls)
+    m = masks.float()[:, None]
+    emb = torch.cat([boxes] + [fn(boxes * 2.0 ** k) for k in range(4) for fn in (torch.sin, torch.cos)], -1).reshape(n, -1)
+    assert (pos - (emb * m + null_pos * (1 - m))).abs().max() < 1e-4
+    assert (cls - (tokens[classes] * m + null_cls * (1 - m))).abs().max() < 1e-6
+
+
+def test_layout_roundtrip_and_cfg_sched():
+    from dualdiff_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n, c, H, W = 6, 4, 28, 50
+    x = torch.randn(n, c, H, W, generator=g).cuda()
+    rows = ops.nchw_to_rows(x)
+    assert torch.equal(rows.float().reshape(n, H, W, c).permute(0, 3, 1, 2), x.to(torch.bfloat16).float())
+    back = ops.rows_to_nchw(rows, n, (H, W))
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+    # cfg + linear-combination scheduler update
+    eps = torch.randn(2 * n * H * W, c, generator=g).cuda()
+    lat = torch.randn(n, c, H, W, generator=g).cuda(); last = torch.randn(n, c, H, W, generator=g).cuda()
+    m0 = torch.randn(n, c, H, W, generator=g).cuda(); m1 = torch.randn(n, c, H, W, generator=g).cuda()
+    coef = torch.tensor([2.0, 0.7, 1.3, 0.11, -0.2, 0.05, 0.3, 0.6, 0.9, -0.4, 0.25, 0, 0, 0, 0, 0]).cuda()
+    e = eps.reshape(2, n, H, W, c).permute(0, 1, 4, 2, 3)
+    eg = e[0] + 2.0 * (e[1] - e[0])
+    x0 = (lat - 0.7 * eg) * 1.3
+    xc = 0.6 * lat + 0.11 * last - 0.2 * m0 + 0.05 * m1 + 0.3 * x0
+    xn = 0.9 * xc - 0.4 * x0 + 0.25 * m0
+    m0_old = m0.clone()
+    ops.cfg_sched_step(eps, lat, last, m0, m1, coef, n_img=n, c=c, hw=H * W, cfg=True)
+    assert (lat - xn).abs().max() < 1e-5 and (last - xc).abs().max() < 1e-5
+    assert (m0 - x0).abs().max() < 1e-5 and torch.equal(m1, m0_old)
