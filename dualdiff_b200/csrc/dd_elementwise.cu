@@ -287,7 +287,7 @@ __global__ void rows_to_nchw_kernel(const TI* __restrict__ rows, long long ld, T
 // ---------------------------------------------------------------------------------------------------
 __global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restrict__ x, float* __restrict__ last,
                                  float* __restrict__ m0, float* __restrict__ m1, const float* __restrict__ coef,
-                                 int n_img, int C, int HW, int cfg) {
+                                 int n_img, int C, int HW, int cfg, int eps_nchw) {
   const float g = coef[0], sigma = coef[1], inv_alpha = coef[2];
   const float a_last = coef[3], a_m0 = coef[4], a_m1 = coef[5], a_x0 = coef[6], a_x = coef[7];
   const float b_xc = coef[8], b_x0 = coef[9], b_m0 = coef[10];
@@ -297,7 +297,7 @@ __global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restric
     const long long t = i / HW;
     const int c = (int)(t % C);
     const int img = (int)(t / C);
-    const long long ei = ((long long)img * HW + p) * C + c;
+    const long long ei = eps_nchw ? i : ((long long)img * HW + p) * C + c;
     float e = eps[ei];
     if (cfg) {
       const float ec = eps[ei + (long long)n_img * HW * C];
@@ -403,10 +403,10 @@ int dd_rows_to_nchw(const void* rows, int rows_f32, long long ld, void* out, int
   return 0;
 }
 int dd_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef, int n_img,
-                      int c, int hw, int cfg, void* stream) {
+                      int c, int hw, int cfg, int eps_nchw, void* stream) {
   if (n_img <= 0 || c <= 0 || hw <= 0) { set_error("dd_cfg_sched_step: bad shape"); return -1; }
   const long long total = (long long)n_img * c * hw;
-  cfg_sched_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(eps, x, last, m0, m1, coef, n_img, c, hw, cfg);
+  cfg_sched_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(eps, x, last, m0, m1, coef, n_img, c, hw, cfg, eps_nchw);
   if (cudaGetLastError() != cudaSuccess) { set_error("dd_cfg_sched_step launch failed"); return -2; }
   count_launch();
   return 0;

@@ -47,6 +47,7 @@ struct GemmDev {
   const bf16* res2;
   long long res2_ld;
   int geglu;
+  int act;      // 0 none, 1 SiLU (applied last)
   int n_store;  // number of valid output columns (N, or N/2 for GEGLU)
 };
 
@@ -258,6 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
                   t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
                 }
+                if (p.act == 1) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+                }
                 if (p.out_f32) {
                   float* o = reinterpret_cast<float*>(p.out) + orow * p.out_ld + nb + j;
                   *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -276,6 +281,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (rv) v += rv[nb + j];
                 if (p.res1) v += __bfloat162float(p.res1[orow * p.res1_ld + nb + j]);
                 if (p.res2) v += __bfloat162float(p.res2[orow * p.res2_ld + nb + j]);
+                if (p.act == 1) v = silu_f(v);
                 if (p.out_f32)
                   reinterpret_cast<float*>(p.out)[orow * p.out_ld + nb + j] = v;
                 else
@@ -393,7 +399,7 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   p.rows_per_img = a->rows_per_img > 0 ? a->rows_per_img : 1;
   p.res1 = reinterpret_cast<const bf16*>(a->res1); p.res1_ld = a->res1_ld;
   p.res2 = reinterpret_cast<const bf16*>(a->res2); p.res2_ld = a->res2_ld;
-  p.geglu = a->geglu; p.n_store = n_store;
+  p.geglu = a->geglu; p.act = a->act; p.n_store = n_store;
   p.m_tiles = p.n_tiles = p.stages = 0;
   switch (bn) {
     case 32: return launch_gemm<32>(tmA, tmA2, tmB, p, stream);

@@ -1,0 +1,509 @@
+"""The CUDA execution engine of the DualDiff denoising step.
+
+`pack_*` turn a diffusers-keyed state dict into kernel-layout buffers once (bf16 GEMM operands, fp32
+biases / norm parameters); `unet_forward` / `controlnet_forward` then run the reference's arithmetic
+(networks/unet_2d_condition_multiview.py:327-527, networks/unet_addon_rawbox.py:794-1082,
+networks/blocks.py:144-238) as a sequence of C-ABI kernel launches on the current stream — no torch math on
+the hot path, no host synchronisation, CUDA-graph capturable.
+
+Activations are bf16 channels-last "compact" rows [n_img*H*W, C]; only the inputs of 3x3 convolutions take
+the zero-haloed padded-pixel layout (written directly by the GroupNorm+SiLU kernel).
+
+Algebraic fusions (exact in real arithmetic; the oracle checks them):
+  * cross-view attention: Q/K/V projected once per view (the reference projects every view twice, once per
+    (view, neighbour) pair) and  connector(W_o(A_l + A_r) + 2 b_o) = (W_c W_o)(A_l + A_r) + (2 W_c b_o + b_c)
+    is ONE GEMM with pre-multiplied weights (blocks.py:203-222);
+  * timestep-invariant work is hoisted into `prepare_*`: text/box/camera tokens, the K/V projections of every
+    text cross-attention, the condition embedding and Semantic Fusion Attention.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .packing import pack_conv1x1, pack_conv3x3, pack_geglu, pack_linear
+
+HEADS = 8
+NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  # configs/dataset/Nuscenes.yaml:27-33
+BF = torch.bfloat16
+
+
+def _dp(d):
+    """Q/K head stride: head_dim 40 is zero-padded to 48 so the UMMA K extent is a multiple of 16"""
+    return 48 if d == 40 else d
+
+
+def pad_heads(w, d, dp):
+    """[heads*d, in] -> [heads*dp, in] with zero rows appended per head"""
+    if d == dp:
+        return w
+    h = w.shape[0] // d
+    out = w.new_zeros((h, dp, w.shape[1]))
+    out[:, :d] = w.reshape(h, d, w.shape[1])
+    return out.reshape(h * dp, w.shape[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# packing
+# ---------------------------------------------------------------------------------------------------
+class Packer:
+    def __init__(self, sd: Dict[str, torch.Tensor], device):
+        self.sd, self.dev, self.out = sd, device, {}
+
+    def f32(self, t):
+        return t.detach().float().contiguous().to(self.dev)
+
+    def put(self, name, t):
+        self.out[name] = t.to(self.dev) if t.device != self.dev else t
+
+    def conv3(self, p, pad_cin_to=None):
+        w = self.sd[p + ".weight"].detach().float()
+        if pad_cin_to is not None and w.shape[1] < pad_cin_to:
+            wp = w.new_zeros((w.shape[0], pad_cin_to, 3, 3))
+            wp[:, :w.shape[1]] = w
+            w = wp
+        self.put(p + ".w", pack_conv3x3(w))
+        self.put(p + ".b", self.f32(self.sd[p + ".bias"]))
+
+    def conv1(self, p):
+        self.put(p + ".w", pack_conv1x1(self.sd[p + ".weight"].detach().float()))
+        self.put(p + ".b", self.f32(self.sd[p + ".bias"]))
+
+    def lin(self, p, bias=True):
+        self.put(p + ".w", pack_linear(self.sd[p + ".weight"].detach().float()))
+        if bias:
+            self.put(p + ".b", self.f32(self.sd[p + ".bias"]))
+
+    def lin32(self, p):
+        self.put(p + ".w32", self.f32(self.sd[p + ".weight"]))
+        self.put(p + ".b32", self.f32(self.sd[p + ".bias"]))
+
+    def norm(self, p):
+        self.put(p + ".g", self.f32(self.sd[p + ".weight"]))
+        self.put(p + ".b", self.f32(self.sd[p + ".bias"]))
+
+    def resnet(self, p, temb_list):
+        self.norm(p + ".norm1"); self.conv3(p + ".conv1"); self.norm(p + ".norm2"); self.conv3(p + ".conv2")
+        if (p + ".conv_shortcut.weight") in self.sd:
+            self.conv1(p + ".conv_shortcut")
+        temb_list.append(p)
+
+    def attn_self(self, p, d):
+        dp = _dp(d)
+        f = lambda n: self.sd[f"{p}.{n}.weight"].detach().float()
+        w = torch.cat([pad_heads(f("to_q"), d, dp), pad_heads(f("to_k"), d, dp), f("to_v")], 0)
+        self.put(p + ".qkv.w", w.to(BF))
+
+    def tblock(self, p, multiview):
+        c = self.sd[p + ".norm1.weight"].shape[0]
+        d = c // HEADS
+        dp = _dp(d)
+        f = lambda n: self.sd[f"{p}.{n}"].detach().float()
+        for n in ("norm1", "norm2", "norm3"):
+            self.norm(f"{p}.{n}")
+        self.attn_self(p + ".attn1", d)
+        self.lin(p + ".attn1.to_out.0")
+        self.put(p + ".attn2.q.w", pad_heads(f("attn2.to_q.weight"), d, dp).to(BF))
+        self.put(p + ".attn2.kv.w", torch.cat([pad_heads(f("attn2.to_k.weight"), d, dp), f("attn2.to_v.weight")], 0).to(BF))
+        self.lin(p + ".attn2.to_out.0")
+        if multiview:
+            self.norm(p + ".norm4")
+            self.attn_self(p + ".attn4", d)
+            wo, bo = f("attn4.to_out.0.weight").double(), f("attn4.to_out.0.bias").double()
+            wc, bc = f("connector.weight").double(), f("connector.bias").double()
+            self.put(p + ".attn4.oc.w", (wc @ wo).float().to(BF))          # connector o to_out, fused
+            self.put(p + ".attn4.oc.b", self.f32(2.0 * (wc @ bo) + bc))    # bias counted twice (blocks.py:203-217)
+        wg, bg = pack_geglu(f("ff.net.0.proj.weight"), f("ff.net.0.proj.bias"))
+        self.put(p + ".ff.geglu.w", wg); self.put(p + ".ff.geglu.b", bg)
+        self.lin(p + ".ff.net.2")
+
+    def transformer2d(self, p, multiview):
+        self.norm(p + ".norm"); self.conv1(p + ".proj_in"); self.conv1(p + ".proj_out")
+        self.tblock(p + ".transformer_blocks.0", multiview)
+
+    def encoder(self, multiview, temb_list):
+        """conv_in, time embedding, 4 down blocks, mid block — shared by the UNet and the ControlNet branches"""
+        self.conv3("conv_in", pad_cin_to=8)
+        self.lin32("time_embedding.linear_1"); self.lin32("time_embedding.linear_2")
+        for i in range(4):
+            for j in range(2):
+                self.resnet(f"down_blocks.{i}.resnets.{j}", temb_list)
+                if i < 3:
+                    self.transformer2d(f"down_blocks.{i}.attentions.{j}", multiview)
+            if i < 3:
+                self.conv3(f"down_blocks.{i}.downsamplers.0.conv")
+        self.resnet("mid_block.resnets.0", temb_list)
+        self.transformer2d("mid_block.attentions.0", multiview)
+        self.resnet("mid_block.resnets.1", temb_list)
+
+    def temb(self, temb_list):
+        ws = [self.sd[p + ".time_emb_proj.weight"].detach().float() for p in temb_list]
+        bs = [self.sd[p + ".time_emb_proj.bias"].detach().float() for p in temb_list]
+        self.put("temb_all.w", torch.cat(ws, 0).to(BF))
+        self.put("temb_all.b", self.f32(torch.cat(bs, 0)))
+        off, offs = 0, {}
+        for p, w in zip(temb_list, ws):
+            offs[p] = (off, w.shape[0])
+            off += w.shape[0]
+        self.out["temb_offsets"] = offs
+        self.out["temb_total"] = off
+
+
+def pack_unet(sd, device):
+    pk = Packer(sd, device)
+    tl: List[str] = []
+    pk.encoder(True, tl)
+    for i in range(4):
+        for j in range(3):
+            pk.resnet(f"up_blocks.{i}.resnets.{j}", tl)
+            if i > 0:
+                pk.transformer2d(f"up_blocks.{i}.attentions.{j}", True)
+        if i < 3:
+            pk.conv3(f"up_blocks.{i}.upsamplers.0.conv")
+    pk.norm("conv_norm_out")
+    pk.conv3("conv_out")
+    pk.temb(tl)
+    return pk.out
+
+
+def pack_controlnet(sd, device, use_occ_3d: bool):
+    pk = Packer(sd, device)
+    tl: List[str] = []
+    pk.encoder(False, tl)
+    pk.temb(tl)
+    for i in range(12):
+        pk.conv1(f"controlnet_down_blocks.{i}")
+    pk.conv1("controlnet_mid_block")
+    # embedders (fp32: camera intrinsics ~1e3 go through sin/cos(x * 2^k), SURVEY hard part 4)
+    pk.lin32("cam2token")
+    pk.put("uncond_cam", pk.f32(sd["uncond_cam.weight"]))
+    for n in ("bbox_proj", "second_linear.0", "second_linear.2", "second_linear.4"):
+        pk.lin32("bbox_embedder." + n)
+    for n in ("_class_tokens", "null_class_feature", "null_pos_feature"):
+        pk.put("bbox_embedder." + n, pk.f32(sd["bbox_embedder." + n]))
+    # Semantic Fusion Attention (txt_con_fusion.py:27-33): 8 heads x 40
+    p = "txt_con_fusion"
+    f = lambda n: sd[f"{p}.{n}.weight"].detach().float()
+    pk.put(p + ".q.w", pad_heads(f("to_q"), 40, 48).to(BF))
+    pk.put(p + ".kv.w", torch.cat([pad_heads(f("to_k"), 40, 48), f("to_v")], 0).to(BF))
+    pk.lin(p + ".to_out.0")
+    if not use_occ_3d:
+        e = "controlnet_cond_embedding"
+        pk.conv3(e + ".conv_in", pad_cin_to=8)
+        for i in range(6):
+            pk.conv3(f"{e}.blocks.{i}")
+        pk.conv3(e + ".conv_out")
+    pk.out["use_occ_3d"] = use_occ_3d
+    return pk.out
+
+
+# ---------------------------------------------------------------------------------------------------
+# forward building blocks
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class Act:
+    """compact channels-last activation: rows [n*H*W, C] bf16"""
+    rows: torch.Tensor
+    n: int
+    H: int
+    W: int
+
+    @property
+    def hw(self):
+        return (self.H, self.W)
+
+    @property
+    def C(self):
+        return self.rows.shape[1]
+
+
+@dataclass
+class StepCtx:
+    n: int
+    temb: torch.Tensor            # fp32 [m, temb_total]
+    temb_rows_per_img_factor: int  # n // m
+    text_kv: Dict[str, torch.Tensor] = field(default_factory=dict)   # attn2 prefix -> [n*Lk, 8*dp + C]
+    lk: int = 0
+    kv_map: Optional[torch.Tensor] = None
+
+
+def time_embedding(P, t: torch.Tensor):
+    """t fp32 [m] -> per-resnet projections fp32 [m, temb_total]  (unet_2d_condition_multiview.py:386-411 +
+    every ResnetBlock2D.time_emb_proj(SiLU(emb)), batched into one tensor-core GEMM)"""
+    c0 = P["time_embedding.linear_1.w32"].shape[1]
+    s = ops.timestep_embedding(t, c0)
+    h = ops.linear_f32(s, P["time_embedding.linear_1.w32"], P["time_embedding.linear_1.b32"], act=1)
+    e16 = torch.empty((t.shape[0], P["time_embedding.linear_2.w32"].shape[0]), device=t.device, dtype=BF)
+    ops.linear_f32(h, P["time_embedding.linear_2.w32"], P["time_embedding.linear_2.b32"], act=1, out16=e16,
+                   want_f32=False)  # act=1: the SiLU every resnet applies to emb before its projection
+    return ops.gemm(e16, P["temb_all.w"], bias=P["temb_all.b"], out_f32=True)
+
+
+def resnet(P, p, x: Act, ctx: StepCtx, x2: Optional[torch.Tensor] = None) -> Act:
+    n, hw = x.n, x.hw
+    g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True,
+                       padded_out=True)
+    off, cout = P["temb_offsets"][p]
+    h = ops.gemm(g1, P[p + ".conv1.w"], bias=P[p + ".conv1.b"], taps=9, conv_hw=hw, n_img=n,
+                 rowvec=ctx.temb[:, off:off + cout], rows_per_img=ctx.temb_rows_per_img_factor * hw[0] * hw[1])
+    g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True, padded_out=True)
+    if (p + ".conv_shortcut.w") in P:
+        sc = ops.gemm(x.rows, P[p + ".conv_shortcut.w"], bias=P[p + ".conv_shortcut.b"], a2=x2)
+    else:
+        assert x2 is None
+        sc = x.rows
+    out = ops.gemm(g2, P[p + ".conv2.w"], bias=P[p + ".conv2.b"], taps=9, conv_hw=hw, n_img=n, res1=sc)
+    return Act(out, n, x.H, x.W)
+
+
+def text_kv(P, p_attn2, enc_rows):
+    """K/V projection of the text/camera/box tokens for one attn2 layer (timestep-invariant)"""
+    return ops.gemm(enc_rows, P[p_attn2 + ".kv.w"])
+
+
+def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool):
+    C = h.shape[1]
+    d = C // HEADS
+    dp = _dp(d)
+    # 1. self-attention (blocks.py:163-172)
+    ln = ops.layernorm(h, P[p + ".norm1.g"], P[p + ".norm1.b"])
+    qkv = ops.gemm(ln, P[p + ".attn1.qkv.w"])
+    a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0, k_col0=HEADS * dp,
+                      v_col0=2 * HEADS * dp)
+    h = ops.gemm(a, P[p + ".attn1.to_out.0.w"], bias=P[p + ".attn1.to_out.0.b"], res1=h)
+    # 2. text cross-attention (blocks.py:175-188); K/V come from the per-sample cache
+    ln = ops.layernorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"])
+    q = ops.gemm(ln, P[p + ".attn2.q.w"])
+    kv = ctx.text_kv[p + ".attn2"]
+    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=ctx.lk, heads=HEADS, head_dim=d, k_col0=0, v_col0=HEADS * dp)
+    h = ops.gemm(a, P[p + ".attn2.to_out.0.w"], bias=P[p + ".attn2.to_out.0.b"], res1=h)
+    # 3. cross-view attention over the two ring neighbours (blocks.py:190-222)
+    if multiview:
+        ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
+        qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
+        a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
+                          k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
+        h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
+    # 4. GEGLU feed-forward (blocks.py:225-236)
+    ln = ops.layernorm(h, P[p + ".norm3.g"], P[p + ".norm3.b"])
+    ff = ops.gemm(ln, P[p + ".ff.geglu.w"], bias=P[p + ".ff.geglu.b"], geglu=True)
+    return ops.gemm(ff, P[p + ".ff.net.2.w"], bias=P[p + ".ff.net.2.b"], res1=h)
+
+
+def transformer_2d(P, p, x: Act, ctx: StepCtx, multiview: bool) -> Act:
+    n, hw = x.n, x.hw
+    g = ops.groupnorm(x.rows, P[p + ".norm.g"], P[p + ".norm.b"], n_img=n, hw=hw, eps=1e-6, silu=False)
+    h = ops.gemm(g, P[p + ".proj_in.w"], bias=P[p + ".proj_in.b"])
+    h = transformer_block(P, p + ".transformer_blocks.0", h, n, hw[0] * hw[1], ctx, multiview)
+    out = ops.gemm(h, P[p + ".proj_out.w"], bias=P[p + ".proj_out.b"], res1=x.rows)
+    return Act(out, n, x.H, x.W)
+
+
+def downsample(P, p, x: Act) -> Act:
+    cols, (ho, wo) = ops.im2col_s2(x.rows, n_img=x.n, hw=x.hw)
+    return Act(ops.gemm(cols, P[p + ".w"], bias=P[p + ".b"]), x.n, ho, wo)
+
+
+def upsample(P, p, x: Act, hw2) -> Act:
+    pad = ops.upsample_pad(x.rows, n_img=x.n, hw=x.hw, hw2=hw2)
+    return Act(ops.gemm(pad, P[p + ".w"], bias=P[p + ".b"], taps=9, conv_hw=hw2, n_img=x.n), x.n, hw2[0], hw2[1])
+
+
+def conv_in(P, latents, n_outer, n_view, H, W, res1=None) -> Act:
+    """latents: fp32/bf16 NCHW storage of n_view images, logically repeated n_outer times (CFG halves)"""
+    assert latents.is_contiguous()
+    pad = ops.nchw_to_padded(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=8,
+                             stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
+                             stride_view=4 * H * W, stride_c=H * W, stride_h=W)
+    n = n_outer * n_view
+    return Act(ops.gemm(pad, P["conv_in.w"], bias=P["conv_in.b"], taps=9, conv_hw=(H, W), n_img=n, res1=res1), n, H, W)
+
+
+def down_path(P, x: Act, ctx: StepCtx, multiview: bool):
+    skips = [x]
+    for i in range(4):
+        for j in range(2):
+            x = resnet(P, f"down_blocks.{i}.resnets.{j}", x, ctx)
+            if i < 3:
+                x = transformer_2d(P, f"down_blocks.{i}.attentions.{j}", x, ctx, multiview)
+            skips.append(x)
+        if i < 3:
+            x = downsample(P, f"down_blocks.{i}.downsamplers.0.conv", x)
+            skips.append(x)
+    return x, skips
+
+
+def mid_block(P, x: Act, ctx: StepCtx, multiview: bool) -> Act:
+    x = resnet(P, "mid_block.resnets.0", x, ctx)
+    x = transformer_2d(P, "mid_block.attentions.0", x, ctx, multiview)
+    return resnet(P, "mid_block.resnets.1", x, ctx)
+
+
+ATTN2_LAYERS_ENC = [f"down_blocks.{i}.attentions.{j}.transformer_blocks.0.attn2" for i in range(3) for j in range(2)] + \
+    ["mid_block.attentions.0.transformer_blocks.0.attn2"]
+ATTN2_LAYERS_UNET = ATTN2_LAYERS_ENC + [f"up_blocks.{i}.attentions.{j}.transformer_blocks.0.attn2"
+                                        for i in range(1, 4) for j in range(3)]
+
+
+def make_kv_map(n, n_cam, device):
+    """kv image of (query image, neighbour slot); view index = image index mod n_cam (blocks.py:196-197)"""
+    assert n % n_cam == 0 and n_cam == len(NEIGHBORS)
+    rows = [[(i // n_cam) * n_cam + nb for nb in NEIGHBORS[i % n_cam]] for i in range(n)]
+    return torch.tensor(rows, dtype=torch.int32, device=device)
+
+
+def prepare_text(P, layers, enc_rows):
+    return {l: text_kv(P, l, enc_rows) for l in layers}
+
+
+# ---------------------------------------------------------------------------------------------------
+# UNet2DConditionModelMultiview.forward
+# ---------------------------------------------------------------------------------------------------
+def unet_forward(P, latents, n_outer, n_view, H, W, ctx: StepCtx, down_res: Optional[List[torch.Tensor]] = None,
+                 mid_res: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """returns eps as fp32 channels-last rows [n*H*W, 4]"""
+    x = conv_in(P, latents, n_outer, n_view, H, W)
+    x, skips = down_path(P, x, ctx, True)
+    if down_res is not None:  # unet_2d_condition_multiview.py:464-473
+        skips = [Act(ops.add_bf16(s.rows, r), s.n, s.H, s.W) for s, r in zip(skips, down_res)]
+    x = mid_block(P, x, ctx, True)
+    if mid_res is not None:
+        x = Act(ops.add_bf16(x.rows, mid_res), x.n, x.H, x.W)
+    for i in range(4):
+        for j in range(3):
+            s = skips.pop()
+            x = resnet(P, f"up_blocks.{i}.resnets.{j}", x, ctx, x2=s.rows)
+            if i > 0:
+                x = transformer_2d(P, f"up_blocks.{i}.attentions.{j}", x, ctx, True)
+        if i < 3:
+            x = upsample(P, f"up_blocks.{i}.upsamplers.0.conv", x, skips[-1].hw)
+    g = ops.groupnorm(x.rows, P["conv_norm_out.g"], P["conv_norm_out.b"], n_img=x.n, hw=x.hw, eps=1e-5, silu=True,
+                      padded_out=True)
+    return ops.gemm(g, P["conv_out.w"], bias=P["conv_out.b"], taps=9, conv_hw=x.hw, n_img=x.n, out_f32=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# BEVControlNetModel: hoisted (timestep-invariant) part and per-step part
+# ---------------------------------------------------------------------------------------------------
+def camera_tokens(P, camera_param):
+    """(b, n_cam, 3, 7) fp32 -> (b*n_cam, 768) fp32   (unet_addon_rawbox.py:308-325,346-349)"""
+    b, n_cam = camera_param.shape[:2]
+    cols = camera_param.permute(0, 1, 3, 2).contiguous().float()      # (b, n, 7, 3): plumbing
+    e = ops.fourier_embed(cols.reshape(-1, 3)).reshape(b * n_cam, -1)  # (b n) x (c d) = 189
+    return ops.linear_f32(e, P["cam2token.w32"], P["cam2token.b32"])
+
+
+def box_tokens(P, bboxes, classes, masks):
+    """bboxes (R, L, 8, 3), classes (R, L), masks (R, L) -> (R*L, 768) fp32   (bbox_embedder.py:155-203)"""
+    R, L = classes.shape
+    nb = R * L
+    dev = bboxes.device
+    pos = torch.empty((nb, 216), device=dev, dtype=torch.float32)
+    cat = torch.empty((nb, 768 + 768), device=dev, dtype=torch.float32)
+    ops.box_features(bboxes.reshape(nb, 8, 3).float().contiguous(), classes.reshape(-1).contiguous(),
+                     masks.reshape(-1), P["bbox_embedder._class_tokens"], P["bbox_embedder.null_pos_feature"],
+                     P["bbox_embedder.null_class_feature"], pos, cat[:, 768:])
+    ops.linear_f32(pos, P["bbox_embedder.bbox_proj.w32"], P["bbox_embedder.bbox_proj.b32"], act=1, out=cat[:, :768])
+    h = ops.linear_f32(cat, P["bbox_embedder.second_linear.0.w32"], P["bbox_embedder.second_linear.0.b32"], act=1)
+    h = ops.linear_f32(h, P["bbox_embedder.second_linear.2.w32"], P["bbox_embedder.second_linear.2.b32"], act=1)
+    return ops.linear_f32(h, P["bbox_embedder.second_linear.4.w32"], P["bbox_embedder.second_linear.4.b32"])
+
+
+def build_tokens(P, camera_param, text, bboxes_3d_data):
+    """encoder_hidden_states_with_cam ++ box tokens: (b*n_cam, 1 + 77 + L, 768) bf16 (unet_addon_rawbox.py:832-896,
+    1007,1066-1069).  Concats/expands here are pure data movement (torch), the arithmetic is in the kernels."""
+    b, n_cam = camera_param.shape[:2]
+    cam = camera_tokens(P, camera_param).reshape(b, n_cam, 1, 768)
+    txt = text.float()[:, None].expand(b, n_cam, text.shape[1], 768)
+    bb, cl, mk = bboxes_3d_data["bboxes"], bboxes_3d_data["classes"], bboxes_3d_data["masks"]
+    n_box, L = bb.shape[1], bb.shape[2]
+    tok = box_tokens(P, bb.reshape(b * n_box, L, 8, 3), cl.reshape(b * n_box, L), mk.reshape(b * n_box, L))
+    tok = tok.reshape(b, n_box, L, 768)
+    if n_box != n_cam:
+        tok = tok.expand(b, n_cam, L, 768)
+    enc = torch.cat([cam, txt, tok], dim=2)                            # (b, n_cam, 78 + L, 768)
+    return enc.reshape(b * n_cam, 78 + L, 768).to(BF).contiguous()
+
+
+def cond_embedding(P, cond, n_cam=6) -> Act:
+    """ControlNetConditioningEmbedding (map_embedder.py:114-138): (b, 3, Hc, 6*Wc) panorama -> (b*6, 320, Hc/8, Wc/8).
+    Every conv runs on the tcgen05 GEMM (stride-1: padded implicit GEMM; stride-2: im2col), SiLU fused."""
+    e = "controlnet_cond_embedding"
+    b, c, Hc, Wt = cond.shape
+    Wc = Wt // n_cam
+    cond = cond.contiguous()
+    pad = ops.nchw_to_padded(cond, n_outer=b, n_view=n_cam, c=c, h=Hc, w=Wc, cp=8, stride_outer=c * Hc * Wt,
+                             stride_view=Wc, stride_c=Hc * Wt, stride_h=Wt)
+    n = b * n_cam
+    x = Act(ops.gemm(pad, P[e + ".conv_in.w"], bias=P[e + ".conv_in.b"], taps=9, conv_hw=(Hc, Wc), n_img=n, act=1), n, Hc, Wc)
+    for i in range(6):
+        p = f"{e}.blocks.{i}"
+        if i % 2 == 0:
+            pad = ops.pad_rows(x.rows, n_img=n, hw=x.hw)
+            x = Act(ops.gemm(pad, P[p + ".w"], bias=P[p + ".b"], taps=9, conv_hw=x.hw, n_img=n, act=1), n, x.H, x.W)
+        else:
+            cols, (ho, wo) = ops.im2col_s2(x.rows, n_img=n, hw=x.hw)
+            x = Act(ops.gemm(cols, P[p + ".w"], bias=P[p + ".b"], act=1), n, ho, wo)
+    pad = ops.pad_rows(x.rows, n_img=n, hw=x.hw)
+    return Act(ops.gemm(pad, P[e + ".conv_out.w"], bias=P[e + ".conv_out.b"], taps=9, conv_hw=x.hw, n_img=n), n, x.H, x.W)
+
+
+def sfa(P, cond: Act, enc_rows, lk_total, n) -> torch.Tensor:
+    """Semantic Fusion Attention (txt_con_fusion.py:74-181): cond + W_o MHA(W_q cond, W_k txt, W_v txt) + b_o.
+    enc_rows: [n*(78+L), 768]; the 77 text tokens are rows 1..77 of each image (camera token dropped, :977)."""
+    p = "txt_con_fusion"
+    q = ops.gemm(cond.rows, P[p + ".q.w"])
+    kv = ops.gemm(enc_rows, P[p + ".kv.w"])   # projects all tokens; the attention reads rows 1..77 only
+    T = cond.H * cond.W
+    kv3 = kv.reshape(n, lk_total, kv.shape[1])[:, 1:78]
+    # a strided view cannot be addressed as [n*77, ld]; copy the 77-token window (plumbing, timestep-invariant)
+    kv77 = kv3.contiguous().reshape(n * 77, kv.shape[1])
+    a = ops.attention(q, kv77, kv77, n_img=n, lq=T, lk=77, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48)
+    return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond.rows)
+
+
+@dataclass
+class BranchPrep:
+    enc_rows: torch.Tensor      # [n*(78+L), 768] bf16
+    lk: int
+    cond: torch.Tensor          # [n*H*W, 320] bf16 — SFA-fused condition feature, added after conv_in (:990)
+    text_kv: Dict[str, torch.Tensor]
+    n: int
+
+
+def controlnet_prepare(P, camera_param, text, bboxes_3d_data, controlnet_cond, H, W) -> BranchPrep:
+    """everything of BEVControlNetModel.forward that does not depend on the timestep or the latents"""
+    b, n_cam = camera_param.shape[:2]
+    n = b * n_cam
+    enc = build_tokens(P, camera_param, text, bboxes_3d_data)
+    lk = enc.shape[1]
+    enc_rows = enc.reshape(n * lk, 768)
+    if P["use_occ_3d"]:
+        assert controlnet_cond.shape[0] == n and controlnet_cond.shape[1] == 320
+        cond = Act(ops.nchw_to_rows(controlnet_cond.contiguous()), n, H, W)   # ORS tensor (b*6, 320, h, w)
+    else:
+        cond = cond_embedding(P, controlnet_cond, n_cam)
+        assert cond.hw == (H, W), (cond.hw, H, W)
+    fused = sfa(P, cond, enc_rows, lk, n)
+    return BranchPrep(enc_rows, lk, fused, prepare_text(P, ATTN2_LAYERS_ENC, enc_rows), n)
+
+
+def controlnet_forward(P, prep: BranchPrep, latents, n_outer, n_view, H, W, t, acc: Optional[List[torch.Tensor]] = None,
+                       conditioning_scale: float = 1.0):
+    """per-step part of one branch.  acc: residuals of the previous branch to accumulate into (pipeline:422-429).
+    Returns (12 down residual rows, mid residual rows)."""
+    assert conditioning_scale == 1.0, "conditioning_scale != 1 is folded at pack time (not needed by the reference configs)"
+    n = n_outer * n_view
+    temb = time_embedding(P, t)
+    ctx = StepCtx(n=n, temb=temb, temb_rows_per_img_factor=n // temb.shape[0], text_kv=prep.text_kv, lk=prep.lk)
+    x = conv_in(P, latents, n_outer, n_view, H, W, res1=prep.cond)             # :965 + :990
+    x, skips = down_path(P, x, ctx, False)
+    x = mid_block(P, x, ctx, False)
+    down = []
+    for i, s in enumerate(skips):                                              # :1029-1039
+        p = f"controlnet_down_blocks.{i}"
+        down.append(ops.gemm(s.rows, P[p + ".w"], bias=P[p + ".b"], res1=None if acc is None else acc[i]))
+    p = "controlnet_mid_block"
+    mid = ops.gemm(x.rows, P[p + ".w"], bias=P[p + ".b"], res1=None if acc is None else acc[12])
+    return down, mid

@@ -1,0 +1,78 @@
+"""BasicMultiviewTransformerBlock — parameter layout + standalone CUDA forward.
+
+Reference: networks/blocks.py:35-238.  The block adds `norm4`, `attn4` and a zero-initialised `connector`
+to diffusers' BasicTransformerBlock and, between the text cross-attention and the feed-forward, lets every
+camera view attend to its two ring neighbours (`neighboring_attn_type="add"`).
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _tree
+
+
+def _ensure_int_pairs(view_pair):
+    return {int(k): [int(x) for x in v] for k, v in view_pair.items()}
+
+
+class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
+    def __init__(self, dim: int, num_attention_heads: int, attention_head_dim: int, dropout=0.0,
+                 cross_attention_dim: Optional[int] = None, activation_fn: str = "geglu",
+                 num_embeds_ada_norm: Optional[int] = None, attention_bias: bool = False,
+                 only_cross_attention: bool = False, double_self_attention: bool = False,
+                 upcast_attention: bool = False, norm_elementwise_affine: bool = True,
+                 norm_type: str = "layer_norm", final_dropout: bool = False,
+                 neighboring_view_pair: Optional[Dict[int, List[int]]] = None,
+                 neighboring_attn_type: Optional[str] = "add", zero_module_type="zero_linear"):
+        if (activation_fn != "geglu" or num_embeds_ada_norm is not None or attention_bias or only_cross_attention
+                or double_self_attention or norm_type != "layer_norm" or not norm_elementwise_affine):
+            raise NotImplementedError("dualdiff_b200 implements the SDv1.5 block configuration the reference uses")
+        if neighboring_attn_type != "add":
+            raise NotImplementedError(f"neighboring_attn_type={neighboring_attn_type!r}: only 'add' is on the hot path")
+        if zero_module_type != "zero_linear":
+            raise TypeError(f"Unknown zero module type: {zero_module_type}")
+        super().__init__(dim, num_attention_heads, attention_head_dim, cross_attention_dim)
+        self.neighboring_view_pair = _ensure_int_pairs(neighboring_view_pair)
+        self.neighboring_attn_type = neighboring_attn_type
+        self.norm4 = nn.LayerNorm(dim)
+        self.attn4 = _tree.Attention(dim, dim, num_attention_heads, attention_head_dim)
+        self.connector = nn.Linear(dim, dim)
+        nn.init.zeros_(self.connector.weight)  # zero_module (blocks.py:83)
+        nn.init.zeros_(self.connector.bias)
+        self._packed = None
+
+    @property
+    def new_module(self):
+        return {"norm4": self.norm4, "attn4": self.attn4, "connector": self.connector}
+
+    @property
+    def n_cam(self):
+        return len(self.neighboring_view_pair)
+
+    def pack(self):
+        from .. import engine
+        pk = engine.Packer({k: v for k, v in self.state_dict().items()}, next(self.parameters()).device)
+        pk.sd = {"b." + k: v for k, v in pk.sd.items()}
+        pk.tblock("b", True)
+        self._packed = pk.out
+        return self
+
+    def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
+                timestep=None, cross_attention_kwargs=None, class_labels=None):
+        """hidden_states (b*n_cam, T, C), encoder_hidden_states (b*n_cam, Lk, 768) -> (b*n_cam, T, C)"""
+        from .. import engine, ops
+        if attention_mask is not None or encoder_attention_mask is not None:
+            raise NotImplementedError("attention masks are not used on the reference path (attention_mask=None)")
+        if self._packed is None:
+            self.pack()
+        P = self._packed
+        n, T, C = hidden_states.shape
+        h = hidden_states.to(torch.bfloat16).reshape(n * T, C).contiguous()
+        enc = encoder_hidden_states.to(torch.bfloat16)
+        lk = enc.shape[1]
+        ctx = engine.StepCtx(n=n, temb=None, temb_rows_per_img_factor=1, lk=lk,
+                             kv_map=engine.make_kv_map(n, self.n_cam, h.device))
+        ctx.text_kv["b.attn2"] = engine.text_kv(P, "b.attn2", enc.reshape(n * lk, enc.shape[2]).contiguous())
+        out = engine.transformer_block(P, "b", h, n, T, ctx, True)
+        return out.reshape(n, T, C).to(hidden_states.dtype)

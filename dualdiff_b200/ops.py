@@ -32,7 +32,7 @@ def padded_rows(n_img, H, W):
 
 
 def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, res2=None, a2=None,
-         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0):
+         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0, act=0):
     """out = epilogue(A @ W^T).  a: [M, K] bf16 (row stride may exceed K); w: [N, taps*K] bf16.
 
     taps=9: ``a`` is the padded-pixel activation [n_img*(H+1)*(W+1), K]; the result has n_img*H*W rows.
@@ -70,6 +70,7 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
     args.out_f32 = 1 if out.dtype == torch.float32 else 0
     args.geglu = 1 if geglu else 0
     args.force_bn = force_bn
+    args.act = act
     if bias is not None:
         _req(bias, torch.float32, "bias")
     if rowvec is not None:
@@ -269,6 +270,8 @@ def rows_to_nchw(rows, n_img, hw, out_dtype=torch.float32, c=None):
     return out
 
 
-def cfg_sched_step(eps, x, last, m0, m1, coef, *, n_img, c, hw, cfg=True):
+def cfg_sched_step(eps, x, last, m0, m1, coef, *, n_img, c, hw, cfg=True, eps_nchw=False):
+    for t_ in (eps, x, last, m0, m1, coef):
+        _req(t_, torch.float32, "cfg_sched_step operand")
     check(_lib.lib().dd_cfg_sched_step(_ptr(eps), _ptr(x), _ptr(last), _ptr(m0), _ptr(m1), _ptr(coef), n_img, c,
-                                       hw, 1 if cfg else 0, _stream()), "dd_cfg_sched_step")
+                                       hw, 1 if cfg else 0, 1 if eps_nchw else 0, _stream()), "dd_cfg_sched_step")

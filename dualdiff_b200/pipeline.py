@@ -1,0 +1,138 @@
+"""The sampler loop body of DualDiff as one B200-resident object.
+
+Reference: pipeline/pipeline_bev_controlnet.py:349-512 (`StableDiffusionBEVControlNetPipeline.__call__`):
+per step, [ControlNet-bg, ControlNet-fg] -> residual sum -> multi-view UNet -> classifier-free guidance ->
+scheduler.step.  `DualDiffDenoiser` keeps that contract (uncond half first, tokens from branch 0, residuals
+summed across branches, same noise handling) but
+  * hoists the timestep-invariant work into `prepare()` (tokens, text K/V of all 30 cross-attentions,
+    condition embedding, Semantic Fusion Attention),
+  * runs a step as a CUDA graph of hand-written kernels (no host sync, no torch math),
+  * fuses CFG + UniPC/DDIM into one kernel.
+Scenes are independent (cross-view attention never crosses scenes, blocks.py:196-197), so multi-GPU use is
+one denoiser per rank over its shard of scenes — no collectives.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import engine, ops
+from .scheduler import UniPCMultistepScheduler
+
+
+class DualDiffDenoiser:
+    def __init__(self, unet, controlnets, scheduler=None, guidance_scale: float = 2.0, use_cuda_graph: bool = True):
+        assert len(controlnets) == 2, "dual branch: [controlnet_bg, controlnet_fg]"
+        self.unet, self.nets = unet, list(controlnets)
+        self.guidance_scale = guidance_scale
+        self.cfg = guidance_scale > 1.0          # pipeline: do_classifier_free_guidance = guidance_scale > 1
+        self.scheduler = scheduler if scheduler is not None else UniPCMultistepScheduler()
+        self.scheduler.guidance_scale = guidance_scale
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.device = None
+
+    # -------------------------------------------------------------------------------------------------
+    def prepare(self, latents, prompt_embeds, camera_param, bboxes_3d_data: List[Dict[str, torch.Tensor]], images,
+                num_inference_steps: int):
+        """latents (B, 6, 4, h, w) fp32; prompt_embeds (2B, 77, 768) uncond first (or (B, ...) without CFG);
+        camera_param (B, 6, 3, 7); bboxes_3d_data = [bg boxes, fg map vectors]; images = [bg panorama
+        (B, 3, 8h, 48w), fg ORS (B*6, 320, h, w)]."""
+        dev = latents.device
+        if dev.type != "cuda":
+            raise RuntimeError("dualdiff_b200 has no CPU path: inputs must be CUDA tensors")
+        self.device = dev
+        B, n_cam, c, H, W = latents.shape
+        self.B, self.n_cam, self.H, self.W = B, n_cam, H, W
+        G = 2 if self.cfg else 1
+        self.G = G
+        n = G * B * n_cam
+        self.n = n
+        for m in [self.unet] + self.nets:
+            if m._packed is None:
+                m.pack(dev)
+        if self.cfg:  # uncond in the front, cond in the tail (pipeline:349-375; camera from nets[0])
+            kw = self.nets[0].add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, image=None)
+            cam, boxes = kw["camera_param"], kw["bboxes_3d_data"]
+            text = prompt_embeds
+            assert text.shape[0] == 2 * B
+        else:
+            cam, boxes = camera_param, bboxes_3d_data
+            text = prompt_embeds[-B:]
+        # condition image / ORS tensor are identical in both CFG halves (pipeline:351-373 skips the uncond map)
+        conds = [torch.cat([images[0]] * G) if G > 1 else images[0], torch.cat([images[1]] * G) if G > 1 else images[1]]
+        self.preps = [net.prepare_condition(cam, text, boxes[i], conds[i], H, W) for i, net in enumerate(self.nets)]
+        Pu = self.unet._packed
+        self.unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, self.preps[0].enc_rows)  # tokens of branch 0
+        self.kv_map = engine.make_kv_map(n, n_cam, dev)
+        self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        self.coef_table = self.scheduler.coef_table(dev)
+        self.t_table = self.scheduler.timesteps.to(device=dev, dtype=torch.float32)
+        # state (fp32, NCHW-flat): latents, last corrected sample, x0 history
+        self.latents = latents.reshape(B * n_cam, c, H, W).float().contiguous().clone()
+        self.last = torch.zeros_like(self.latents)
+        self.m0 = torch.zeros_like(self.latents)
+        self.m1 = torch.zeros_like(self.latents)
+        self.t_cur = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.coef_cur = torch.zeros(16, device=dev, dtype=torch.float32)
+        self.eps_rows = None
+        self._graph = None
+        self.step_index = 0
+        return self
+
+    # -------------------------------------------------------------------------------------------------
+    def _step_kernels(self):
+        """one loop body (pipeline:381-504) on the current stream; reads t / coefficients from device buffers"""
+        B6, H, W, G = self.B * self.n_cam, self.H, self.W, self.G
+        acc = None
+        for net, prep in zip(self.nets, self.preps):
+            down, mid = engine.controlnet_forward(net._packed, prep, self.latents, G, B6, H, W, self.t_cur,
+                                                  None if acc is None else acc)
+            acc = down + [mid]
+        Pu = self.unet._packed
+        temb = engine.time_embedding(Pu, self.t_cur)
+        ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
+                             lk=self.preps[0].lk, kv_map=self.kv_map)
+        eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
+        ops.cfg_sched_step(eps, self.latents, self.last, self.m0, self.m1, self.coef_cur, n_img=B6, c=4, hw=H * W,
+                           cfg=self.cfg, eps_nchw=False)
+        self.eps_rows = eps
+        return eps
+
+    def step(self, i: Optional[int] = None):
+        """advance the latents by one sampler step (index i of scheduler.timesteps)"""
+        i = self.step_index if i is None else i
+        self.t_cur.copy_(self.t_table[i:i + 1], non_blocking=True)
+        self.coef_cur.copy_(self.coef_table[i], non_blocking=True)
+        if not self.use_cuda_graph:
+            self._step_kernels()
+        else:
+            if self._graph is None:
+                # warm-up on a side stream (lazy kernel-attribute init, allocator warm-up), restoring the state after
+                saved = [t.clone() for t in (self.latents, self.last, self.m0, self.m1)]
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._step_kernels()
+                torch.cuda.current_stream().wait_stream(s)
+                for t, sv in zip((self.latents, self.last, self.m0, self.m1), saved):
+                    t.copy_(sv)
+                self._graph = torch.cuda.CUDAGraph()
+                n0 = _launches()
+                with torch.cuda.graph(self._graph):
+                    self._step_kernels()
+                self.launches_per_step = _launches() - n0
+                for t, sv in zip((self.latents, self.last, self.m0, self.m1), saved):
+                    t.copy_(sv)
+            self._graph.replay()
+        self.step_index = i + 1
+        return self.latents
+
+    def run(self):
+        for i in range(len(self.scheduler.timesteps)):
+            self.step(i)
+        return self.latents.reshape(self.B, self.n_cam, 4, self.H, self.W)
+
+
+def _launches():
+    from . import _lib
+    return _lib.lib().dd_launch_count()

@@ -63,6 +63,7 @@ typedef struct dd_gemm_args {
   int geglu;          /* 1: out[:, j] = v[:, j] * gelu(g[:, j]); W packed as 128-value / 128-gate
                          column groups per 256-wide tile (dd pack_geglu in dualdiff_b200/packing.py) */
   int force_bn;       /* 0 = auto tile width; testing hook                                        */
+  int act;            /* 0 none, 1 SiLU applied after bias/residuals (ControlNetConditioningEmbedding) */
 } dd_gemm_args;
 DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 
@@ -159,7 +160,8 @@ DD_API int dd_rows_to_nchw(const void* rows, int rows_f32, long long ld, void* o
                            int hw, void* stream);
 
 /* ---- CFG combine + UniPC/DDIM update, one pass (pipeline/pipeline_bev_controlnet.py:487-499) -------- */
-/* eps: fp32 channels-last [2*n_img*hw, c] (uncond half first) or [n_img*hw, c] when cfg == 0.
+/* eps: fp32 channels-last [2*n_img*hw, c] (uncond half first) or [n_img*hw, c] when cfg == 0
+ * (eps_nchw = 1: same but NCHW, the layout UNet2DConditionModelMultiview.forward returns).
  * State (fp32, NCHW, n_img*c*hw each): x (latents, in/out), last (corrected sample), m0, m1 (x0 history).
  * coef (device, fp32[16]): {guidance, sigma_t, 1/alpha_t, a_last, a_m0, a_m1, a_x0, a_x, b_xc, b_x0, b_m0, ...}
  *   x0  = (x - sigma_t*eps) / alpha_t
@@ -167,7 +169,7 @@ DD_API int dd_rows_to_nchw(const void* rows, int rows_f32, long long ld, void* o
  *   x'  = b_xc*xc + b_x0*x0 + b_m0*m0                                 (UniP predictor / DDIM)
  *   then last <- xc, m1 <- m0, m0 <- x0, x <- x'.   Coefficients are computed on the host in fp64. */
 DD_API int dd_cfg_sched_step(const float* eps, float* x, float* last, float* m0, float* m1, const float* coef,
-                             int n_img, int c, int hw, int cfg, void* stream);
+                             int n_img, int c, int hw, int cfg, int eps_nchw, void* stream);
 
 #ifdef __cplusplus
 }
