@@ -15,6 +15,42 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# ---- optional per-launch instrumentation (bench.py roofline pass; never active on the timed path) ----
+_PROF = None
+
+
+def profile_start():
+    global _PROF
+    _PROF = []
+
+
+def profile_stop():
+    """-> list of (kernel family, milliseconds, algorithmic flops, algorithmic bytes, tag)"""
+    global _PROF
+    rec, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return [(n, a.elapsed_time(b), f, by, tag) for (n, a, b, f, by, tag) in rec]
+
+
+class _Rec:
+    def __init__(self, name, flops=0.0, nbytes=0.0, tag=""):
+        self.args = (name, flops, nbytes, tag)
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            self.b.record()
+            n, f, by, tag = self.args
+            _PROF.append((n, self.a, self.b, f, by, tag))
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -75,7 +111,10 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
         _req(bias, torch.float32, "bias")
     if rowvec is not None:
         _req(rowvec, torch.float32, "rowvec")
-    check(_lib.lib().dd_gemm(C.byref(args), _stream()), "dd_gemm")
+    with _Rec("gemm_tcgen05", 2.0 * rows_out * N * K * taps,
+              2.0 * (rows_out * K * (1 if taps == 1 else 1) + N * K * taps + rows_out * n_store),
+              f"M{rows_out}_N{N}_K{K * taps}"):
+        check(_lib.lib().dd_gemm(C.byref(args), _stream()), "dd_gemm")
     return out
 
 
@@ -106,7 +145,8 @@ def groupnorm(x1, gamma, beta, *, n_img, hw, x2=None, eps=1e-5, silu=True, padde
     a.x1_ld = x1.stride(0); a.x2_ld = x2.stride(0) if x2 is not None else 0; a.out_ld = out.stride(0)
     a.n_img = n_img; a.h = H; a.w = W; a.c1 = c1; a.c2 = c2; a.groups = groups
     a.eps = eps; a.silu = 1 if silu else 0; a.padded_out = 1 if padded_out else 0
-    check(_lib.lib().dd_groupnorm(C.byref(a), _stream()), "dd_groupnorm")
+    with _Rec("groupnorm_silu", 0.0, 2.0 * (2 * n_img * H * W * C_ + rows * C_), f"C{C_}_HW{H * W}"):
+        check(_lib.lib().dd_groupnorm(C.byref(a), _stream()), "dd_groupnorm")
     return out
 
 
@@ -118,7 +158,8 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     a = LayerNormArgs()
     a.x = _ptr(x); a.out = _ptr(out); a.gamma = _ptr(gamma); a.beta = _ptr(beta)
     a.x_ld = x.stride(0); a.out_ld = out.stride(0); a.rows = rows; a.c = c; a.eps = eps
-    check(_lib.lib().dd_layernorm(C.byref(a), _stream()), "dd_layernorm")
+    with _Rec("layernorm", 0.0, 4.0 * rows * c, f"C{c}"):
+        check(_lib.lib().dd_layernorm(C.byref(a), _stream()), "dd_layernorm")
     return out
 
 
@@ -145,7 +186,9 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
     a.n_img = n_img; a.n_kv_img = n_kv_img; a.heads = heads; a.head_dim = head_dim
     a.lq = lq; a.lk = lk; a.n_src = n_src
     a.scale = float(head_dim) ** -0.5 if scale is None else scale
-    check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")
+    with _Rec("attn_tcgen05", 4.0 * n_img * lq * lk * heads * head_dim * n_src,
+              2.0 * heads * head_dim * (2 * n_img * lq + 2 * n_kv_img * lk), f"d{head_dim}_Lq{lq}_Lk{lk}_s{n_src}"):
+        check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")
     return out
 
 
@@ -170,7 +213,8 @@ def im2col_s2(x, *, n_img, hw, out=None):
     ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     if out is None:
         out = torch.empty((n_img * ho * wo, 9 * c), device=x.device, dtype=torch.bfloat16)
-    check(_lib.lib().dd_im2col_s2(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s2")
+    with _Rec("layout", 0.0, 2.0 * (n_img * H * W * c + out.numel())):
+        check(_lib.lib().dd_im2col_s2(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s2")
     return out, (ho, wo)
 
 
@@ -181,8 +225,9 @@ def upsample_pad(x, *, n_img, hw, hw2, out=None):
     c = x.shape[1]
     if out is None:
         out = torch.empty((padded_rows(n_img, H2, W2), c), device=x.device, dtype=torch.bfloat16)
-    check(_lib.lib().dd_upsample_pad(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, H2, W2, _stream()),
-          "dd_upsample_pad")
+    with _Rec("layout", 0.0, 2.0 * (n_img * H * W * c + out.numel())):
+        check(_lib.lib().dd_upsample_pad(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, H2, W2, _stream()),
+              "dd_upsample_pad")
     return out
 
 
@@ -245,7 +290,8 @@ def add_bf16(a, b, c=None, out=None):
     _req(a, torch.bfloat16, "a")
     if out is None:
         out = torch.empty_like(a)
-    check(_lib.lib().dd_add_bf16(_ptr(a), _ptr(b), _ptr(c), _ptr(out), _L(a.numel()), _stream()), "dd_add_bf16")
+    with _Rec("elementwise", 0.0, 2.0 * a.numel() * (3 if c is None else 4)):
+        check(_lib.lib().dd_add_bf16(_ptr(a), _ptr(b), _ptr(c), _ptr(out), _L(a.numel()), _stream()), "dd_add_bf16")
     return out
 
 
