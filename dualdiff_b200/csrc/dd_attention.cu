@@ -18,6 +18,12 @@
 
 namespace dd {
 
+__device__ __forceinline__ float fast_exp2(float x) {  // inputs are <= 0 after the max subtraction; ftz is fine
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 static constexpr int ATT_BM = 128;
 static constexpr int ATT_BN = 128;
 static constexpr int ATT_THREADS = 160;     // 4 softmax warps + 1 TMA/UMMA warp
@@ -32,8 +38,8 @@ struct AttnDev {
   int q_col0, k_col0, v_col0, q_hs, k_hs, v_hs, o_hs;
 };
 
-template <int DQK, int DV, int DVP, int STAGES>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int DQK, int DV, int DVP, int STAGES, int MINB>
+__global__ void __launch_bounds__(ATT_THREADS, MINB)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
   constexpr int QCH = (DQK + 63) / 64;
@@ -43,19 +49,23 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
   constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, DVP, 0, 1);  // B (=V) is MN-major
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // No static shared memory: the dynamic segment then starts at the CTA's (1024-byte aligned) window, so the
+  // swizzled tiles need no alignment slack and two CTAs fit one SM for head_dim 40.  Barriers live at the tail.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t sQ = smem_base;
   const uint32_t sKV = sQ + QCH * CHUNK_BYTES;
   const uint32_t sP = sKV + STAGES * KV_STAGE_BYTES;
-  __shared__ __align__(8) uint64_t bars[10];
-  __shared__ uint32_t tmem_ptr_smem;
-  const uint32_t q_full = smem_u32(&bars[0]);
-  const uint32_t s_full = smem_u32(&bars[1]);
-  const uint32_t p_full = smem_u32(&bars[2]);
-  const uint32_t o_full = smem_u32(&bars[3]);
-  const uint32_t kv_full = smem_u32(&bars[4]);   // [STAGES]
-  const uint32_t kv_empty = smem_u32(&bars[6]);  // [STAGES]
+  const uint32_t bar0 = sP + 2 * CHUNK_BYTES;
+  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - smem_base) + 96);
+  const uint32_t q_full = bar0;
+  const uint32_t s_full = bar0 + 8;
+  const uint32_t p_full = bar0 + 16;
+  const uint32_t o_full = bar0 + 24;
+  const uint32_t kv_full = bar0 + 32;   // [STAGES]
+  const uint32_t kv_empty = bar0 + 48;  // [STAGES]
+  const uint32_t s_free = bar0 + 64;    // softmax threads hold S in registers -> the next Q K^T may overwrite TMEM
+  if ((smem_base & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,6 +76,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
+    mbar_init(s_free, 128);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(kv_full + 8 * s, 1);
       mbar_init(kv_empty + 8 * s, 1);
@@ -73,13 +84,13 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 4) {
-    tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+    tmem_alloc(bar0 + 96, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_ptr_smem;
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_gen);
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
   const int total = p.n_src * p.n_kv_tiles;
@@ -107,15 +118,11 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int c = 0; c < VCH; ++c)
           tma_load_3d(sV + c * CHUNK_BYTES, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs + c * 64, jt * ATT_BN, kv_img);
       };
-      produce(0);
-      mbar_wait(q_full, 0);
-      for (int g = 0; g < total; ++g) {
+      auto issue_qk = [&](int g) {
         const int s = g % STAGES;
-        const uint32_t ph = (g / STAGES) & 1;
-        mbar_wait(kv_full + 8 * s, ph);
+        mbar_wait(kv_full + 8 * s, (g / STAGES) & 1);
         tc_fence_after();
         const uint32_t sK = sKV + s * KV_STAGE_BYTES;
-        const uint32_t sV = sK + QCH * CHUNK_BYTES;
         // S = Q K^T  (both operands K-major, 64-column swizzle chunks)
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) {
@@ -124,24 +131,48 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     kk != 0 ? 1u : 0u);
         }
         umma_commit(s_full);
-        if (STAGES > 1 && g + 1 < total) produce(g + 1);
+      };
+      produce(0);
+      if (STAGES > 1 && total > 1) produce(1);
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int g = 0; g < total; ++g) {
+        const int s = g % STAGES;
+        // Software pipeline: as soon as the softmax threads have pulled S(g) into registers, S(g+1) = Q K(g+1)^T is
+        // issued, so it is ready in TMEM when they come back; P(g) V(g) follows once P(g) has been written.
+        if (STAGES > 1 && g + 1 < total) {
+          mbar_wait(s_free, g & 1);
+          tc_fence_after();
+          issue_qk(g + 1);
+        }
         mbar_wait(p_full, g & 1);
         tc_fence_after();
-        // O_tile = P V : A = P (K-major, 2 chunks of 64 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
+        const uint32_t sV = sKV + s * KV_STAGE_BYTES + QCH * CHUNK_BYTES;
+        // O += P V : A = P (K-major, 2 chunks of 64 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           const uint32_t offP = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
           const uint32_t offV = kk * 16 * 128;  // 16 key rows of 128 B
           umma_bf16(tmem_O, umma_smem_desc(sP + offP, 16, 1024, 2),
-                    umma_smem_desc(sV + offV, CHUNK_BYTES, 1024, 2), IDESC_O, kk != 0 ? 1u : 0u);
+                    umma_smem_desc(sV + offV, CHUNK_BYTES, 1024, 2), IDESC_O,
+                    (kk != 0 || (g % p.n_kv_tiles) != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
         }
         umma_commit(kv_empty + 8 * s);
         umma_commit(o_full);
-        if (STAGES == 1 && g + 1 < total) produce(g + 1);
+        if (STAGES > 1) {
+          if (g + 2 < total) produce(g + 2);   // stage s is free once P(g) V(g) retires (kv_empty)
+        } else if (g + 1 < total) {
+          produce(g + 1);
+          mbar_wait(s_free, g & 1);
+          tc_fence_after();
+          issue_qk(g + 1);
+        }
       }
     }
   } else {
-    // ------------------------------- softmax / accumulate / epilogue -------------------------------
+    // ------------------------------- softmax / correction / epilogue -------------------------------
+    // One pass over S held in registers.  O accumulates in TMEM; the running max is only advanced (and O rescaled
+    // in TMEM) when it grows by more than 2^8, so p = exp2(s - m_ref) stays <= 256 and the correction is rare.
     const int row = threadIdx.x;  // == TMEM lane
     const int q_row = q_tile * ATT_BM + row;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
@@ -152,88 +183,114 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int g = 0;
     for (int src = 0; src < p.n_src; ++src) {
       float m = -INFINITY, l = 0.f;
-      float o[DVP];
-#pragma unroll
-      for (int i = 0; i < DVP; ++i) o[i] = 0.f;
       for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
         mbar_wait(s_full, g & 1);
         tc_fence_after();
         const int key0 = jt * ATT_BN;
-        // pass 1: row max over the valid keys
+        uint32_t sv[ATT_BN];
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 32) tmem_ld_32x32(tmem_S + lane_sel + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free);             // S(g) now lives in registers
+        const int nvalid = p.Lk - key0;  // keys >= nvalid in this tile are padding
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < ATT_BN; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tmem_S + lane_sel + c, sv);
-          tmem_ld_wait();
+        if (nvalid >= ATT_BN) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (key0 + c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+          for (int j = 0; j < ATT_BN; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < ATT_BN; ++j)
+            if (j < nvalid) mx = fmaxf(mx, __uint_as_float(sv[j]));
         }
-        const float m_new = fmaxf(m, mx * sl2);
-        const float alpha = exp2f(m - m_new);
+        const float m_cand = fmaxf(m, mx * sl2);
+        const bool grow = __any_sync(0xffffffffu, m_cand > m + 8.f);   // warp-uniform (first tile: m = -inf)
+        float alpha = 1.f;
+        if (grow) {
+          alpha = fast_exp2(m - m_cand);
+          m = m_cand;
+          l *= alpha;
+        }
+        // p = exp2(s*scale*log2e - m), packed to bf16 (registers: 64)
+        uint32_t pk[ATT_BN / 2];
         float lsum = 0.f;
-        // pass 2: p = exp2(s*scale*log2e - m_new), write bf16 P into the swizzled K-major A tile
-#pragma unroll 1
-        for (int c = 0; c < ATT_BN; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tmem_S + lane_sel + c, sv);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        if (nvalid >= ATT_BN) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = (key0 + c + j < p.Lk) ? exp2f(__uint_as_float(sv[j]) * sl2 - m_new) : 0.f;
-            float p1 = (key0 + c + j + 1 < p.Lk) ? exp2f(__uint_as_float(sv[j + 1]) * sl2 - m_new) : 0.f;
+          for (int j = 0; j < ATT_BN; j += 2) {
+            const float p0 = fast_exp2(__uint_as_float(sv[j]) * sl2 - m);
+            const float p1 = fast_exp2(__uint_as_float(sv[j + 1]) * sl2 - m);
             lsum += p0 + p1;
             pk[j >> 1] = pack_bf16(p0, p1);
           }
-          const uint32_t chunk_base = p_row_base + (c >> 6) * CHUNK_BYTES;
-          const uint32_t u0 = (uint32_t)((c & 63) >> 3);  // first 16-byte unit of this 32-key group
+        } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t addr = chunk_base + (((u0 + u) ^ xr) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
-                         "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
-                         : "memory");
+          for (int j = 0; j < ATT_BN; j += 2) {
+            const float p0 = (j < nvalid) ? fast_exp2(__uint_as_float(sv[j]) * sl2 - m) : 0.f;
+            const float p1 = (j + 1 < nvalid) ? fast_exp2(__uint_as_float(sv[j + 1]) * sl2 - m) : 0.f;
+            lsum += p0 + p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
           }
         }
-        l = l * alpha + lsum;
-        m = m_new;
+        l += lsum;
+        // the previous tile's P V must have retired before P is overwritten / O is rescaled
+        if (g > 0) {
+          mbar_wait(o_full, (g - 1) & 1);
+          tc_fence_after();
+        }
+        if (grow && jt > 0) {
+#pragma unroll
+          for (int c = 0; c < DVP; c += 16) {
+            uint32_t ov[16];
+            tmem_ld_32x16(tmem_O + lane_sel + c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+            tmem_st_32x16(tmem_O + lane_sel + c, ov);
+          }
+          tmem_st_wait();
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {  // 16-byte units of this row: 8 per 64-key swizzle chunk
+          const uint32_t addr = p_row_base + (u >> 3) * CHUNK_BYTES + ((((uint32_t)u & 7) ^ xr) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                       "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                       : "memory");
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(p_full);
-        // accumulate this tile's O contribution
-        mbar_wait(o_full, g & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < DVP; c += 16) {
-          uint32_t ov[16];
-          tmem_ld_32x16(tmem_O + lane_sel + c, ov);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[c + j] = o[c + j] * alpha + __uint_as_float(ov[j]);
-        }
-        tc_fence_before();
       }
-      if (q_row < p.Lq) {
-        const float inv = 1.f / l;
+      // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first)
+      mbar_wait(o_full, (g - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.f / l;
 #pragma unroll
-        for (int c = 0; c < DV; c += 8) {
-          float v[8];
+      for (int c = 0; c < DVP; c += 16) {
+        uint32_t ov[16];
+        tmem_ld_32x16(tmem_O + lane_sel + c, ov);
+        tmem_ld_wait();
+        if (q_row < p.Lq) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = o[c + e] * inv;
-          if (src > 0) {
-            const uint4 r = *reinterpret_cast<const uint4*>(orow + c);
-            float2 t;
-            t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
-            t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
-            t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
-            t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+          for (int hh = 0; hh < 16; hh += 8) {
+            if (c + hh + 8 <= DV) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(ov[hh + e]) * inv;
+              if (src > 0) {
+                const uint4 r = *reinterpret_cast<const uint4*>(orow + c + hh);
+                float2 t;
+                t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+              }
+              *reinterpret_cast<uint4*>(orow + c + hh) =
+                  make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
           }
-          *reinterpret_cast<uint4*>(orow + c) =
-              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
       }
+      tc_fence_before();
     }
   }
   tc_fence_before();
@@ -244,19 +301,19 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int DQK, int DV, int DVP, int STAGES>
+template <int DQK, int DV, int DVP, int STAGES, int MINB>
 static int launch_attn(const dd_attention_args* a, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, AttnDev p, cudaStream_t stream) {
   constexpr int QCH = (DQK + 63) / 64, VCH = (DVP + 63) / 64;
-  constexpr size_t smem = (size_t)QCH * CHUNK_BYTES + (size_t)STAGES * (QCH + VCH) * CHUNK_BYTES + 2 * CHUNK_BYTES + 1024;
+  constexpr size_t smem = (size_t)QCH * CHUNK_BYTES + (size_t)STAGES * (QCH + VCH) * CHUNK_BYTES + 2 * CHUNK_BYTES + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    DD_CUDA(cudaFuncSetAttribute(attn_tcgen05_kernel<DQK, DV, DVP, STAGES>,
+    DD_CUDA(cudaFuncSetAttribute(attn_tcgen05_kernel<DQK, DV, DVP, STAGES, MINB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   dim3 grid((a->lq + ATT_BM - 1) / ATT_BM, a->heads, a->n_img);
-  attn_tcgen05_kernel<DQK, DV, DVP, STAGES><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  attn_tcgen05_kernel<DQK, DV, DVP, STAGES, MINB><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -293,9 +350,9 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
     case 40:
       DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
                "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
-      return launch_attn<48, 40, 48, 2>(a, tmQ, tmK, tmV, p, stream);
-    case 80: return launch_attn<80, 80, 80, 2>(a, tmQ, tmK, tmV, p, stream);
-    case 160: return launch_attn<160, 160, 160, 1>(a, tmQ, tmK, tmV, p, stream);
+      return launch_attn<48, 40, 48, 2, 2>(a, tmQ, tmK, tmV, p, stream);
+    case 80: return launch_attn<80, 80, 80, 2, 1>(a, tmQ, tmK, tmV, p, stream);
+    case 160: return launch_attn<160, 160, 160, 1, 1>(a, tmQ, tmK, tmV, p, stream);
   }
   return -1;
 }

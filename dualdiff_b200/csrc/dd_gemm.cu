@@ -29,6 +29,7 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 static constexpr int GEMM_THREADS = 192;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
+static constexpr int EPI_WARP_BYTES = 32 * 64 * 4;  // per-epilogue-warp transpose buffer (32 rows x 64 fp32)
 
 struct GemmDev {
   int M, N, K, K1, taps;
@@ -160,18 +161,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------- epilogue warps ------------------------------
+    // TMEM lane == tile row, so a thread owns one output row; storing straight from that mapping writes 16 B per
+    // lane at a row pitch of N*2 bytes (every warp store touches 32 cache lines).  Instead each warp transposes
+    // 32x64 fp32 sub-tiles through a private, bank-rotated smem buffer so that 8 consecutive lanes own 64 consecutive
+    // columns of ONE row: residual/bias loads and the bf16 stores become full 128-byte row segments.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t local_tile = 0;
     const int HW1 = (p.conv_H + 1) * pitch;
+    const uint32_t stage_buf = smem_base + stages * STAGE_BYTES + q * EPI_WARP_BYTES;
+    const int OUTW = p.geglu ? BN / 2 : BN;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
       const int m0 = (tile / p.n_tiles) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
+      const int nout0 = p.geglu ? (n0 / BN) * (BN / 2) : n0;
       const uint32_t as = local_tile & 1;
       const uint32_t aph = (local_tile >> 1) & 1;
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
-      bool valid = m < p.M;
+      int valid = m < p.M;
       long long orow = m;
       if (p.taps == 9) {
         const int img = m / HW1;
@@ -181,115 +189,133 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         valid = valid && (hp < p.conv_H) && (wp < p.conv_W);
         orow = ((long long)img * p.conv_H + hp) * p.conv_W + wp;
       }
-      const float* rv = nullptr;
-      if (p.rowvec != nullptr && valid) rv = p.rowvec + (orow / p.rows_per_img) * (long long)p.rowvec_ld;
       const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 
-      if (p.geglu) {
-        // tile columns [0, BN/2) = value half, [BN/2, BN) = gate half (weights are packed that way)
-        constexpr int HALF = BN / 2;
-        const int nout0 = (n0 / BN) * HALF;
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-          uint32_t a[32], g[32];
-          tmem_ld_32x32(tmem_acc + c, a);
-          tmem_ld_32x32(tmem_acc + HALF + c, g);
-          tmem_ld_wait();
-          if (valid) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + orow * p.out_ld + nout0 + c;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) {
-                float v0 = __uint_as_float(a[j + e]), v1 = __uint_as_float(a[j + e + 1]);
-                float g0 = __uint_as_float(g[j + e]), g1 = __uint_as_float(g[j + e + 1]);
-                if (p.bias) {
-                  v0 += p.bias[n0 + c + j + e];
-                  v1 += p.bias[n0 + c + j + e + 1];
-                  g0 += p.bias[n0 + HALF + c + j + e];
-                  g1 += p.bias[n0 + HALF + c + j + e + 1];
-                }
-                pk[e >> 1] = pack_bf16(v0 * gelu_erf_f(g0), v1 * gelu_erf_f(g1));
-              }
-              if (nout0 + c + j + 8 <= p.n_store)
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-          }
-        }
-      } else {
+      for (int c = 0; c < OUTW; c += 64) {
+        const int width = (OUTW - c) < 64 ? (OUTW - c) : 64;  // 64, or 32 for the last chunk of BN = 32/160
+        // ---- TMEM -> registers -> rotated smem (thread = row) ----
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int h = 0; h < width; h += 32) {
           uint32_t a[32];
-          if (BN >= 32 || c == 0) tmem_ld_32x32(tmem_acc + c, a);
-          tmem_ld_wait();
-          const int nb = n0 + c;
-          if (valid && nb < p.n_store) {
-            if (nb + 32 <= p.n_store) {
+          tmem_ld_32x32(tmem_acc + c + h, a);
+          if (p.geglu) {
+            uint32_t g[32];
+            tmem_ld_32x32(tmem_acc + BN / 2 + c + h, g);
+            tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a[j + e]);
-                if (p.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb + j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(p.bias + nb + j + 4);
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (rv) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(rv + nb + j);
-                  const float4 b1 = *reinterpret_cast<const float4*>(rv + nb + j + 4);
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (p.res1) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(p.res1 + orow * p.res1_ld + nb + j);
-                  float2 t;
-                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
-                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
-                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
-                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
-                }
-                if (p.res2) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow * p.res2_ld + nb + j);
-                  float2 t;
-                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
-                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
-                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
-                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
-                }
-                if (p.act == 1) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
-                }
-                if (p.out_f32) {
-                  float* o = reinterpret_cast<float*>(p.out) + orow * p.out_ld + nb + j;
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-                  bf16* o = reinterpret_cast<bf16*>(p.out) + orow * p.out_ld + nb + j;
-                  *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                }
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(a[j]), gg = __uint_as_float(g[j]);
+              if (p.bias) {
+                v += p.bias[n0 + c + h + j];
+                gg += p.bias[n0 + BN / 2 + c + h + j];
               }
+              a[j] = __float_as_uint(v * gelu_erf_f(gg));
+            }
+          } else {
+            tmem_ld_wait();
+          }
+          const uint32_t rbase = stage_buf + lane * 256;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int uu = (h >> 2) + u;  // 16-byte unit index inside the 256-byte row
+            const uint32_t pu = (uint32_t)((uu & 8) | (((uu & 7) + (uu >> 3) + lane) & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (pu << 4)), "r"(a[4 * u]),
+                         "r"(a[4 * u + 1]), "r"(a[4 * u + 2]), "r"(a[4 * u + 3])
+                         : "memory");
+          }
+        }
+        __syncwarp();
+        // ---- smem -> registers (8 lanes = one row's 64 columns) -> epilogue math -> coalesced global store ----
+        const int lpr = width >> 3;           // lanes per row: 8 (or 4)
+        const int rpi = 32 / lpr;             // rows per iteration: 4 (or 8)
+        const int k = lane % lpr;             // 8-column group owned by this lane
+        const int col = nout0 + c + k * 8;    // output column of v[0]
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const int rr = r0 + lane / lpr;
+          const long long orow_r = __shfl_sync(0xffffffffu, orow, rr);
+          const int valid_r = __shfl_sync(0xffffffffu, valid, rr);
+          const uint32_t rbase = stage_buf + rr * 256;
+          const int u0 = 2 * k, u1 = 2 * k + 1;
+          const uint32_t p0 = (uint32_t)((u0 & 8) | (((u0 & 7) + (u0 >> 3) + rr) & 7));
+          const uint32_t p1 = (uint32_t)((u1 & 8) | (((u1 & 7) + (u1 >> 3) + rr) & 7));
+          float v[8];
+          {
+            uint32_t t0, t1, t2, t3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p0 << 4)));
+            v[0] = __uint_as_float(t0); v[1] = __uint_as_float(t1); v[2] = __uint_as_float(t2); v[3] = __uint_as_float(t3);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p1 << 4)));
+            v[4] = __uint_as_float(t0); v[5] = __uint_as_float(t1); v[6] = __uint_as_float(t2); v[7] = __uint_as_float(t3);
+          }
+          if (!valid_r || col >= p.n_store) continue;
+          if (col + 8 <= p.n_store) {
+            if (!p.geglu) {
+              if (p.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.rowvec) {
+                const float* rv = p.rowvec + (orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col;
+                const float4 b0 = *reinterpret_cast<const float4*>(rv);
+                const float4 b1 = *reinterpret_cast<const float4*>(rv + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.res1) {
+                const uint4 r = *reinterpret_cast<const uint4*>(p.res1 + orow_r * p.res1_ld + col);
+                float2 t;
+                t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+              }
+              if (p.res2) {
+                const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow_r * p.res2_ld + col);
+                float2 t;
+                t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+              }
+              if (p.act == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+              }
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + orow_r * p.out_ld + col;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
             } else {
-              // ragged right edge (N not a multiple of 32): scalar path
-              for (int j = 0; j < 32 && nb + j < p.n_store; ++j) {
-                float v = __uint_as_float(a[j]);
-                if (p.bias) v += p.bias[nb + j];
-                if (rv) v += rv[nb + j];
-                if (p.res1) v += __bfloat162float(p.res1[orow * p.res1_ld + nb + j]);
-                if (p.res2) v += __bfloat162float(p.res2[orow * p.res2_ld + nb + j]);
-                if (p.act == 1) v = silu_f(v);
+              bf16* o = reinterpret_cast<bf16*>(p.out) + orow_r * p.out_ld + col;
+              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                        pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          } else {
+            // ragged right edge (N not a multiple of 8, e.g. conv_out N = 4): scalar path
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (col + e < p.n_store) {
+                float x = v[e];
+                if (!p.geglu) {
+                  if (p.bias) x += p.bias[col + e];
+                  if (p.rowvec) x += p.rowvec[(orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col + e];
+                  if (p.res1) x += __bfloat162float(p.res1[orow_r * p.res1_ld + col + e]);
+                  if (p.res2) x += __bfloat162float(p.res2[orow_r * p.res2_ld + col + e]);
+                  if (p.act == 1) x = silu_f(x);
+                }
                 if (p.out_f32)
-                  reinterpret_cast<float*>(p.out)[orow * p.out_ld + nb + j] = v;
+                  reinterpret_cast<float*>(p.out)[orow_r * p.out_ld + col + e] = x;
                 else
-                  reinterpret_cast<bf16*>(p.out)[orow * p.out_ld + nb + j] = __float2bfloat16(v);
+                  reinterpret_cast<bf16*>(p.out)[orow_r * p.out_ld + col + e] = __float2bfloat16(x);
               }
             }
           }
         }
+        __syncwarp();
       }
       // release the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -313,13 +339,13 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                        GemmDev p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (200 * 1024) / STAGE_BYTES;
+  int stages = (227 * 1024 - 3072 - 4 * EPI_WARP_BYTES) / STAGE_BYTES;
   if (stages > 8) stages = 8;
   const int iters = p.taps * ((p.K + BK - 1) / BK);
   if (stages > iters && iters >= 2) stages = iters;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 1024;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -11,60 +11,74 @@
 namespace dd {
 
 // ---------------------------------------------------------------------------------------------------
-// GroupNorm pass 1: per (image, channel) sum and sum of squares -> stats[img][C][2] (fp32, pre-zeroed)
+// GroupNorm pass 1: per (image, channel) sum / sum of squares.  A CTA owns a slab of rows of one image; threads
+// that share a channel octet reduce through shared memory, so only C*2 atomics leave each CTA.
+// stats[img][C][2] (fp32, pre-zeroed).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(512)
 gn_stats_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
                 long long ld2, int C, int HW, int rows_per_cta, float* __restrict__ stats) {
+  extern __shared__ float red[];  // [rpi][C][2]
   const int img = blockIdx.y;
   const int tpr = C >> 3;                    // threads per row (8 channels each)
   const int rpi = blockDim.x / tpr;          // rows per iteration
   const int lane_c = threadIdx.x % tpr;
   const int sub = threadIdx.x / tpr;
-  if (sub >= rpi) return;
   const int c0 = lane_c * 8;
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(HW, r_begin + rows_per_cta);
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
-  const bool from1 = c0 < C1;
-  const bf16* base = from1 ? x1 + c0 : x2 + (c0 - C1);
-  const long long ld = from1 ? ld1 : ld2;
-  for (int r = r_begin + sub; r < r_end; r += rpi) {
-    const uint4 v = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + r) * ld);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if (sub < rpi) {
+    const bool from1 = c0 < C1;
+    const bf16* base = from1 ? x1 + c0 : x2 + (c0 - C1);
+    const long long ld = from1 ? ld1 : ld2;
+    int r = r_begin + sub;
+    // two independent 16-byte loads in flight per thread
+    for (; r + rpi < r_end; r += 2 * rpi) {
+      const uint4 v0 = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + r) * ld);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + r + rpi) * ld);
+      const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_bf16(w[e]);
-      s[2 * e] += f.x; q[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      for (int e = 0; e < 8; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const int j = (e & 3) * 2;
+        s[j] += f.x; q[j] += f.x * f.x;
+        s[j + 1] += f.y; q[j + 1] += f.y * f.y;
+      }
+    }
+    for (; r < r_end; r += rpi) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + ((long long)img * HW + r) * ld);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        s[2 * e] += f.x; q[2 * e] += f.x * f.x;
+        s[2 * e + 1] += f.y; q[2 * e + 1] += f.y * f.y;
+      }
+    }
+    float* o = red + ((size_t)sub * C + c0) * 2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      o[2 * e] = s[e];
+      o[2 * e + 1] = q[e];
     }
   }
-  float* o = stats + ((long long)img * C + c0) * 2;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    atomicAdd(o + 2 * e, s[e]);
-    atomicAdd(o + 2 * e + 1, q[e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < rpi; ++k) acc += red[(size_t)k * 2 * C + i];
+    atomicAdd(stats + (long long)img * 2 * C + i, acc);
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// GroupNorm pass 2: normalise + affine (+ SiLU), write compact or padded layout
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(384)
-gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
-                long long ld2, int C, int H, int W, int groups, float eps,
-                const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ stats, int silu, int padded, bf16* __restrict__ out,
-                long long out_ld, int rows_per_cta) {
-  extern __shared__ float sm[];  // scale[C], shift[C]
-  float* scale = sm;
-  float* shift = sm + C;
-  const int img = blockIdx.y;
+// pass 1b: per-(image, channel) affine  y = x * scale + shift  from the group statistics (tiny)
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ ss, int C, int groups,
+                                   int HW, float eps) {
+  const int img = blockIdx.x;
   const int cpg = C / groups;
-  const int HW = H * W;
-  // per-group mean / rstd from the per-channel sums (one warp-level pass over the channels)
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, q = 0.f;
     const float* st = stats + ((long long)img * C + g * cpg) * 2;
@@ -79,11 +93,21 @@ gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
     for (int c = 0; c < cpg; ++c) {
       const int ch = g * cpg + c;
       const float ga = gamma[ch] * rstd;
-      scale[ch] = ga;
-      shift[ch] = beta[ch] - mean * ga;
+      ss[((long long)img * C + ch) * 2] = ga;
+      ss[((long long)img * C + ch) * 2 + 1] = beta[ch] - mean * ga;
     }
   }
-  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm pass 2: normalise + affine (+ SiLU), write compact or padded layout
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
+                long long ld2, int C, int H, int W, const float* __restrict__ ss, int silu, int padded,
+                bf16* __restrict__ out, long long out_ld, int rows_per_cta) {
+  const int img = blockIdx.y;
+  const int HW = H * W;
   const int tpr = C >> 3;
   const int rpi = blockDim.x / tpr;
   const int lane_c = threadIdx.x % tpr;
@@ -98,10 +122,13 @@ gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(rows_img, r_begin + rows_per_cta);
   float sc[8], sh[8];
+  {
+    const float4* p4 = reinterpret_cast<const float4*>(ss + ((long long)img * C + c0) * 2);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    sc[e] = scale[c0 + e];
-    sh[e] = shift[c0 + e];
+    for (int e = 0; e < 4; ++e) {
+      const float4 t = p4[e];
+      sc[2 * e] = t.x; sh[2 * e] = t.y; sc[2 * e + 1] = t.z; sh[2 * e + 1] = t.w;
+    }
   }
   for (int r = r_begin + sub; r < r_end; r += rpi) {
     int src = r;
@@ -139,35 +166,58 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
   DD_CHECK(a->n_img > 0 && a->h > 0 && a->w > 0 && C > 0, -1, "dd_groupnorm: bad shape");
   DD_CHECK(C % 8 == 0 && a->c1 % 8 == 0, -1, "dd_groupnorm: channels must be multiples of 8 (C=%d c1=%d)", C, a->c1);
   DD_CHECK(C % a->groups == 0, -1, "dd_groupnorm: C=%d not divisible by groups=%d", C, a->groups);
-  DD_CHECK(C <= 2048 * 8 && (C >> 3) <= 256 * 4, -1, "dd_groupnorm: C=%d too large", C);
+  DD_CHECK(C <= 4096, -1, "dd_groupnorm: C=%d too large (max 4096)", C);
   DD_CHECK(a->c2 == 0 || a->x2 != nullptr, -1, "dd_groupnorm: x2 missing");
   const int HW = a->h * a->w;
-  int tpr = C >> 3;
-  int threads = 256;
-  if (tpr > 256) threads = ((tpr + 31) / 32) * 32;  // C up to 2560 -> 320 threads
-  DD_CHECK(threads <= 384, -1, "dd_groupnorm: C=%d too large (max 3072)", C);
-  DD_CUDA(cudaMemsetAsync(a->stats, 0, sizeof(float) * 2 * (size_t)a->n_img * C, stream));
+  const int tpr = C >> 3;
+  int threads = 512;
+  if (tpr > 512) threads = tpr;
+  threads = (threads / tpr) * tpr;                 // whole rows only
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
   const int rpi = threads / tpr;
-  int rows_per_cta = rpi * 8;
+  DD_CHECK(rpi >= 1, -1, "dd_groupnorm: C=%d too large", C);
+  // stats scratch layout: [n_img*C*2] sums followed by [n_img*C*2] (scale, shift)
+  float* sums = a->stats;
+  float* ss = a->stats + (size_t)a->n_img * C * 2;
+  DD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)a->n_img * C, stream));
+  const int sms = num_sms();
   {
+    // enough CTAs to fill the machine, few enough that the per-CTA atomics stay negligible
+    int per_img = (2 * sms + a->n_img - 1) / a->n_img;
+    if (per_img < 1) per_img = 1;
+    int rows_per_cta = (HW + per_img - 1) / per_img;
+    const int min_rows = rpi * 4;
+    if (rows_per_cta < min_rows) rows_per_cta = min_rows;
     dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, a->n_img);
-    gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1,
-                                                  reinterpret_cast<const bf16*>(a->x2), a->x2_ld, C, HW,
-                                                  rows_per_cta, a->stats);
+    const size_t smem = sizeof(float) * 2 * (size_t)C * rpi;
+    static bool attr = false;
+    if (!attr) {
+      DD_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr = true;
+    }
+    DD_CHECK(smem <= 96 * 1024, -1, "dd_groupnorm: reduction buffer too large");
+    gn_stats_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1,
+                                                     reinterpret_cast<const bf16*>(a->x2), a->x2_ld, C, HW,
+                                                     rows_per_cta, sums);
     DD_CUDA(cudaGetLastError());
   }
+  gn_finalize_kernel<<<a->n_img, 32, 0, stream>>>(sums, a->gamma, a->beta, ss, C, a->groups, HW, a->eps);
+  DD_CUDA(cudaGetLastError());
   {
     const int rows_img = a->padded_out ? (a->h + 1) * (a->w + 1) : HW;
-    rows_per_cta = rpi * 16;
+    int per_img = (8 * sms + a->n_img - 1) / a->n_img;
+    if (per_img < 1) per_img = 1;
+    int rows_per_cta = (rows_img + per_img - 1) / per_img;
+    if (rows_per_cta < rpi * 4) rows_per_cta = rpi * 4;
     dim3 grid((rows_img + rows_per_cta - 1) / rows_per_cta, a->n_img);
-    const size_t smem = sizeof(float) * 2 * C;
-    gn_apply_kernel<<<grid, threads, smem, stream>>>(
+    gn_apply_kernel<<<grid, threads, 0, stream>>>(
         reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1, reinterpret_cast<const bf16*>(a->x2),
-        a->x2_ld, C, a->h, a->w, a->groups, a->eps, a->gamma, a->beta, a->stats, a->silu, a->padded_out,
-        reinterpret_cast<bf16*>(a->out), a->out_ld, rows_per_cta);
+        a->x2_ld, C, a->h, a->w, ss, a->silu, a->padded_out, reinterpret_cast<bf16*>(a->out), a->out_ld,
+        rows_per_cta);
     DD_CUDA(cudaGetLastError());
   }
-  count_launch(2);
+  count_launch(3);
   return 0;
 }
 

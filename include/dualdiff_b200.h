@@ -72,7 +72,7 @@ DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
  * conv_norm_out + conv_act (networks/unet_2d_condition_multiview.py:519-521).
  * Input: compact channels-last rows [n_img*H*W, c1] (+ optional second source [.., c2], concatenated along
  * channels = the up-block skip concat).  Output: compact rows, or (padded_out=1) the zero-haloed layout
- * [n_img][(H+1)][(W+1)][C] that dd_gemm(taps=9) consumes.  stats: fp32 scratch [n_img*C*2]. */
+ * [n_img][(H+1)][(W+1)][C] that dd_gemm(taps=9) consumes.  stats: fp32 scratch [n_img*C*4] (per-channel sums, then per-channel scale/shift). */
 typedef struct dd_groupnorm_args {
   const void* x1; const void* x2; void* out; float* stats;
   const float* gamma; const float* beta;
