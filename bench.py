@@ -176,9 +176,20 @@ def run_ours(args):
                      [inp["cond_bg"], inp["cond_fg"]], num_inference_steps=4)
         for _ in range(2):
             den2.step(0)
+        torch.cuda.synchronize()
+        # give the host a head start so the per-launch event intervals are pure device time (kernels back to back)
+        torch.cuda._sleep(int(0.08 * 1.9e9))
         ops.profile_start()
         den2.step(1)
         rec = ops.profile_stop()
+        if os.environ.get("DD_BENCH_SHAPES"):
+            agg = {}
+            for name, t_ms, fl, by, tag in rec:
+                a = agg.setdefault((name, tag), [0.0, 0, 0.0])
+                a[0] += t_ms; a[1] += 1; a[2] += fl
+            with open(os.environ["DD_BENCH_SHAPES"], "w") as fh:
+                for (name, tag), (t_ms, cnt, fl) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+                    fh.write(f"{name:16s} {tag:28s} x{cnt:3d} {t_ms:8.3f} ms  {fl / max(t_ms, 1e-9) / 1e9:8.1f} TFLOP/s\n")
         fam = {}
         for name, t_ms, fl, by, tag in rec:
             f = fam.setdefault(name, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))

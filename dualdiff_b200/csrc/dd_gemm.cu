@@ -49,13 +49,15 @@ struct GemmDev {
   long long res2_ld;
   int geglu;
   int act;      // 0 none, 1 SiLU (applied last)
+  int tma_epi;  // 1: epilogue moves residual/output tiles with TMA (plain GEMM, bf16 out)
   int n_store;  // number of valid output columns (N, or N/2 for GEGLU)
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                    const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmR1, const GemmDev p) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int ACC_COLS = (BN < 32) ? 32 : BN;      // columns per accumulator buffer
@@ -64,7 +66,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 4];
   __shared__ uint32_t tmem_ptr_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -79,6 +81,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&tmOut);
+      tma_prefetch_desc(&tmR1);
+    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -87,6 +93,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp
     }
+    for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -170,6 +177,137 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int HW1 = (p.conv_H + 1) * pitch;
     const uint32_t stage_buf = smem_base + stages * STAGE_BYTES + q * EPI_WARP_BYTES;
     const int OUTW = p.geglu ? BN / 2 : BN;
+    if (p.tma_epi) {
+      // ---------------- TMA epilogue (plain GEMM, bf16 out): everything stays in the row-per-thread domain ----------
+      // per 64-column chunk: TMEM -> regs, + bias, + residual tile (TMA-loaded into swizzled smem, prefetched one
+      // chunk ahead), activation, bf16 pack -> swizzled smem tile -> TMA store.  No strided global access at all.
+      if constexpr (BN % 64 == 0) {
+        const uint32_t out_stage = stage_buf;          // 32 rows x 128 B, SWIZZLE_128B
+        const uint32_t r1_stage = stage_buf + 4096;
+        const uint32_t r1_bar = smem_u32(&bars[20 + q]);
+        const bool has_r1 = p.res1 != nullptr;
+        const uint32_t xr = (uint32_t)(lane & 7);
+        uint32_t r1_phase = 0;
+        constexpr int NCH = (BN / 64);
+        const int nch = p.geglu ? NCH / 2 : NCH;
+        auto r1_issue = [&](int t, int ch) {
+          const int tm0 = (t / p.n_tiles) * BM + q * 32;
+          const int tn0 = (t % p.n_tiles) * BN + ch * 64;
+          mbar_arrive_expect_tx(r1_bar, 4096);
+          tma_load_2d(r1_stage, &tmR1, r1_bar, tn0, tm0);
+        };
+        if (has_r1 && lane == 0 && (int)blockIdx.x < total_tiles) r1_issue(blockIdx.x, 0);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+          const int m0 = (tile / p.n_tiles) * BM;
+          const int n0 = (tile % p.n_tiles) * BN;
+          const int nout0 = p.geglu ? (n0 / BN) * (BN / 2) : n0;
+          const uint32_t as = local_tile & 1;
+          const uint32_t aph = (local_tile >> 1) & 1;
+          mbar_wait(tfull_bar + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+          for (int ch = 0; ch < nch; ++ch) {
+            const int c = ch * 64;
+            uint32_t pk[32];  // 64 bf16 outputs of this row
+#pragma unroll
+            for (int h = 0; h < 64; h += 32) {
+              uint32_t a[32];
+              tmem_ld_32x32(tmem_acc + c + h, a);
+              if (p.geglu) {
+                uint32_t g[32];
+                tmem_ld_32x32(tmem_acc + BN / 2 + c + h, g);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+                  if (p.bias) {
+                    bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h + j));
+                    bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + h + j));
+                  }
+                  const float v0 = (__uint_as_float(a[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
+                  const float v1 = (__uint_as_float(a[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
+                  const float v2 = (__uint_as_float(a[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
+                  const float v3 = (__uint_as_float(a[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
+                  pk[(h + j) >> 1] = pack_bf16(v0, v1);
+                  pk[((h + j) >> 1) + 1] = pack_bf16(v2, v3);
+                }
+              } else {
+                tmem_ld_wait();
+                if (p.bias) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h + j));
+                    a[j] = __float_as_uint(__uint_as_float(a[j]) + b.x);
+                    a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + b.y);
+                    a[j + 2] = __float_as_uint(__uint_as_float(a[j + 2]) + b.z);
+                    a[j + 3] = __float_as_uint(__uint_as_float(a[j + 3]) + b.w);
+                  }
+                }
+                if (has_r1) {
+                  if (h == 0) {
+                    mbar_wait(r1_bar, r1_phase);
+                    r1_phase ^= 1;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {  // 4 x 16 B = 32 bf16 of this row
+                    const uint32_t uu = (uint32_t)((h >> 3) + u);
+                    uint32_t t0, t1, t2, t3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3)
+                                 : "r"(r1_stage + lane * 128 + ((uu ^ xr) << 4)));
+                    const uint32_t w[4] = {t0, t1, t2, t3};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = unpack_bf16(w[e]);
+                      const int j = u * 8 + e * 2;
+                      a[j] = __float_as_uint(__uint_as_float(a[j]) + f.x);
+                      a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + f.y);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float v0 = __uint_as_float(a[j]), v1 = __uint_as_float(a[j + 1]);
+                  if (p.act == 1) {
+                    v0 = silu_f(v0);
+                    v1 = silu_f(v1);
+                  }
+                  pk[(h + j) >> 1] = pack_bf16(v0, v1);
+                }
+              }
+            }
+            // residual tile consumed: prefetch the next one (next chunk, or chunk 0 of this CTA's next tile)
+            if (has_r1) {
+              __syncwarp();
+              if (lane == 0) {
+                if (ch + 1 < nch) r1_issue(tile, ch + 1);
+                else if (tile + (int)gridDim.x < total_tiles) r1_issue(tile + gridDim.x, 0);
+              }
+            }
+            // the previous TMA store must have finished reading the staging tile
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t addr = out_stage + lane * 128 + ((((uint32_t)u) ^ xr) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
+                           "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, out_stage, nout0 + c, m0 + q * 32);  // clipped at [M, n_store] by the tensor map
+              bulk_commit();
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+        }
+        if (lane == 0) bulk_wait0();
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
       const int m0 = (tile / p.n_tiles) * BM;
       const int n0 = (tile % p.n_tiles) * BN;
@@ -337,7 +475,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                       GemmDev p, cudaStream_t stream) {
+                       const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
   int stages = (227 * 1024 - 3072 - 4 * EPI_WARP_BYTES) / STAGE_BYTES;
   if (stages > 8) stages = 8;
@@ -357,9 +495,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CU
   int grid = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, p);
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmR1, p);
   DD_CUDA(cudaGetLastError());
   return 0;
+}
+
+static int pick_bn_tma(int N, int geglu) {
+  // TMA epilogue moves 64-column boxes -> tile widths are multiples of 64.  Small-K GEMMs are bound by operand
+  // traffic ~ n_tiles * (128 + BN): prefer the widest tile unless it wastes a whole extra tile of columns.
+  if (geglu) return 256;
+  if (N <= 64) return 64;
+  const int cands[] = {256, 192, 128};
+  int best = 128;
+  long best_cost = 1L << 60;
+  for (int bn : cands) {
+    const long cost = (long)((N + bn - 1) / bn) * (128 + bn);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 static int pick_bn(int N, int geglu, int force) {
@@ -404,8 +560,12 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   DD_CHECK(a->out_ld >= n_store, -1, "dd_gemm: out_ld too small");
   if (n_store % 8 != 0) DD_CHECK(a->res1 == nullptr || true, -1, "unreachable");
 
-  const int bn = pick_bn(a->N, a->geglu, a->force_bn);
-  CUtensorMap tmA, tmA2, tmB;
+  const bool tma_ok = a->taps == 1 && !a->out_f32 && n_store % 8 == 0 && a->res2 == nullptr && a->rowvec == nullptr &&
+                      a->out_ld % 8 == 0 && (a->res1 == nullptr || (a->res1_ld % 8 == 0 && ((uintptr_t)a->res1 & 15) == 0)) &&
+                      a->N > 32 && (a->force_bn == 0 || a->force_bn % 64 == 0) && !a->no_tma_epilogue;
+  int bn = pick_bn(a->N, a->geglu, a->force_bn);
+  if (tma_ok && a->force_bn == 0) bn = pick_bn_tma(a->N, a->geglu);
+  CUtensorMap tmA, tmA2, tmB, tmOut, tmR1;
   int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, BM, BK);
   if (rc) return rc;
   if (a->a2 != nullptr) {
@@ -417,7 +577,21 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   rc = make_tmap_2d_bf16(&tmB, a->w, (uint64_t)a->N, (uint64_t)a->K * a->taps, (uint64_t)a->w_ld, bn, BK);
   if (rc) return rc;
 
+  if (tma_ok) {
+    rc = make_tmap_2d_bf16(&tmOut, a->out, (uint64_t)a->M, (uint64_t)n_store, (uint64_t)a->out_ld, 32, 64);
+    if (rc) return rc;
+    if (a->res1 != nullptr) {
+      rc = make_tmap_2d_bf16(&tmR1, a->res1, (uint64_t)a->M, (uint64_t)n_store, (uint64_t)a->res1_ld, 32, 64);
+      if (rc) return rc;
+    } else {
+      tmR1 = tmOut;
+    }
+  } else {
+    tmOut = tmA;
+    tmR1 = tmA;
+  }
   GemmDev p;
+  p.tma_epi = tma_ok ? 1 : 0;
   p.M = a->M; p.N = a->N; p.K = a->K; p.K1 = K1; p.taps = a->taps;
   p.conv_H = a->conv_h; p.conv_W = a->conv_w;
   p.out = a->out; p.out_ld = a->out_ld; p.out_f32 = a->out_f32;
@@ -428,12 +602,12 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   p.geglu = a->geglu; p.act = a->act; p.n_store = n_store;
   p.m_tiles = p.n_tiles = p.stages = 0;
   switch (bn) {
-    case 32: return launch_gemm<32>(tmA, tmA2, tmB, p, stream);
-    case 64: return launch_gemm<64>(tmA, tmA2, tmB, p, stream);
-    case 128: return launch_gemm<128>(tmA, tmA2, tmB, p, stream);
-    case 160: return launch_gemm<160>(tmA, tmA2, tmB, p, stream);
-    case 192: return launch_gemm<192>(tmA, tmA2, tmB, p, stream);
-    case 256: return launch_gemm<256>(tmA, tmA2, tmB, p, stream);
+    case 32: return launch_gemm<32>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 64: return launch_gemm<64>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 128: return launch_gemm<128>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 160: return launch_gemm<160>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 192: return launch_gemm<192>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 256: return launch_gemm<256>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
     default: DD_CHECK(false, -1, "dd_gemm: unsupported tile width %d", bn);
   }
   return 0;

@@ -64,6 +64,7 @@ typedef struct dd_gemm_args {
                          column groups per 256-wide tile (dd pack_geglu in dualdiff_b200/packing.py) */
   int force_bn;       /* 0 = auto tile width; testing hook                                        */
   int act;            /* 0 none, 1 SiLU applied after bias/residuals (ControlNetConditioningEmbedding) */
+  int no_tma_epilogue;/* testing hook: 1 forces the register/smem-transpose epilogue                 */
 } dd_gemm_args;
 DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 

@@ -75,3 +75,20 @@ def test_conv3x3_implicit_gemm(n, H, W, ci, co):
     out = ops.gemm(packing.to_padded(x), packing.pack_conv3x3(w), bias=bias, taps=9, conv_hw=(H, W), n_img=n)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co)
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K,res,act", [(134400 // 8, 320, 320, True, 0), (1000, 1088, 320, False, 0), (4200, 640, 640, True, 1),
+                                           (257, 1280, 1280, True, 0), (130, 384, 320, False, 0), (5000, 72, 320, True, 0)])
+def test_tma_epilogue_equals_register_epilogue(M, N, K, res, act):
+    """plain bf16 GEMMs take the TMA load/store epilogue; it must agree with the register path bit-for-bit-ish"""
+    from dualdiff_b200 import ops
+    a = _mk((M, K), 1); w = _mk((N, K), 2, K ** -0.5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    r1 = _mk((M, N), 4) if res else None
+    out_tma = ops.gemm(a, w, bias=bias, res1=r1, act=act)
+    out_reg = ops.gemm(a, w, bias=bias, res1=r1, act=act, no_tma_epilogue=True)
+    ref = a.float() @ w.float().t() + bias + (r1.float() if res else 0)
+    if act:
+        ref = F.silu(ref)
+    assert _rel(out_tma, ref) < 1e-2 and _rel(out_reg, ref) < 1e-2
+    assert (out_tma.float() - out_reg.float()).abs().max() <= 2e-2 * ref.abs().max()
