@@ -27,7 +27,8 @@ namespace dd {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 192;      // 2 + 4 epilogue warps (register / smem-transpose epilogue)
+static constexpr int GEMM_THREADS_MAX = 320;  // 2 + 8 epilogue warps (TMA epilogue)
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARP_BYTES = 32 * 64 * 4;  // per-epilogue-warp transpose buffer (32 rows x 64 fp32)
 
@@ -54,7 +55,7 @@ struct GemmDev {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_MAX, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmR1, const GemmDev p) {
@@ -66,7 +67,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 4];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 8];
   __shared__ uint32_t tmem_ptr_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -91,9 +92,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * s, (blockDim.x - 64) / 32);  // one arrive per epilogue warp
     }
-    for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
+    for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -182,62 +183,72 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // per 64-column chunk: TMEM -> regs, + bias, + residual tile (TMA-loaded into swizzled smem, prefetched one
       // chunk ahead), activation, bf16 pack -> swizzled smem tile -> TMA store.  No strided global access at all.
       if constexpr (BN % 64 == 0) {
-        const uint32_t out_stage = stage_buf;          // 32 rows x 128 B, SWIZZLE_128B
-        const uint32_t r1_stage = stage_buf + 4096;
-        const uint32_t r1_bar = smem_u32(&bars[20 + q]);
+        // TMA mode runs 8 epilogue warps: warps 2-5 take the even 64-column chunks, warps 6-9 the odd ones
+        // (two warps per TMEM lane quarter -> two warps per scheduler, hiding each other's TMEM/smem latency).
+        const int half = (warp - 2) >> 2;
+        const uint32_t my_stage = smem_base + stages * STAGE_BYTES + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+        const uint32_t out_stage = my_stage;           // 32 rows x 128 B, SWIZZLE_128B
+        const uint32_t r1_stage = my_stage + 4096;
+        const uint32_t r1_bar = smem_u32(&bars[20 + (warp - 2)]);
         const bool has_r1 = p.res1 != nullptr;
+        const bool geglu = p.geglu != 0;
+        const int act = p.act;
+        const float* __restrict__ bias = p.bias;
         const uint32_t xr = (uint32_t)(lane & 7);
         uint32_t r1_phase = 0;
-        constexpr int NCH = (BN / 64);
-        const int nch = p.geglu ? NCH / 2 : NCH;
+        const int nch = geglu ? (BN / 128) : (BN / 64);
+        const int n_epi_halves = (int)(blockDim.x - 64) / 128;   // 2 in TMA mode
         auto r1_issue = [&](int t, int ch) {
           const int tm0 = (t / p.n_tiles) * BM + q * 32;
           const int tn0 = (t % p.n_tiles) * BN + ch * 64;
           mbar_arrive_expect_tx(r1_bar, 4096);
           tma_load_2d(r1_stage, &tmR1, r1_bar, tn0, tm0);
         };
-        if (has_r1 && lane == 0 && (int)blockIdx.x < total_tiles) r1_issue(blockIdx.x, 0);
+        if (has_r1 && lane == 0 && (int)blockIdx.x < total_tiles && half < nch) r1_issue(blockIdx.x, half);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
           const int m0 = (tile / p.n_tiles) * BM;
           const int n0 = (tile % p.n_tiles) * BN;
-          const int nout0 = p.geglu ? (n0 / BN) * (BN / 2) : n0;
+          const int nout0 = geglu ? (n0 / BN) * (BN / 2) : n0;
           const uint32_t as = local_tile & 1;
           const uint32_t aph = (local_tile >> 1) & 1;
           mbar_wait(tfull_bar + 8 * as, aph);
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-          for (int ch = 0; ch < nch; ++ch) {
+          for (int ch = half; ch < nch; ch += n_epi_halves) {
             const int c = ch * 64;
-            uint32_t pk[32];  // 64 bf16 outputs of this row
-#pragma unroll
+            if (lane == 0) bulk_wait_read0();   // the previous TMA store has finished reading the staging tile
+            __syncwarp();
+            if (has_r1) {
+              mbar_wait(r1_bar, r1_phase);
+              r1_phase ^= 1;
+            }
+#pragma unroll 1
             for (int h = 0; h < 64; h += 32) {
               uint32_t a[32];
               tmem_ld_32x32(tmem_acc + c + h, a);
-              if (p.geglu) {
+              if (geglu) {
                 uint32_t g[32];
                 tmem_ld_32x32(tmem_acc + BN / 2 + c + h, g);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-                  if (p.bias) {
-                    bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h + j));
-                    bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + h + j));
+                  if (bias) {
+                    bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
+                    bg = __ldg(reinterpret_cast<const float4*>(bias + n0 + BN / 2 + c + h + j));
                   }
-                  const float v0 = (__uint_as_float(a[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x);
-                  const float v1 = (__uint_as_float(a[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y);
-                  const float v2 = (__uint_as_float(a[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z);
-                  const float v3 = (__uint_as_float(a[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w);
-                  pk[(h + j) >> 1] = pack_bf16(v0, v1);
-                  pk[((h + j) >> 1) + 1] = pack_bf16(v2, v3);
+                  a[j] = __float_as_uint((__uint_as_float(a[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x));
+                  a[j + 1] = __float_as_uint((__uint_as_float(a[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y));
+                  a[j + 2] = __float_as_uint((__uint_as_float(a[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z));
+                  a[j + 3] = __float_as_uint((__uint_as_float(a[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w));
                 }
               } else {
                 tmem_ld_wait();
-                if (p.bias) {
+                if (bias) {
 #pragma unroll
                   for (int j = 0; j < 32; j += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h + j));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
                     a[j] = __float_as_uint(__uint_as_float(a[j]) + b.x);
                     a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + b.y);
                     a[j + 2] = __float_as_uint(__uint_as_float(a[j + 2]) + b.z);
@@ -245,10 +256,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   }
                 }
                 if (has_r1) {
-                  if (h == 0) {
-                    mbar_wait(r1_bar, r1_phase);
-                    r1_phase ^= 1;
-                  }
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {  // 4 x 16 B = 32 bf16 of this row
                     const uint32_t uu = (uint32_t)((h >> 3) + u);
@@ -265,34 +272,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                   }
                 }
+                if (act == 1) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  float v0 = __uint_as_float(a[j]), v1 = __uint_as_float(a[j + 1]);
-                  if (p.act == 1) {
-                    v0 = silu_f(v0);
-                    v1 = silu_f(v1);
-                  }
-                  pk[(h + j) >> 1] = pack_bf16(v0, v1);
+                  for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(silu_f(__uint_as_float(a[j])));
                 }
               }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t uu = (uint32_t)((h >> 3) + u);
+                const uint32_t addr = out_stage + lane * 128 + ((uu ^ xr) << 4);
+                const uint32_t k0 = pack_bf16(__uint_as_float(a[8 * u]), __uint_as_float(a[8 * u + 1]));
+                const uint32_t k1 = pack_bf16(__uint_as_float(a[8 * u + 2]), __uint_as_float(a[8 * u + 3]));
+                const uint32_t k2 = pack_bf16(__uint_as_float(a[8 * u + 4]), __uint_as_float(a[8 * u + 5]));
+                const uint32_t k3 = pack_bf16(__uint_as_float(a[8 * u + 6]), __uint_as_float(a[8 * u + 7]));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(k0), "r"(k1), "r"(k2), "r"(k3)
+                             : "memory");
+              }
             }
-            // residual tile consumed: prefetch the next one (next chunk, or chunk 0 of this CTA's next tile)
+            // residual tile consumed: prefetch this warp's next one (same tile, or its first chunk of the next tile)
             if (has_r1) {
               __syncwarp();
               if (lane == 0) {
-                if (ch + 1 < nch) r1_issue(tile, ch + 1);
-                else if (tile + (int)gridDim.x < total_tiles) r1_issue(tile + gridDim.x, 0);
+                if (ch + n_epi_halves < nch) r1_issue(tile, ch + n_epi_halves);
+                else if (tile + (int)gridDim.x < total_tiles && half < nch) r1_issue(tile + gridDim.x, half);
               }
-            }
-            // the previous TMA store must have finished reading the staging tile
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t addr = out_stage + lane * 128 + ((((uint32_t)u) ^ xr) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]),
-                           "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3])
-                           : "memory");
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -477,13 +480,14 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                        const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
   constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
-  int stages = (227 * 1024 - 3072 - 4 * EPI_WARP_BYTES) / STAGE_BYTES;
+  const int epi_warps = p.tma_epi ? 8 : 4;
+  int stages = (227 * 1024 - 3072 - epi_warps * EPI_WARP_BYTES) / STAGE_BYTES;
   if (stages > 8) stages = 8;
   const int iters = p.taps * ((p.K + BK - 1) / BK);
   if (stages > iters && iters >= 2) stages = iters;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 4 * EPI_WARP_BYTES + 1024;
+  const size_t smem = (size_t)stages * STAGE_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -495,7 +499,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CU
   int grid = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmR1, p);
+  gemm_tcgen05_kernel<BN><<<grid, p.tma_epi ? GEMM_THREADS_MAX : GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmR1, p);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
