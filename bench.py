@@ -211,6 +211,8 @@ def run_ours(args):
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     value = world * B * K / (ms * 1e-3)
     pk = peaks()
@@ -236,7 +238,9 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sds, budget_s=args.cpu_budget)
-    print(json.dumps(out))
+    emit(out)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -301,10 +305,29 @@ def run_reference(args):
            "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """the contract is ONE JSON line on stdout: route everything else written to fd 1 (NCCL's version banner,
+    library chatter) to stderr and keep the real stdout for the final line"""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
