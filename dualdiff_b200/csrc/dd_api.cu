@@ -95,6 +95,8 @@ int dd_layernorm(const dd_layernorm_args* args, void* stream) {
   return dd::layernorm_run(args, reinterpret_cast<cudaStream_t>(stream));
 }
 int dd_attention(const dd_attention_args* args, void* stream) {
-  return dd::attention_run(args, reinterpret_cast<cudaStream_t>(stream));
+  int rc = dd::attention_run(args, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) dd::count_launch();
+  return rc;
 }
 }

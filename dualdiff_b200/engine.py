@@ -226,6 +226,8 @@ class StepCtx:
     text_kv: Dict[str, torch.Tensor] = field(default_factory=dict)   # attn2 prefix -> [n*Lk, 8*dp + C]
     lk: int = 0
     kv_map: Optional[torch.Tensor] = None
+    view_shard: Optional[object] = None   # sharding.ViewShard when camera views are split across ranks
+    n_outer: int = 0                      # scenes x CFG halves (sharded mode)
 
 
 def time_embedding(P, t: torch.Tensor):
@@ -281,9 +283,20 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
     # 3. cross-view attention over the two ring neighbours (blocks.py:190-222)
     if multiview:
         ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
-        qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
-        a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
-                          k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
+        if ctx.view_shard is None:
+            qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
+            a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
+        else:
+            # camera views sharded across ranks: project locally, then fetch the two halo views' rows from the ring
+            # neighbours straight into the tail of the projection buffer (the only exchange step of the path)
+            vs = ctx.view_shard
+            wq = P[p + ".attn4.qkv.w"].shape[0]
+            buf = torch.empty((vs.kv_rows(ctx.n_outer) * T, wq), device=h.device, dtype=BF)
+            ops.gemm(ln, P[p + ".attn4.qkv.w"], out=buf[: n * T])
+            vs.exchange(buf, ctx.n_outer, T)
+            a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=vs.kv_rows(ctx.n_outer), lq=T, lk=T, heads=HEADS,
+                              head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
     # 4. GEGLU feed-forward (blocks.py:225-236)
     ln = ops.layernorm(h, P[p + ".norm3.g"], P[p + ".norm3.b"])

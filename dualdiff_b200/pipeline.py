@@ -20,14 +20,16 @@ from .scheduler import UniPCMultistepScheduler
 
 
 class DualDiffDenoiser:
-    def __init__(self, unet, controlnets, scheduler=None, guidance_scale: float = 2.0, use_cuda_graph: bool = True):
+    def __init__(self, unet, controlnets, scheduler=None, guidance_scale: float = 2.0, use_cuda_graph: bool = True,
+                 view_shard=None):
         assert len(controlnets) == 2, "dual branch: [controlnet_bg, controlnet_fg]"
         self.unet, self.nets = unet, list(controlnets)
         self.guidance_scale = guidance_scale
         self.cfg = guidance_scale > 1.0          # pipeline: do_classifier_free_guidance = guidance_scale > 1
         self.scheduler = scheduler if scheduler is not None else UniPCMultistepScheduler()
         self.scheduler.guidance_scale = guidance_scale
-        self.use_cuda_graph = use_cuda_graph
+        self.view_shard = view_shard               # sharding.ViewShard: camera views split across ranks (config 4)
+        self.use_cuda_graph = use_cuda_graph and view_shard is None   # the K/V exchange runs eagerly on NCCL
         self._graph = None
         self.device = None
 
@@ -37,6 +39,14 @@ class DualDiffDenoiser:
         """latents (B, 6, 4, h, w) fp32; prompt_embeds (2B, 77, 768) uncond first (or (B, ...) without CFG);
         camera_param (B, 6, 3, 7); bboxes_3d_data = [bg boxes, fg map vectors]; images = [bg panorama
         (B, 3, 8h, 48w), fg ORS (B*6, 320, h, w)]."""
+        if self.view_shard is not None:   # every rank passes the full scene inputs and keeps its own camera views
+            from .sharding import slice_views
+            full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
+                        cond_fg=images[1])
+            loc = slice_views(full, self.view_shard.views, latents.shape[1])
+            latents, camera_param = loc["latents"], loc["camera_param"]
+            bboxes_3d_data = [loc["boxes_bg"], bboxes_3d_data[1]]
+            images = [loc["cond_bg"], loc["cond_fg"]]
         dev = latents.device
         if dev.type != "cuda":
             raise RuntimeError("dualdiff_b200 has no CPU path: inputs must be CUDA tensors")
@@ -63,7 +73,11 @@ class DualDiffDenoiser:
         self.preps = [net.prepare_condition(cam, text, boxes[i], conds[i], H, W) for i, net in enumerate(self.nets)]
         Pu = self.unet._packed
         self.unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, self.preps[0].enc_rows)  # tokens of branch 0
-        self.kv_map = engine.make_kv_map(n, n_cam, dev)
+        if self.view_shard is None:
+            self.kv_map = engine.make_kv_map(n, n_cam, dev)
+        else:
+            assert self.view_shard.v_loc == n_cam
+            self.kv_map = self.view_shard.kv_map(G * B, dev)
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         self.coef_table = self.scheduler.coef_table(dev)
         self.t_table = self.scheduler.timesteps.to(device=dev, dtype=torch.float32)
@@ -91,7 +105,8 @@ class DualDiffDenoiser:
         Pu = self.unet._packed
         temb = engine.time_embedding(Pu, self.t_cur)
         ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                             lk=self.preps[0].lk, kv_map=self.kv_map)
+                             lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
+                             n_outer=self.G * self.B)
         eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
         ops.cfg_sched_step(eps, self.latents, self.last, self.m0, self.m1, self.coef_cur, n_img=B6, c=4, hw=H * W,
                            cfg=self.cfg, eps_nchw=False)

@@ -24,3 +24,84 @@ def reduce_max_ms(ms: float, device=None) -> float:
     t = torch.tensor([ms], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+class ViewShard:
+    """Camera-view sharding inside a scene (BASELINE config 4).
+
+    Rank r owns the V_loc = n_cam / world consecutive views [r*V_loc, (r+1)*V_loc) of every scene (and CFG half).
+    Convolutions, norms, self- and text-attention and the ControlNet branches are per image -> unit-local.  The one
+    exchange step of the path is the cross-view attention (networks/blocks.py:190-222): view v attends to views
+    v-1 and v+1 (ring, configs/dataset/Nuscenes.yaml:27-33), so per transformer block each rank sends the projected
+    rows of its FIRST view to the left rank and of its LAST view to the right rank (grouped NCCL send/recv over
+    NVLink) and receives the two halo views into the tail of its own projection buffer; the attention kernel then
+    addresses local and halo images uniformly through `kv_map`.
+    """
+
+    def __init__(self, rank: int, world: int, n_cam: int = 6, group=None):
+        if n_cam % world != 0:
+            raise ValueError(f"world size {world} must divide the number of camera views {n_cam}")
+        self.rank, self.world, self.n_cam, self.group = rank, world, n_cam, group
+        self.v_loc = n_cam // world
+        self.left = (rank - 1) % world
+        self.right = (rank + 1) % world
+
+    @property
+    def views(self):
+        return list(range(self.rank * self.v_loc, (self.rank + 1) * self.v_loc))
+
+    def kv_rows(self, n_outer: int) -> int:
+        """images in the K/V buffer: local images followed by the left and right halo views of every scene"""
+        return n_outer * self.v_loc + 2 * n_outer
+
+    def kv_map(self, n_outer: int, device=None) -> torch.Tensor:
+        """int32 [n_outer*V_loc, 2]: K/V image index of the (left, right) neighbour of every local image"""
+        v, n_loc = self.v_loc, n_outer * self.v_loc
+        rows = []
+        for o in range(n_outer):
+            for j in range(v):
+                left = o * v + (j - 1) if j > 0 else n_loc + o                   # left halo block
+                right = o * v + (j + 1) if j < v - 1 else n_loc + n_outer + o     # right halo block
+                rows.append([left, right])
+        return torch.tensor(rows, dtype=torch.int32, device=device)
+
+    def exchange(self, buf: torch.Tensor, n_outer: int, T: int) -> None:
+        """buf: [(n_loc + 2*n_outer) * T, W] projection rows; fills the halo tail in place."""
+        import torch.distributed as dist
+        v, W = self.v_loc, buf.shape[1]
+        n_loc = n_outer * v
+        local = buf[: n_loc * T].view(n_outer, v, T, W)
+        send_first = local[:, 0].contiguous()        # my first view  -> right halo of the left rank
+        send_last = local[:, v - 1].contiguous()     # my last view   -> left halo of the right rank
+        halo_left = buf[n_loc * T:(n_loc + n_outer) * T].view(n_outer, T, W)
+        halo_right = buf[(n_loc + n_outer) * T:].view(n_outer, T, W)
+        if self.world == 1:
+            halo_left.copy_(send_last)
+            halo_right.copy_(send_first)
+            return
+        # posting order matters when left == right (world 2): the peer's sends arrive in the order (first view,
+        # last view), which are my (right halo, left halo)
+        ops = [dist.P2POp(dist.isend, send_first, self.left, self.group),
+               dist.P2POp(dist.isend, send_last, self.right, self.group),
+               dist.P2POp(dist.irecv, halo_right, self.right, self.group),
+               dist.P2POp(dist.irecv, halo_left, self.left, self.group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+def slice_views(inputs: dict, views, n_cam: int = 6) -> dict:
+    """select the camera views of one rank from full-scene step inputs (layouts of synthetic.make_inputs /
+    dataset/utils.py:390-445): per-view tensors are sliced, view-shared ones kept."""
+    idx = torch.as_tensor(list(views))
+    out = dict(inputs)
+    out["latents"] = inputs["latents"][:, idx].contiguous()
+    out["camera_param"] = inputs["camera_param"][:, idx].contiguous()
+    bb = inputs["boxes_bg"]
+    out["boxes_bg"] = {k: (v[:, idx].contiguous() if v.shape[1] == n_cam else v) for k, v in bb.items()}
+    cb = inputs["cond_bg"]                                   # (B, 3, H, n_cam*W) panorama
+    w = cb.shape[-1] // n_cam
+    out["cond_bg"] = torch.cat([cb[..., v * w:(v + 1) * w] for v in views], dim=-1).contiguous()
+    cf = inputs["cond_fg"]                                   # (B*n_cam, 320, h, w)
+    B = cf.shape[0] // n_cam
+    out["cond_fg"] = cf.reshape(B, n_cam, *cf.shape[1:])[:, idx].reshape(B * len(views), *cf.shape[1:]).contiguous()
+    return out

@@ -1,0 +1,61 @@
+"""torchrun entry: camera views sharded over WORLD_SIZE GPUs with the neighbour K/V exchange over NCCL (config 4)
+must reproduce the single-GPU step.  Rank 0 prints 'VIEWSHARD OK ...' on success."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import common  # noqa: E402
+from dualdiff_b200 import synthetic as S  # noqa: E402
+from dualdiff_b200.pipeline import DualDiffDenoiser  # noqa: E402
+from dualdiff_b200.sharding import ViewShard  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    h, w = (int(x) for x in os.environ.get("LATENT", "28x50").split("x"))
+    B, steps = int(os.environ.get("SCENES", "1")), 2
+    unet, nets, _ = common.build_models()
+    for m in [unet] + nets:
+        m.pack(dev)
+    inp = common.to_dev(S.make_inputs(B, h, w, seed=1, L_bg=28, L_fg=32), dev)
+    args = (inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]],
+            [inp["cond_bg"], inp["cond_fg"]])
+    vs = ViewShard(rank, world)
+    den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, view_shard=vs)
+    den.prepare(*args, num_inference_steps=4)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        den.step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    shard = den.latents.reshape(B, vs.v_loc, 4, h, w)
+    # reference: the same two steps unsharded on this rank's GPU
+    ref = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=False)
+    ref.prepare(*args, num_inference_steps=4)
+    for i in range(steps):
+        ref.step(i)
+    full = ref.latents.reshape(B, 6, 4, h, w)[:, vs.views]
+    m = common.metrics(shard.float().cpu(), full.float().cpu())
+    t = torch.tensor([m["rel_l2"], ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ok = float(t[0]) < 2e-2
+        print(f"VIEWSHARD {'OK' if ok else 'FAIL'} world={world} latent={h}x{w} scenes={B} rel_l2(max over ranks)={float(t[0]):.3e} "
+              f"ms/step(max over ranks)={float(t[1]):.2f}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
