@@ -172,6 +172,7 @@ def run_ours(args):
     roof, breakdown = None, None
     if rank == 0:
         den2 = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=False)
+        den2.parallel_branches = False   # serial launch order: clean per-kernel device times
         den2.prepare(inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]],
                      [inp["cond_bg"], inp["cond_fg"]], num_inference_steps=4)
         for _ in range(2):

@@ -374,15 +374,21 @@ def prepare_text(P, layers, enc_rows):
 # UNet2DConditionModelMultiview.forward
 # ---------------------------------------------------------------------------------------------------
 def unet_forward(P, latents, n_outer, n_view, H, W, ctx: StepCtx, down_res: Optional[List[torch.Tensor]] = None,
-                 mid_res: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """returns eps as fp32 channels-last rows [n*H*W, 4]"""
+                 mid_res: Optional[torch.Tensor] = None, down_res2: Optional[List[torch.Tensor]] = None,
+                 mid_res2: Optional[torch.Tensor] = None, before_residuals=None) -> torch.Tensor:
+    """returns eps as fp32 channels-last rows [n*H*W, 4].  down_res2 / mid_res2: residuals of a second branch added
+    in the same pass (pipeline:422-429 sums the branches); before_residuals(): hook called right before the first
+    use of the residuals (stream join when the branches run concurrently with the UNet encoder)."""
     x = conv_in(P, latents, n_outer, n_view, H, W)
     x, skips = down_path(P, x, ctx, True)
-    if down_res is not None:  # unet_2d_condition_multiview.py:464-473
-        skips = [Act(ops.add_bf16(s.rows, r), s.n, s.H, s.W) for s, r in zip(skips, down_res)]
     x = mid_block(P, x, ctx, True)
+    if before_residuals is not None:
+        before_residuals()
+    if down_res is not None:  # unet_2d_condition_multiview.py:464-473
+        r2 = down_res2 if down_res2 is not None else [None] * len(down_res)
+        skips = [Act(ops.add_bf16(s.rows, r, r_), s.n, s.H, s.W) for s, r, r_ in zip(skips, down_res, r2)]
     if mid_res is not None:
-        x = Act(ops.add_bf16(x.rows, mid_res), x.n, x.H, x.W)
+        x = Act(ops.add_bf16(x.rows, mid_res, mid_res2), x.n, x.H, x.W)
     for i in range(4):
         for j in range(3):
             s = skips.pop()

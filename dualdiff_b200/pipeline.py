@@ -32,6 +32,11 @@ class DualDiffDenoiser:
         self.use_cuda_graph = use_cuda_graph and view_shard is None   # the K/V exchange runs eagerly on NCCL
         self._graph = None
         self.device = None
+        # The two condition branches and the UNet encoder are mutually independent until the skip/mid residual adds
+        # (unet_2d_condition_multiview.py:464-488): run them on three streams so the small low-resolution kernels
+        # (grids below one wave of 148 SMs) overlap instead of serialising.
+        self.parallel_branches = True
+        self._side = None
 
     # -------------------------------------------------------------------------------------------------
     def prepare(self, latents, prompt_embeds, camera_param, bboxes_3d_data: List[Dict[str, torch.Tensor]], images,
@@ -97,17 +102,41 @@ class DualDiffDenoiser:
     def _step_kernels(self):
         """one loop body (pipeline:381-504) on the current stream; reads t / coefficients from device buffers"""
         B6, H, W, G = self.B * self.n_cam, self.H, self.W, self.G
-        acc = None
-        for net, prep in zip(self.nets, self.preps):
-            down, mid = engine.controlnet_forward(net._packed, prep, self.latents, G, B6, H, W, self.t_cur,
-                                                  None if acc is None else acc)
-            acc = down + [mid]
         Pu = self.unet._packed
-        temb = engine.time_embedding(Pu, self.t_cur)
-        ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                             lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
-                             n_outer=self.G * self.B)
-        eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
+        if not self.parallel_branches:
+            acc = None
+            for net, prep in zip(self.nets, self.preps):
+                down, mid = engine.controlnet_forward(net._packed, prep, self.latents, G, B6, H, W, self.t_cur,
+                                                      None if acc is None else acc)
+                acc = down + [mid]
+            temb = engine.time_embedding(Pu, self.t_cur)
+            ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
+                                 n_outer=self.G * self.B)
+            eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
+        else:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = [torch.cuda.Stream(), torch.cuda.Stream()]
+            res = []
+            for net, prep, st in zip(self.nets, self.preps, self._side):
+                st.wait_stream(main)                       # fork
+                with torch.cuda.stream(st):
+                    down, mid = engine.controlnet_forward(net._packed, prep, self.latents, G, B6, H, W, self.t_cur, None)
+                for t in down + [mid]:
+                    t.record_stream(main)                  # consumed on the main stream after the join
+                res.append((down, mid))
+            temb = engine.time_embedding(Pu, self.t_cur)
+            ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
+                                 n_outer=self.G * self.B)
+
+            def join():
+                for st in self._side:
+                    main.wait_stream(st)
+
+            eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, res[0][0], res[0][1], res[1][0], res[1][1],
+                                      before_residuals=join)
         ops.cfg_sched_step(eps, self.latents, self.last, self.m0, self.m1, self.coef_cur, n_img=B6, c=4, hw=H * W,
                            cfg=self.cfg, eps_nchw=False)
         self.eps_rows = eps
