@@ -91,6 +91,7 @@ int dd_gemm(const dd_gemm_args* args, void* stream) {
 int dd_groupnorm(const dd_groupnorm_args* args, void* stream) {
   return dd::groupnorm_run(args, reinterpret_cast<cudaStream_t>(stream));
 }
+long long dd_groupnorm_scratch_floats(int n_img, int c, int hw) { return dd::groupnorm_scratch_floats(n_img, c, hw); }
 int dd_layernorm(const dd_layernorm_args* args, void* stream) {
   return dd::layernorm_run(args, reinterpret_cast<cudaStream_t>(stream));
 }

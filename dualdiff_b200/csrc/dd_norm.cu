@@ -12,8 +12,8 @@ namespace dd {
 
 // ---------------------------------------------------------------------------------------------------
 // GroupNorm pass 1: per (image, channel) sum / sum of squares.  A CTA owns a slab of rows of one image; threads
-// that share a channel octet reduce through shared memory, so only C*2 atomics leave each CTA.
-// stats[img][C][2] (fp32, pre-zeroed).
+// that share a channel octet reduce through shared memory and the CTA stores ONE partial row:
+// partial[img][cta][C][2] (fp32).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* __restrict__ x2,
@@ -66,35 +66,43 @@ gn_stats_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
     }
   }
   __syncthreads();
+  // one partial per CTA, plain stores: no atomics, no pre-zeroing, bit-reproducible run to run
+  float* part = stats + ((long long)img * gridDim.x + blockIdx.x) * 2 * C;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float acc = 0.f;
     for (int k = 0; k < rpi; ++k) acc += red[(size_t)k * 2 * C + i];
-    atomicAdd(stats + (long long)img * 2 * C + i, acc);
+    part[i] = acc;
   }
 }
 
-// pass 1b: per-(image, channel) affine  y = x * scale + shift  from the group statistics (tiny)
-__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ ss, int C, int groups,
-                                   int HW, float eps) {
+// pass 1b: reduce the per-CTA partials, group statistics -> per-(image, channel) affine y = x*scale + shift.
+// One warp per group (32 groups -> 1024 threads), lanes stride over the group's channels.
+__global__ void __launch_bounds__(1024)
+gn_finalize_kernel(const float* __restrict__ partial, int n_part, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ ss, int C, int groups, int HW, float eps) {
   const int img = blockIdx.x;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int g = threadIdx.x >> 5; g < groups; g += blockDim.x >> 5) {
     float s = 0.f, q = 0.f;
-    const float* st = stats + ((long long)img * C + g * cpg) * 2;
-    for (int c = 0; c < cpg; ++c) {
-      s += st[2 * c];
-      q += st[2 * c + 1];
+    for (int c = lane; c < cpg; c += 32) {
+      const int ch = g * cpg + c;
+      for (int k = 0; k < n_part; ++k) {
+        const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)img * n_part + k) * C + ch) * 2);
+        s += v.x;
+        q += v.y;
+      }
     }
+    s = warp_sum(s);
+    q = warp_sum(q);
     const float inv_n = 1.f / (float)(cpg * HW);
     const float mean = s * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
-    for (int c = 0; c < cpg; ++c) {
+    for (int c = lane; c < cpg; c += 32) {
       const int ch = g * cpg + c;
       const float ga = gamma[ch] * rstd;
-      ss[((long long)img * C + ch) * 2] = ga;
-      ss[((long long)img * C + ch) * 2 + 1] = beta[ch] - mean * ga;
+      *reinterpret_cast<float2*>(ss + ((long long)img * C + ch) * 2) = make_float2(ga, beta[ch] - mean * ga);
     }
   }
 }
@@ -160,6 +168,35 @@ gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
   }
 }
 
+// number of stats CTAs (= partial rows) per image: enough to fill the machine, every CTA non-empty
+static int groupnorm_partials(int n_img, int HW, int rpi) {
+  const int sms = num_sms();
+  int per_img = (2 * sms + n_img - 1) / n_img;
+  if (per_img < 1) per_img = 1;
+  int rows_per_cta = (HW + per_img - 1) / per_img;
+  const int min_rows = rpi * 4;
+  if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+  return (HW + rows_per_cta - 1) / rows_per_cta;
+}
+
+static int groupnorm_threads(int C, int* rpi_out) {
+  const int tpr = C >> 3;
+  int threads = 512;
+  if (tpr > 512) threads = tpr;
+  threads = (threads / tpr) * tpr;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  *rpi_out = threads / tpr;
+  return threads;
+}
+
+long long groupnorm_scratch_floats(int n_img, int C, int HW) {
+  int rpi = 1;
+  groupnorm_threads(C, &rpi);
+  if (rpi < 1) rpi = 1;
+  return (long long)n_img * C * 2 * (groupnorm_partials(n_img, HW, rpi) + 1);
+}
+
 int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
   DD_CHECK(a != nullptr, -1, "dd_groupnorm: null args");
   const int C = a->c1 + a->c2;
@@ -170,26 +207,18 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
   DD_CHECK(a->c2 == 0 || a->x2 != nullptr, -1, "dd_groupnorm: x2 missing");
   const int HW = a->h * a->w;
   const int tpr = C >> 3;
-  int threads = 512;
-  if (tpr > 512) threads = tpr;
-  threads = (threads / tpr) * tpr;                 // whole rows only
-  threads = ((threads + 31) / 32) * 32;
-  if (threads > 512) threads = 512;
-  const int rpi = threads / tpr;
+  int rpi = 0;
+  const int threads = groupnorm_threads(C, &rpi);
   DD_CHECK(rpi >= 1, -1, "dd_groupnorm: C=%d too large", C);
-  // stats scratch layout: [n_img*C*2] sums followed by [n_img*C*2] (scale, shift)
-  float* sums = a->stats;
-  float* ss = a->stats + (size_t)a->n_img * C * 2;
-  DD_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)a->n_img * C, stream));
+  // stats scratch layout: [n_img][per_img][C][2] per-CTA partial sums followed by [n_img][C][2] (scale, shift)
   const int sms = num_sms();
+  const int n_part = groupnorm_partials(a->n_img, HW, rpi);
+  float* sums = a->stats;
+  float* ss = a->stats + (size_t)a->n_img * n_part * C * 2;
   {
     // enough CTAs to fill the machine, few enough that the per-CTA atomics stay negligible
-    int per_img = (2 * sms + a->n_img - 1) / a->n_img;
-    if (per_img < 1) per_img = 1;
-    int rows_per_cta = (HW + per_img - 1) / per_img;
-    const int min_rows = rpi * 4;
-    if (rows_per_cta < min_rows) rows_per_cta = min_rows;
-    dim3 grid((HW + rows_per_cta - 1) / rows_per_cta, a->n_img);
+    const int rows_per_cta = (HW + n_part - 1) / n_part;
+    dim3 grid(n_part, a->n_img);
     const size_t smem = sizeof(float) * 2 * (size_t)C * rpi;
     static bool attr = false;
     if (!attr) {
@@ -202,7 +231,7 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
                                                      rows_per_cta, sums);
     DD_CUDA(cudaGetLastError());
   }
-  gn_finalize_kernel<<<a->n_img, 32, 0, stream>>>(sums, a->gamma, a->beta, ss, C, a->groups, HW, a->eps);
+  gn_finalize_kernel<<<a->n_img, 1024, 0, stream>>>(sums, n_part, a->gamma, a->beta, ss, C, a->groups, HW, a->eps);
   DD_CUDA(cudaGetLastError());
   {
     const int rows_img = a->padded_out ? (a->h + 1) * (a->w + 1) : HW;

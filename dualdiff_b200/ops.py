@@ -139,7 +139,8 @@ def groupnorm(x1, gamma, beta, *, n_img, hw, x2=None, eps=1e-5, silu=True, padde
     if out is None:
         out = torch.empty((rows, C_), device=x1.device, dtype=torch.bfloat16)
     if stats is None:
-        stats = torch.empty((n_img * C_ * 4,), device=x1.device, dtype=torch.float32)
+        stats = torch.empty((_lib.lib().dd_groupnorm_scratch_floats(n_img, C_, H * W),), device=x1.device,
+                            dtype=torch.float32)
     a = GroupNormArgs()
     a.x1 = _ptr(x1); a.x2 = _ptr(x2); a.out = _ptr(out); a.stats = _ptr(stats)
     a.gamma = _ptr(gamma); a.beta = _ptr(beta)

@@ -73,7 +73,8 @@ DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
  * conv_norm_out + conv_act (networks/unet_2d_condition_multiview.py:519-521).
  * Input: compact channels-last rows [n_img*H*W, c1] (+ optional second source [.., c2], concatenated along
  * channels = the up-block skip concat).  Output: compact rows, or (padded_out=1) the zero-haloed layout
- * [n_img][(H+1)][(W+1)][C] that dd_gemm(taps=9) consumes.  stats: fp32 scratch [n_img*C*4] (per-channel sums, then per-channel scale/shift). */
+ * [n_img][(H+1)][(W+1)][C] that dd_gemm(taps=9) consumes.  stats: fp32 scratch of dd_groupnorm_scratch_floats()
+ * elements (per-CTA partial sums, then per-channel scale/shift; no atomics -> bit-reproducible). */
 typedef struct dd_groupnorm_args {
   const void* x1; const void* x2; void* out; float* stats;
   const float* gamma; const float* beta;
@@ -83,6 +84,7 @@ typedef struct dd_groupnorm_args {
   int silu, padded_out;
 } dd_groupnorm_args;
 DD_API int dd_groupnorm(const dd_groupnorm_args* args, void* stream);
+DD_API long long dd_groupnorm_scratch_floats(int n_img, int c, int hw);
 
 /* ---- LayerNorm over token rows (networks/blocks.py:163,177,192,225) -------------------------------- */
 typedef struct dd_layernorm_args {
