@@ -19,6 +19,7 @@
 // Pipelines: smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "dd_api_internal.h"
 #include "dd_common.cuh"
@@ -54,16 +55,22 @@ struct GemmDev {
   int n_store;  // number of valid output columns (N, or N/2 for GEGLU)
 };
 
-template <int BN>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
+// CTA stages its own 128 A rows and HALF of the B tile, the leader's single thread issues M=256 UMMAs that read both
+// CTAs' shared memory and write both CTAs' TMEM.  Per SM that halves the B bytes written (TMA) and read (UMMA) per
+// MMA cycle: 128 + 0.5*(8192/BN+...) -- the 128 B/clk shared-memory port is what caps the 1-CTA kernel at ~57 %
+// tensor-pipe activity (ncu, profiles/r01_ncu_conv_*.txt).
+template <int BN, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS_MAX, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmR1, const GemmDev p) {
-  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;   // per CTA: the whole B tile, or its half of the pair's tile
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TILE_M = BM * CG;
   constexpr int ACC_COLS = (BN < 32) ? 32 : BN;      // columns per accumulator buffer
   constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN, 0, 0);
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM * CG, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -73,6 +80,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the CTA pair
+  const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t full_bar = smem_u32(&bars[0]);
   const uint32_t empty_bar = smem_u32(&bars[8]);
   const uint32_t tfull_bar = smem_u32(&bars[16]);
@@ -87,22 +97,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tma_prefetch_desc(&tmR1);
     }
     for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, CG);   // CG = 2: leader's arrive.expect_tx + the peer's remote arrive
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, (blockDim.x - 64) / 32);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * s, CG * ((blockDim.x - 64) / 32));  // one arrive per epilogue warp (of both CTAs)
     }
     for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_2cta(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(smem_u32(&tmem_ptr_smem), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_ptr_smem;
 
@@ -113,36 +128,58 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow lets ptxas keep barrier addresses, coordinates and
+    // descriptors in uniform registers); one elected lane issues.  Inside `if (lane == 0)` every operand of
+    // UTMALDG / UTCHMMA had to be moved vector->uniform (R2UR) per instruction, which made the kernel issue-bound.
+    {
       uint32_t it_global = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BM;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
         const int n0 = (tile % p.n_tiles) * BN;
         for (int it = 0; it < iters; ++it, ++it_global) {
           const int s = it_global % stages;
           const uint32_t ph = (it_global / stages) & 1;
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
           const int tap = it / kchunks;
           const int kc = (it - tap * kchunks) * BK;
           int arow = m0;
           if (p.taps == 9) arow += (tap / 3 - 1) * pitch + (tap % 3 - 1);
           const uint32_t sA = smem_base + s * STAGE_BYTES;
           const uint32_t sB = sA + A_STAGE_BYTES;
-          if (kc < p.K1)
-            tma_load_2d(sA, &tmA, full_bar + 8 * s, kc, arow);
-          else
-            tma_load_2d(sA, &tmA2, full_bar + 8 * s, kc - p.K1, arow);
-          tma_load_2d(sB, &tmB, full_bar + 8 * s, tap * p.K + kc, n0);
+          if constexpr (CG == 1) {
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+              if (kc < p.K1)
+                tma_load_2d(sA, &tmA, full_bar + 8 * s, kc, arow);
+              else
+                tma_load_2d(sA, &tmA2, full_bar + 8 * s, kc - p.K1, arow);
+              tma_load_2d(sB, &tmB, full_bar + 8 * s, tap * p.K + kc, n0);
+            }
+          } else {
+            // both CTAs load into their own smem; every byte is credited to the LEADER's full barrier
+            const uint32_t full_leader = mapa_shared(full_bar + 8 * s, 0);
+            if (elect_one()) {
+              if (kc < p.K1)
+                tma_load_2d_2cta(sA, &tmA, full_leader, kc, arow);
+              else
+                tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, arow);
+              tma_load_2d_2cta(sB, &tmB, full_leader, tap * p.K + kc, n0 + (int)crank * (BN / 2));
+              if (crank == 0)
+                mbar_arrive_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);
+              else
+                mbar_arrive_cluster(full_leader);
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------- UMMA issuer --------------------------------
-    if (lane == 0) {
+    if (crank == 0) {   // CG = 2: only the leader CTA issues (its UMMAs drive both SMs); warp-uniform loop, elected issue
       uint32_t it_global = 0;
       uint32_t local_tile = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
         const uint32_t as = local_tile & 1;
         const uint32_t aph = (local_tile >> 1) & 1;
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
@@ -157,14 +194,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sB = sA + A_STAGE_BYTES;
           const uint64_t dA = umma_smem_desc(sA, 16, 1024, 2);
           const uint64_t dB = umma_smem_desc(sB, 16, 1024, 2);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
-            umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
+              if constexpr (CG == 2) {
+                umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+              } else {
+                umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+              }
+            }
+            // frees the smem slot (in both CTAs of a pair) when these UMMAs retire
+            if constexpr (CG == 2) umma_commit_2cta(empty_bar + 8 * s, 3); else umma_commit(empty_bar + 8 * s);
           }
-          umma_commit(empty_bar + 8 * s);  // frees the smem slot when these UMMAs retire
+          __syncwarp();
         }
-        umma_commit(tfull_bar + 8 * as);  // accumulator complete
+        // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
+        if (elect_one()) {
+          if constexpr (CG == 2) umma_commit_2cta(tfull_bar + 8 * as, 3); else umma_commit(tfull_bar + 8 * as);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -199,14 +248,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int nch = geglu ? (BN / 128) : (BN / 64);
         const int n_epi_halves = (int)(blockDim.x - 64) / 128;   // 2 in TMA mode
         auto r1_issue = [&](int t, int ch) {
-          const int tm0 = (t / p.n_tiles) * BM + q * 32;
+          const int tm0 = (t / p.n_tiles) * TILE_M + (int)crank * BM + q * 32;
           const int tn0 = (t % p.n_tiles) * BN + ch * 64;
           mbar_arrive_expect_tx(r1_bar, 4096);
           tma_load_2d(r1_stage, &tmR1, r1_bar, tn0, tm0);
         };
-        if (has_r1 && lane == 0 && (int)blockIdx.x < total_tiles && half < nch) r1_issue(blockIdx.x, half);
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
-          const int m0 = (tile / p.n_tiles) * BM;
+        if (has_r1 && lane == 0 && worker < total_tiles && half < nch) r1_issue(worker, half);
+        for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
+          const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
           const int n0 = (tile % p.n_tiles) * BN;
           const int nout0 = geglu ? (n0 / BN) * (BN / 2) : n0;
           const uint32_t as = local_tile & 1;
@@ -294,7 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               __syncwarp();
               if (lane == 0) {
                 if (ch + n_epi_halves < nch) r1_issue(tile, ch + n_epi_halves);
-                else if (tile + (int)gridDim.x < total_tiles && half < nch) r1_issue(tile + gridDim.x, half);
+                else if (tile + n_workers < total_tiles && half < nch) r1_issue(tile + n_workers, half);
               }
             }
             fence_proxy_async_smem();
@@ -306,13 +355,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+          if (lane == 0) {
+            if (crank == 0) mbar_arrive(tempty_bar + 8 * as);
+            else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
+          }
         }
         if (lane == 0) bulk_wait0();
       }
     } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
-      const int m0 = (tile / p.n_tiles) * BM;
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
+      const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
       const int n0 = (tile % p.n_tiles) * BN;
       const int nout0 = p.geglu ? (n0 / BN) * (BN / 2) : n0;
       const uint32_t as = local_tile & 1;
@@ -461,25 +513,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // release the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+      if (lane == 0) {
+        if (crank == 0) mbar_arrive(tempty_bar + 8 * as);
+        else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: nobody leaves while the peer may still signal us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
-                       const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + BN * BK * 2;
+template <int BN, int CG>
+static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                          const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / CG) * BK * 2;
   const int epi_warps = p.tma_epi ? 8 : 4;
   int stages = (227 * 1024 - 3072 - epi_warps * EPI_WARP_BYTES) / STAGE_BYTES;
   if (stages > 8) stages = 8;
@@ -490,18 +545,36 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CU
   const size_t smem = (size_t)stages * STAGE_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - 2048));
     attr_done = true;
   }
-  p.m_tiles = (p.M + BM - 1) / BM;
+  p.m_tiles = (p.M + BM * CG - 1) / (BM * CG);   // tiles of 128 (one CTA) or 256 (CTA pair) rows
   p.n_tiles = (p.N + BN - 1) / BN;
-  int grid = p.m_tiles * p.n_tiles;
+  int workers = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
-  if (grid > sms) grid = sms;
-  gemm_tcgen05_kernel<BN><<<grid, p.tma_epi ? GEMM_THREADS_MAX : GEMM_THREADS, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmR1, p);
-  DD_CUDA(cudaGetLastError());
+  if (workers > sms / CG) workers = sms / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(workers * CG);
+  cfg.blockDim = dim3(p.tma_epi ? GEMM_THREADS_MAX : GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, tmA, tmA2, tmB, tmOut, tmR1, p));
   return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
+                       const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream, int cg) {
+  if (cg == 2) return launch_gemm_cg<BN, 2>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+  return launch_gemm_cg<BN, 1>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
 }
 
 static int pick_bn_tma(int N, int geglu) {
@@ -569,6 +642,8 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
                       a->N > 32 && (a->force_bn == 0 || a->force_bn % 64 == 0) && !a->no_tma_epilogue;
   int bn = pick_bn(a->N, a->geglu, a->force_bn);
   if (tma_ok && a->force_bn == 0) bn = pick_bn_tma(a->N, a->geglu);
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work
+  const int cg = (a->M > BM && !a->one_cta) ? 2 : 1;
   CUtensorMap tmA, tmA2, tmB, tmOut, tmR1;
   int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, BM, BK);
   if (rc) return rc;
@@ -578,7 +653,7 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   } else {
     tmA2 = tmA;
   }
-  rc = make_tmap_2d_bf16(&tmB, a->w, (uint64_t)a->N, (uint64_t)a->K * a->taps, (uint64_t)a->w_ld, bn, BK);
+  rc = make_tmap_2d_bf16(&tmB, a->w, (uint64_t)a->N, (uint64_t)a->K * a->taps, (uint64_t)a->w_ld, bn / cg, BK);
   if (rc) return rc;
 
   if (tma_ok) {
@@ -606,12 +681,12 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   p.geglu = a->geglu; p.act = a->act; p.n_store = n_store;
   p.m_tiles = p.n_tiles = p.stages = 0;
   switch (bn) {
-    case 32: return launch_gemm<32>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-    case 64: return launch_gemm<64>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-    case 128: return launch_gemm<128>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-    case 160: return launch_gemm<160>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-    case 192: return launch_gemm<192>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-    case 256: return launch_gemm<256>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    case 32: return launch_gemm<32>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
+    case 64: return launch_gemm<64>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
+    case 128: return launch_gemm<128>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
+    case 160: return launch_gemm<160>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
+    case 192: return launch_gemm<192>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
+    case 256: return launch_gemm<256>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
     default: DD_CHECK(false, -1, "dd_gemm: unsupported tile width %d", bn);
   }
   return 0;

@@ -15,6 +15,9 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_FORCE_ONE_CTA = bool(int(__import__('os').environ.get('DD_ONE_CTA', '0')))   # A/B switch for benchmarking
+
+
 # ---- optional per-launch instrumentation (bench.py roofline pass; never active on the timed path) ----
 _PROF = None
 
@@ -68,7 +71,7 @@ def padded_rows(n_img, H, W):
 
 
 def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, res2=None, a2=None,
-         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0, act=0, no_tma_epilogue=False):
+         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0, act=0, no_tma_epilogue=False, one_cta=False):
     """out = epilogue(A @ W^T).  a: [M, K] bf16 (row stride may exceed K); w: [N, taps*K] bf16.
 
     taps=9: ``a`` is the padded-pixel activation [n_img*(H+1)*(W+1), K]; the result has n_img*H*W rows.
@@ -108,6 +111,7 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
     args.force_bn = force_bn
     args.act = act
     args.no_tma_epilogue = 1 if no_tma_epilogue else 0
+    args.one_cta = 1 if (one_cta or _FORCE_ONE_CTA) else 0
     if bias is not None:
         _req(bias, torch.float32, "bias")
     if rowvec is not None:

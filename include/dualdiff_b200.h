@@ -65,6 +65,7 @@ typedef struct dd_gemm_args {
   int force_bn;       /* 0 = auto tile width; testing hook                                        */
   int act;            /* 0 none, 1 SiLU applied after bias/residuals (ControlNetConditioningEmbedding) */
   int no_tma_epilogue;/* testing hook: 1 forces the register/smem-transpose epilogue                 */
+  int one_cta;        /* testing hook: 1 forces the single-CTA kernel (default: CTA pairs, cta_group::2) */
 } dd_gemm_args;
 DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 

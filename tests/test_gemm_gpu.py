@@ -92,3 +92,22 @@ def test_tma_epilogue_equals_register_epilogue(M, N, K, res, act):
         ref = F.silu(ref)
     assert _rel(out_tma, ref) < 1e-2 and _rel(out_reg, ref) < 1e-2
     assert (out_tma.float() - out_reg.float()).abs().max() <= 2e-2 * ref.abs().max()
+
+
+@pytest.mark.parametrize("M,N,K,taps", [(1000, 1280, 1280, 1), (129, 320, 320, 1), (5000, 640, 2560, 1), (2 * 29 * 51, 320, 320, 9)])
+def test_cta_pair_kernel_equals_single_cta_kernel(M, N, K, taps):
+    """default = CTA pairs (tcgen05 cta_group::2, 256-row tiles); one_cta=True = the single-CTA kernel"""
+    from dualdiff_b200 import ops, packing
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    if taps == 9:
+        x = _mk((2, 28, 50, K), 1); w = _mk((N, K, 3, 3), 2, (9 * K) ** -0.5)
+        a, wp = packing.to_padded(x), packing.pack_conv3x3(w)
+        kw = dict(taps=9, conv_hw=(28, 50), n_img=2)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    else:
+        a = _mk((M, K), 1); wp = _mk((N, K), 2, K ** -0.5); kw = {}
+        ref = a.float() @ wp.float().t() + bias
+    o2 = ops.gemm(a, wp, bias=bias, **kw)
+    o1 = ops.gemm(a, wp, bias=bias, one_cta=True, **kw)
+    assert _rel(o2, ref) < 1e-2 and _rel(o1, ref) < 1e-2
+    assert torch.equal(o1, o2)   # same accumulation order per output element -> bit-identical
