@@ -96,27 +96,35 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int total = p.n_src * p.n_kv_tiles;
 
   if (warp == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      // Q tile (once)
-      mbar_arrive_expect_tx(q_full, QCH * CHUNK_BYTES);
-      for (int c = 0; c < QCH; ++c)
-        tma_load_3d(sQ + c * CHUNK_BYTES, &tmQ, q_full, p.q_col0 + head * p.q_hs + c * 64, q_tile * ATT_BM, img);
+    // whole warp runs the control flow (warp-uniform -> uniform registers for barrier addresses / descriptors);
+    // one elected lane issues the TMA loads and UMMAs
+    {
+      if (elect_one()) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        // Q tile (once)
+        mbar_arrive_expect_tx(q_full, QCH * CHUNK_BYTES);
+        for (int c = 0; c < QCH; ++c)
+          tma_load_3d(sQ + c * CHUNK_BYTES, &tmQ, q_full, p.q_col0 + head * p.q_hs + c * 64, q_tile * ATT_BM, img);
+      }
+      __syncwarp();
       auto produce = [&](int g) {
         const int s = g % STAGES;
         const uint32_t ph = (g / STAGES) & 1;
         mbar_wait(kv_empty + 8 * s, ph ^ 1);
-        mbar_arrive_expect_tx(kv_full + 8 * s, KV_STAGE_BYTES);
         const int src = g / p.n_kv_tiles, jt = g - src * p.n_kv_tiles;
         const int kv_img = p.kv_map ? p.kv_map[img * p.n_src + src] : img;
         const uint32_t sK = sKV + s * KV_STAGE_BYTES;
         const uint32_t sV = sK + QCH * CHUNK_BYTES;
-        for (int c = 0; c < QCH; ++c)
-          tma_load_3d(sK + c * CHUNK_BYTES, &tmK, kv_full + 8 * s, p.k_col0 + head * p.k_hs + c * 64, jt * ATT_BN, kv_img);
-        for (int c = 0; c < VCH; ++c)
-          tma_load_3d(sV + c * CHUNK_BYTES, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs + c * 64, jt * ATT_BN, kv_img);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kv_full + 8 * s, KV_STAGE_BYTES);
+          for (int c = 0; c < QCH; ++c)
+            tma_load_3d(sK + c * CHUNK_BYTES, &tmK, kv_full + 8 * s, p.k_col0 + head * p.k_hs + c * 64, jt * ATT_BN, kv_img);
+          for (int c = 0; c < VCH; ++c)
+            tma_load_3d(sV + c * CHUNK_BYTES, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs + c * 64, jt * ATT_BN, kv_img);
+        }
+        __syncwarp();
       };
       auto issue_qk = [&](int g) {
         const int s = g % STAGES;
@@ -124,13 +132,16 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const uint32_t sK = sKV + s * KV_STAGE_BYTES;
         // S = Q K^T  (both operands K-major, 64-column swizzle chunks)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < DQK / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-          umma_bf16(tmem_S, umma_smem_desc(sQ + off, 16, 1024, 2), umma_smem_desc(sK + off, 16, 1024, 2), IDESC_S,
-                    kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < DQK / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+            umma_bf16(tmem_S, umma_smem_desc(sQ + off, 16, 1024, 2), umma_smem_desc(sK + off, 16, 1024, 2), IDESC_S,
+                      kk != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full);
         }
-        umma_commit(s_full);
+        __syncwarp();
       };
       produce(0);
       if (STAGES > 1 && total > 1) produce(1);
@@ -149,16 +160,19 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const uint32_t sV = sKV + s * KV_STAGE_BYTES + QCH * CHUNK_BYTES;
         // O += P V : A = P (K-major, 2 chunks of 64 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-          const uint32_t offP = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
-          const uint32_t offV = kk * 16 * 128;  // 16 key rows of 128 B
-          umma_bf16(tmem_O, umma_smem_desc(sP + offP, 16, 1024, 2),
-                    umma_smem_desc(sV + offV, CHUNK_BYTES, 1024, 2), IDESC_O,
-                    (kk != 0 || (g % p.n_kv_tiles) != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
+          for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+            const uint32_t offP = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
+            const uint32_t offV = kk * 16 * 128;  // 16 key rows of 128 B
+            umma_bf16(tmem_O, umma_smem_desc(sP + offP, 16, 1024, 2),
+                      umma_smem_desc(sV + offV, CHUNK_BYTES, 1024, 2), IDESC_O,
+                      (kk != 0 || (g % p.n_kv_tiles) != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
+          }
+          umma_commit(kv_empty + 8 * s);
+          umma_commit(o_full);
         }
-        umma_commit(kv_empty + 8 * s);
-        umma_commit(o_full);
+        __syncwarp();
         if (STAGES > 1) {
           if (g + 2 < total) produce(g + 2);   // stage s is free once P(g) V(g) retires (kv_empty)
         } else if (g + 1 < total) {
