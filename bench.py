@@ -36,6 +36,15 @@ def peaks():
     return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, src="fallback")
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel`, from the committed ncu launch list of one step (profiles/); None if absent"""
+    p = os.path.join(ROOT, "profiles", "r01_launches_traffic.json")
+    try:
+        return round(json.load(open(p))[kernel]["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -203,7 +212,8 @@ def run_ours(args):
         roof = {"kernel": "gemm_tcgen05_kernel (Linear / 1x1 / implicit-GEMM 3x3 conv)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4), "peak_source": f"{pk['src']} (bf16 sustained)",
-                "traffic": None, "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
+                "traffic": ncu_traffic("gemm_tcgen05_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_launches_traffic.json)",
+                "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
                 "share_of_step": round(g["ms"] / tot, 3),
                 "flops_per_step": g["flops"], "note": "algorithmic 2*M*N*K per launch summed over one step / summed CUDA-event durations"}
         breakdown = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 3), "launches": v["launches"],

@@ -190,6 +190,57 @@ class AttrDict(dict):
 class ModelBase(nn.Module):
     """the slice of diffusers ModelMixin/ConfigMixin the reference's callers touch (SURVEY §8c attribute surface)"""
 
+    config_name = "config.json"
+    weights_names = ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, subfolder=None, **kwargs):
+        """load a diffusers-format checkpoint directory (config.json + diffusion_pytorch_model.{safetensors,bin}) the
+        way misc/test_utils.py:111-113,146-147 does.  Unknown kwargs of the diffusers loader (low_cpu_mem_usage,
+        device_map, ignore_mismatched_sizes, ...) are accepted and ignored; mismatched / missing keys are skipped
+        like `ignore_mismatched_sizes=True`."""
+        import inspect
+        import json
+        import os
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(root, cls.config_name)) as fh:
+            cfg = {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+        accepted = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in cfg.items() if k in accepted})
+        sd = None
+        for name in cls.weights_names:
+            path = os.path.join(root, name)
+            if os.path.exists(path):
+                if name.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(path)
+                else:
+                    sd = torch.load(path, map_location="cpu", weights_only=True)
+                break
+        if sd is None:
+            raise FileNotFoundError(f"no {' / '.join(cls.weights_names)} under {root}")
+        own = model.state_dict()
+        sd = {k: v for k, v in sd.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
+        model.load_state_dict(sd, strict=False)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        return model.eval()
+
+    def save_pretrained(self, save_directory, safe_serialization=True, **kwargs):
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {"_class_name": type(self).__name__, "_diffusers_version": "0.17.1"}
+        cfg.update({k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.items()})
+        with open(os.path.join(save_directory, self.config_name), "w") as fh:
+            json.dump(cfg, fh, indent=2, default=str)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, self.weights_names[0]))
+        else:
+            torch.save(sd, os.path.join(save_directory, self.weights_names[1]))
+
     @property
     def dtype(self):
         return torch.bfloat16 if getattr(self, "_packed", None) is not None else next(self.parameters()).dtype
