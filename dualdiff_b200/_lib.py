@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("M", _i), ("N", _i), ("K", _i), ("k1", _i), ("taps", _i), ("conv_h", _i), ("conv_w", _i),
         ("a_ld", _ll), ("a2_ld", _ll), ("w_ld", _ll), ("out_ld", _ll), ("res1_ld", _ll), ("res2_ld", _ll),
         ("rowvec_ld", _i), ("rows_per_img", _i), ("out_f32", _i), ("geglu", _i), ("force_bn", _i), ("act", _i), ("no_tma_epilogue", _i), ("one_cta", _i),
+        ("stream_k", _i), ("workspace", _vp), ("workspace_bytes", _ll),
     ]
 
 

@@ -53,6 +53,37 @@ struct GemmDev {
   int act;      // 0 none, 1 SiLU (applied last)
   int tma_epi;  // 1: epilogue moves residual/output tiles with TMA (plain GEMM, bf16 out)
   int n_store;  // number of valid output columns (N, or N/2 for GEGLU)
+  // stream-K (sk_chunk > 0): the flattened (tile, k-iteration) space is cut into equal contiguous ranges, one per worker;
+  // every segment's raw fp32 accumulator goes to ws[tile * sk_maxc + contributor][TILE_M][BN] and splitk_reduce_kernel
+  // sums the contributors in fixed order and applies the epilogue (bit-reproducible, no atomics).
+  int sk_chunk, sk_maxc;
+  float* ws;
+};
+
+// Work iterator shared by the three roles of the GEMM kernel.  Classic: tiles worker, worker + n_workers, ... with all
+// k-iterations each.  Stream-K: the worker's contiguous range of the flattened (tile, k-iteration) space, cut at tile
+// boundaries into segments.
+struct WorkIter {
+  int tile, it0, it1;
+  int pos, end, iters, step, total_tiles, sk;
+  __device__ __forceinline__ WorkIter(int worker, int n_workers, int total_tiles_, int iters_, int sk_chunk)
+      : tile(worker - n_workers), it0(0), it1(iters_), pos(worker * sk_chunk), iters(iters_), step(n_workers),
+        total_tiles(total_tiles_), sk(sk_chunk) {
+    const int total = total_tiles_ * iters_;
+    end = pos + sk_chunk < total ? pos + sk_chunk : total;
+  }
+  __device__ __forceinline__ bool next() {
+    if (sk == 0) {
+      tile += step;
+      return tile < total_tiles;
+    }
+    if (pos >= end) return false;
+    tile = pos / iters;
+    it0 = pos - tile * iters;
+    it1 = it0 + (end - pos) < iters ? it0 + (end - pos) : iters;
+    pos += it1 - it0;
+    return true;
+  }
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile — each
@@ -133,10 +164,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // UTMALDG / UTCHMMA had to be moved vector->uniform (R2UR) per instruction, which made the kernel issue-bound.
     {
       uint32_t it_global = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+      while (wi.next()) {
+        const int tile = wi.tile;
         const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
         const int n0 = (tile % p.n_tiles) * BN;
-        for (int it = 0; it < iters; ++it, ++it_global) {
+        for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
           const int s = it_global % stages;
           const uint32_t ph = (it_global / stages) & 1;
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -179,13 +212,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (crank == 0) {   // CG = 2: only the leader CTA issues (its UMMAs drive both SMs); warp-uniform loop, elected issue
       uint32_t it_global = 0;
       uint32_t local_tile = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
+      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+      for (; wi.next(); ++local_tile) {
         const uint32_t as = local_tile & 1;
         const uint32_t aph = (local_tile >> 1) & 1;
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * ACC_COLS;
-        for (int it = 0; it < iters; ++it, ++it_global) {
+        const int it_first = wi.it0;
+        for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
           const int s = it_global % stages;
           const uint32_t ph = (it_global / stages) & 1;
           mbar_wait(full_bar + 8 * s, ph);
@@ -199,9 +234,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
               if constexpr (CG == 2) {
-                umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it != it_first || k != 0) ? 1u : 0u);
               } else {
-                umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it | k) != 0 ? 1u : 0u);
+                umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it != it_first || k != 0) ? 1u : 0u);
               }
             }
             // frees the smem slot (in both CTAs of a pair) when these UMMAs retire
@@ -362,11 +397,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (lane == 0) bulk_wait0();
       }
-    } else
-    for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
+    } else {
+    WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+    const bool sk = p.sk_chunk != 0;
+    const int n_store = sk ? BN : p.n_store;
+    const long long out_ld = sk ? (long long)BN : p.out_ld;
+    void* const outp = sk ? (void*)p.ws : p.out;
+    for (; wi.next(); ++local_tile) {
+      const int tile = wi.tile;
       const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
       const int n0 = (tile % p.n_tiles) * BN;
-      const int nout0 = p.geglu ? (n0 / BN) * (BN / 2) : n0;
+      const int nout0 = sk ? 0 : p.geglu ? (n0 / BN) * (BN / 2) : n0;
       const uint32_t as = local_tile & 1;
       const uint32_t aph = (local_tile >> 1) & 1;
       mbar_wait(tfull_bar + 8 * as, aph);
@@ -374,7 +415,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m = m0 + q * 32 + lane;
       int valid = m < p.M;
       long long orow = m;
-      if (p.taps == 9) {
+      if (sk) {
+        // raw partial accumulator -> workspace slot of (tile, contributor); every row of the tile is written
+        const int slot = tile * p.sk_maxc + (worker - (tile * iters) / p.sk_chunk);
+        valid = 1;
+        orow = (long long)slot * TILE_M + (int)crank * BM + q * 32 + lane;
+      } else if (p.taps == 9) {
         const int img = m / HW1;
         const int rem = m - img * HW1;
         const int hp = rem / pitch;
@@ -441,8 +487,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p1 << 4)));
             v[4] = __uint_as_float(t0); v[5] = __uint_as_float(t1); v[6] = __uint_as_float(t2); v[7] = __uint_as_float(t3);
           }
-          if (!valid_r || col >= p.n_store) continue;
-          if (col + 8 <= p.n_store) {
+          if (!valid_r || col >= n_store) continue;
+          if (col + 8 <= n_store) {
             if (!p.geglu) {
               if (p.bias) {
                 const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
@@ -479,11 +525,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
             if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + orow_r * p.out_ld + col;
+              float* o = reinterpret_cast<float*>(outp) + orow_r * out_ld + col;
               *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
               *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
             } else {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + orow_r * p.out_ld + col;
+              bf16* o = reinterpret_cast<bf16*>(outp) + orow_r * out_ld + col;
               *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                                                         pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             }
@@ -491,7 +537,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ragged right edge (N not a multiple of 8, e.g. conv_out N = 4): scalar path
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              if (col + e < p.n_store) {
+              if (col + e < n_store) {
                 float x = v[e];
                 if (!p.geglu) {
                   if (p.bias) x += p.bias[col + e];
@@ -501,9 +547,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   if (p.act == 1) x = silu_f(x);
                 }
                 if (p.out_f32)
-                  reinterpret_cast<float*>(p.out)[orow_r * p.out_ld + col + e] = x;
+                  reinterpret_cast<float*>(outp)[orow_r * out_ld + col + e] = x;
                 else
-                  reinterpret_cast<bf16*>(p.out)[orow_r * p.out_ld + col + e] = __float2bfloat16(x);
+                  reinterpret_cast<bf16*>(outp)[orow_r * out_ld + col + e] = __float2bfloat16(x);
               }
             }
           }
@@ -518,6 +564,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -525,6 +572,71 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-K second pass: out = epilogue( sum over the contributors of a tile, in worker order )
+// grid (tiles, TILE_M / 32), 256 threads; a thread owns 4 consecutive columns of a row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const GemmDev p, const int BN, const int TILE_M, const int iters) {
+  const int tile = blockIdx.x;
+  const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+  const int w_first = (tile * iters) / p.sk_chunk;
+  const int w_last = ((tile + 1) * iters - 1) / p.sk_chunk;
+  const int nc = w_last - w_first + 1;
+  const int tpr = BN >> 2;                    // threads per row
+  const int rpi = 256 / tpr;                  // rows per iteration
+  const int cq = threadIdx.x % tpr;
+  const int col = n_tile * BN + cq * 4;
+  if (col >= p.n_store || (int)threadIdx.x >= rpi * tpr) return;
+  const int pitch = p.conv_W + 1;
+  const int HW1 = (p.conv_H + 1) * pitch;
+  const float* base = p.ws + (size_t)tile * p.sk_maxc * TILE_M * BN + cq * 4;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias) bv = *reinterpret_cast<const float4*>(p.bias + col);
+  for (int r = blockIdx.y * 32 + threadIdx.x / tpr; r < blockIdx.y * 32 + 32; r += rpi) {
+    const int m = m_tile * TILE_M + r;
+    if (m >= p.M) break;
+    long long orow = m;
+    if (p.taps == 9) {
+      const int img = m / HW1;
+      const int rem = m - img * HW1;
+      const int hp = rem / pitch;
+      const int wp = rem - hp * pitch;
+      if (hp >= p.conv_H || wp >= p.conv_W) continue;
+      orow = ((long long)img * p.conv_H + hp) * p.conv_W + wp;
+    }
+    float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * BN);
+    for (int k = 1; k < nc; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(base + ((size_t)k * TILE_M + r) * BN);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    if (p.rowvec) {
+      const float4 t = *reinterpret_cast<const float4*>(p.rowvec + (orow / p.rows_per_img) * (long long)p.rowvec_ld + col);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    if (p.res1) {
+      const uint2 t = *reinterpret_cast<const uint2*>(p.res1 + orow * p.res1_ld + col);
+      const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
+      v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+    }
+    if (p.res2) {
+      const uint2 t = *reinterpret_cast<const uint2*>(p.res2 + orow * p.res2_ld + col);
+      const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
+      v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+    }
+    if (p.act == 1) {
+      v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+    }
+    if (p.out_f32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.out_ld + col) = v;
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow * p.out_ld + col) =
+          make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
   }
 }
 
@@ -554,6 +666,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   int workers = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (workers > sms / CG) workers = sms / CG;
+  if (p.sk_chunk > 0) workers = (p.m_tiles * p.n_tiles * iters + p.sk_chunk - 1) / p.sk_chunk;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * CG);
   cfg.blockDim = dim3(p.tma_epi ? GEMM_THREADS_MAX : GEMM_THREADS);
@@ -644,6 +757,36 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   if (tma_ok && a->force_bn == 0) bn = pick_bn_tma(a->N, a->geglu);
   // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile of work
   const int cg = (a->M > BM && !a->one_cta) ? 2 : 1;
+  // stream-K: when the tiles fill the last wave badly (e.g. the 4x7-pixel level: 75 pair-tiles on 74 CTA pairs) and the
+  // K loop is long, split the flattened (tile, k-iteration) space evenly over the workers instead
+  int sk_chunk = 0, sk_maxc = 0;
+  bool tma_epi = tma_ok;
+  if (a->workspace != nullptr && a->stream_k >= 0 && !a->geglu && a->N % 4 == 0) {
+    const int bn_sk = pick_bn(a->N, 0, a->force_bn);
+    const int tile_m = BM * cg;
+    const long tiles = (long)((a->M + tile_m - 1) / tile_m) * ((a->N + bn_sk - 1) / bn_sk);
+    const long W = num_sms() / cg;
+    const long iters = (long)a->taps * ((a->K + BK - 1) / BK);
+    const long waves = (tiles + W - 1) / W;
+    const double eff = (double)tiles / (double)(waves * W);
+    if (a->stream_k == 1 || (iters >= 32 && eff < 0.75 && tiles <= 4 * W)) {
+      const long total = tiles * iters;
+      const long chunk = (total + W - 1) / W;
+      const long maxc = (iters + chunk - 2) / chunk + 1;
+      const long long need = (long long)tiles * maxc * tile_m * bn_sk * 4;
+      if (need <= a->workspace_bytes && total < (1L << 30)) {
+        sk_chunk = (int)chunk;
+        sk_maxc = (int)maxc;
+        bn = bn_sk;
+        tma_epi = false;
+      } else {
+        DD_CHECK(a->stream_k != 1, -1, "dd_gemm: stream-K workspace too small (%lld > %lld bytes)", need,
+                 (long long)a->workspace_bytes);
+      }
+    }
+  } else {
+    DD_CHECK(a->stream_k != 1, -1, "dd_gemm: stream-K needs a workspace, no GEGLU and N %% 4 == 0");
+  }
   CUtensorMap tmA, tmA2, tmB, tmOut, tmR1;
   int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, BM, BK);
   if (rc) return rc;
@@ -656,7 +799,7 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   rc = make_tmap_2d_bf16(&tmB, a->w, (uint64_t)a->N, (uint64_t)a->K * a->taps, (uint64_t)a->w_ld, bn / cg, BK);
   if (rc) return rc;
 
-  if (tma_ok) {
+  if (tma_epi) {
     rc = make_tmap_2d_bf16(&tmOut, a->out, (uint64_t)a->M, (uint64_t)n_store, (uint64_t)a->out_ld, 32, 64);
     if (rc) return rc;
     if (a->res1 != nullptr) {
@@ -670,7 +813,8 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
     tmR1 = tmA;
   }
   GemmDev p;
-  p.tma_epi = tma_ok ? 1 : 0;
+  p.tma_epi = tma_epi ? 1 : 0;
+  p.sk_chunk = sk_chunk; p.sk_maxc = sk_maxc; p.ws = reinterpret_cast<float*>(a->workspace);
   p.M = a->M; p.N = a->N; p.K = a->K; p.K1 = K1; p.taps = a->taps;
   p.conv_H = a->conv_h; p.conv_W = a->conv_w;
   p.out = a->out; p.out_ld = a->out_ld; p.out_f32 = a->out_f32;
@@ -680,6 +824,29 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   p.res2 = reinterpret_cast<const bf16*>(a->res2); p.res2_ld = a->res2_ld;
   p.geglu = a->geglu; p.act = a->act; p.n_store = n_store;
   p.m_tiles = p.n_tiles = p.stages = 0;
+  if (sk_chunk > 0) {
+    // pass 1: raw fp32 partial tiles into the workspace; pass 2: ordered sum + the real epilogue
+    GemmDev pk = p;
+    pk.bias = nullptr; pk.rowvec = nullptr; pk.res1 = nullptr; pk.res2 = nullptr; pk.act = 0; pk.out_f32 = 1;
+    switch (bn) {
+      case 32: rc = launch_gemm<32>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      case 64: rc = launch_gemm<64>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      case 128: rc = launch_gemm<128>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      case 160: rc = launch_gemm<160>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      case 192: rc = launch_gemm<192>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      case 256: rc = launch_gemm<256>(tmA, tmA2, tmB, tmOut, tmR1, pk, stream, cg); break;
+      default: DD_CHECK(false, -1, "dd_gemm: unsupported tile width %d", bn);
+    }
+    if (rc) return rc;
+    const int tile_m = BM * cg;
+    p.m_tiles = (p.M + tile_m - 1) / tile_m;
+    p.n_tiles = (p.N + bn - 1) / bn;
+    const int iters = p.taps * ((p.K + BK - 1) / BK);
+    splitk_reduce_kernel<<<dim3(p.m_tiles * p.n_tiles, tile_m / 32), 256, 0, stream>>>(p, bn, tile_m, iters);
+    DD_CUDA(cudaGetLastError());
+    count_launch(1);
+    return 0;
+  }
   switch (bn) {
     case 32: return launch_gemm<32>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);
     case 64: return launch_gemm<64>(tmA, tmA2, tmB, tmOut, tmR1, p, stream, cg);

@@ -70,8 +70,24 @@ def padded_rows(n_img, H, W):
     return n_img * (H + 1) * (W + 1)
 
 
+_WORKSPACE = {}
+_WORKSPACE_BYTES = 64 << 20
+_STREAM_K = int(__import__('os').environ.get('DD_STREAM_K', '0'))   # A/B switch: -1 disables stream-K
+
+
+def gemm_workspace(device):
+    """fp32 scratch for stream-K partial tiles: one buffer per (device, stream) so that the concurrently running
+    ControlNet / UNet streams never share one.  Allocated on first use, kept for the life of the process."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACE.get(key)
+    if ws is None:
+        ws = _WORKSPACE[key] = torch.empty(_WORKSPACE_BYTES, device=device, dtype=torch.uint8)
+    return ws
+
+
 def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, res2=None, a2=None,
-         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0, act=0, no_tma_epilogue=False, one_cta=False):
+         taps=1, conv_hw=None, n_img=None, geglu=False, out_f32=False, force_bn=0, act=0, no_tma_epilogue=False, one_cta=False,
+         stream_k=0):
     """out = epilogue(A @ W^T).  a: [M, K] bf16 (row stride may exceed K); w: [N, taps*K] bf16.
 
     taps=9: ``a`` is the padded-pixel activation [n_img*(H+1)*(W+1), K]; the result has n_img*H*W rows.
@@ -112,6 +128,10 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
     args.act = act
     args.no_tma_epilogue = 1 if no_tma_epilogue else 0
     args.one_cta = 1 if (one_cta or _FORCE_ONE_CTA) else 0
+    args.stream_k = stream_k if stream_k != 0 else _STREAM_K
+    if args.stream_k >= 0 and not geglu:
+        ws = gemm_workspace(a.device)
+        args.workspace = _ptr(ws); args.workspace_bytes = ws.numel()
     if bias is not None:
         _req(bias, torch.float32, "bias")
     if rowvec is not None:

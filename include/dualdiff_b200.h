@@ -66,6 +66,9 @@ typedef struct dd_gemm_args {
   int act;            /* 0 none, 1 SiLU applied after bias/residuals (ControlNetConditioningEmbedding) */
   int no_tma_epilogue;/* testing hook: 1 forces the register/smem-transpose epilogue                 */
   int one_cta;        /* testing hook: 1 forces the single-CTA kernel (default: CTA pairs, cta_group::2) */
+  int stream_k;       /* 0 auto (used when the tiles fill the last wave badly and K is long), 1 force, -1 never */
+  void* workspace;    /* optional fp32 scratch for stream-K partial tiles (caller-owned, one per stream) or NULL */
+  long long workspace_bytes;
 } dd_gemm_args;
 DD_API int dd_gemm(const dd_gemm_args* args, void* stream);
 

@@ -107,7 +107,46 @@ def test_cta_pair_kernel_equals_single_cta_kernel(M, N, K, taps):
     else:
         a = _mk((M, K), 1); wp = _mk((N, K), 2, K ** -0.5); kw = {}
         ref = a.float() @ wp.float().t() + bias
-    o2 = ops.gemm(a, wp, bias=bias, **kw)
-    o1 = ops.gemm(a, wp, bias=bias, one_cta=True, **kw)
+    o2 = ops.gemm(a, wp, bias=bias, stream_k=-1, **kw)
+    o1 = ops.gemm(a, wp, bias=bias, one_cta=True, stream_k=-1, **kw)
     assert _rel(o2, ref) < 1e-2 and _rel(o1, ref) < 1e-2
     assert torch.equal(o1, o2)   # same accumulation order per output element -> bit-identical
+
+
+@pytest.mark.parametrize("case", ["conv_l3", "conv_small", "linear_res", "linear_rowvec_f32", "one_cta", "dual"])
+def test_stream_k_equals_classic(case):
+    """stream-K (flattened (tile, k-iteration) space cut evenly over the CTA pairs, fp32 partial tiles summed in worker
+    order by a second pass that applies the epilogue) against the one-tile-per-worker kernel and torch fp32"""
+    from dualdiff_b200 import ops, packing
+    kw, kw_ref = {}, {}
+    if case in ("conv_l3", "conv_small"):
+        n, H, W, ci, co = (24, 4, 7, 1280, 1280) if case == "conv_l3" else (3, 7, 13, 192, 200)
+        x = _mk((n, H, W, ci), 1); w = _mk((co, ci, 3, 3), 2, (9 * ci) ** -0.5)
+        bias = torch.randn(co, generator=torch.Generator().manual_seed(3)).cuda()
+        rv = torch.randn(n, co, generator=torch.Generator().manual_seed(6)).cuda()
+        r1 = _mk((n * H * W, co), 4)
+        a, wp = packing.to_padded(x), packing.pack_conv3x3(w)
+        kw = dict(taps=9, conv_hw=(H, W), n_img=n, bias=bias, rowvec=rv, rows_per_img=H * W, res1=r1)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, co)
+        ref = ref + rv.repeat_interleave(H * W, 0) + r1.float()
+    elif case == "dual":
+        M, K1, K2, N = 700, 640, 320, 320
+        a = _mk((M, K1), 1); a2 = _mk((M, K2), 2); wp = _mk((N, K1 + K2), 3, (K1 + K2) ** -0.5)
+        kw = dict(a2=a2)
+        ref = torch.cat([a, a2], 1).float() @ wp.float().t()
+    else:
+        M, N, K = (2688, 1280, 5120) if case != "one_cta" else (100, 328, 2560)
+        a = _mk((M, K), 1); wp = _mk((N, K), 2, K ** -0.5)
+        bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+        r1 = _mk((M, N), 4); r2 = _mk((M, N), 5)
+        ref = a.float() @ wp.float().t() + bias + r1.float() + r2.float()
+        kw = dict(bias=bias, res1=r1, res2=r2)
+        if case == "linear_rowvec_f32":
+            rv = torch.randn(M // 28, N, generator=torch.Generator().manual_seed(6)).cuda()
+            kw.update(rowvec=rv, rows_per_img=28, out_f32=True, act=1)
+            ref = F.silu(ref + rv.repeat_interleave(28, 0))
+    o_sk = ops.gemm(a, wp, stream_k=1, **kw)
+    o_cl = ops.gemm(a, wp, stream_k=-1, **kw)
+    assert _rel(o_sk, ref) < 1e-2 and _rel(o_cl, ref) < 1e-2, (_rel(o_sk, ref), _rel(o_cl, ref))
+    assert (o_sk.float() - o_cl.float()).abs().max() <= 1e-2 * ref.abs().max()
+    assert torch.equal(o_sk, ops.gemm(a, wp, stream_k=1, **kw))   # fixed summation order -> bit-reproducible
