@@ -32,11 +32,18 @@ static constexpr int GEMM_THREADS = 192;      // 2 + 4 epilogue warps (register 
 static constexpr int GEMM_THREADS_MAX = 320;  // 2 + 8 epilogue warps (TMA epilogue)
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARP_BYTES = 32 * 64 * 4;  // per-epilogue-warp transpose buffer (32 rows x 64 fp32)
+// 3x3 conv mode: one staged activation box of 128 + 2 halo rows serves the three kw taps of a kernel row (the UMMA
+// descriptor of tap kw starts kw rows = kw * 128 B into the box: SWIZZLE_128B phases follow the absolute shared-memory
+// address, profiles/micro/desc_shift_test.cu), so the activation crosses the L2 -> SM fabric 3x instead of 9x.
+static constexpr int A_CONV_ROWS = BM + 2;
+static constexpr int A_CONV_BYTES = 17 * 1024;   // 130 rows x 128 B = 16640, slots kept 1024-byte aligned
+static constexpr int A_CONV_TX = A_CONV_ROWS * BK * 2;
 
 struct GemmDev {
   int M, N, K, K1, taps;
   int conv_H, conv_W;  // conv mode (taps == 9): image geometry of the padded layout
   int m_tiles, n_tiles, stages;
+  int a_stages;   // conv mode: slots of the activation ring (stages = slots of the weight ring)
   // epilogue
   void* out;
   long long out_ld;
@@ -91,7 +98,7 @@ struct WorkIter {
 // CTAs' shared memory and write both CTAs' TMEM.  Per SM that halves the B bytes written (TMA) and read (UMMA) per
 // MMA cycle: 128 + 0.5*(8192/BN+...) -- the 128 B/clk shared-memory port is what caps the 1-CTA kernel at ~57 %
 // tensor-pipe activity (ncu, profiles/r01_ncu_conv_*.txt).
-template <int BN, int CG>
+template <int BN, int CG, bool CONV>
 __global__ void __launch_bounds__(GEMM_THREADS_MAX, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -135,7 +142,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, CG * ((blockDim.x - 64) / 32));  // one arrive per epilogue warp (of both CTAs)
     }
-    for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
+    if constexpr (CONV) {
+      for (int s = 0; s < 4; ++s) {
+        mbar_init(smem_u32(&bars[20 + s]), CG);  // activation ring: full
+        mbar_init(smem_u32(&bars[24 + s]), 1);   //                  empty
+      }
+    } else {
+      for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -153,7 +167,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = tmem_ptr_smem;
 
   const int kchunks = (p.K + BK - 1) / BK;
-  const int iters = p.taps * kchunks;
+  // conv mode: an iteration = one (kernel row kh, 64-channel chunk): 1 activation box + 3 weight boxes, 12 UMMAs
+  const int iters = CONV ? 3 * kchunks : p.taps * kchunks;
+  const uint32_t afull_bar = smem_u32(&bars[20]);
+  const uint32_t aempty_bar = smem_u32(&bars[24]);
+  const uint32_t ring_b = CONV ? smem_base + (uint32_t)p.a_stages * A_CONV_BYTES : smem_base;   // weight ring (conv)
+  const uint32_t epi_base = CONV ? ring_b + (uint32_t)stages * B_STAGE_BYTES : smem_base + (uint32_t)stages * STAGE_BYTES;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int pitch = p.conv_W + 1;
 
@@ -169,6 +188,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tile = wi.tile;
         const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
         const int n0 = (tile % p.n_tiles) * BN;
+        if constexpr (CONV) {
+          for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
+            const int kh = it / kchunks;
+            const int kc = (it - kh * kchunks) * BK;
+            const int sa = it_global % p.a_stages;
+            mbar_wait(aempty_bar + 8 * sa, ((it_global / p.a_stages) & 1) ^ 1);
+            const int arow = m0 + (kh - 1) * pitch - 1;   // box rows [arow, arow + 130): taps kw = 0, 1, 2 start at row kw
+            const uint32_t sA = smem_base + sa * A_CONV_BYTES;
+            if constexpr (CG == 1) {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(afull_bar + 8 * sa, A_CONV_TX);
+                if (kc < p.K1) tma_load_2d(sA, &tmA, afull_bar + 8 * sa, kc, arow);
+                else tma_load_2d(sA, &tmA2, afull_bar + 8 * sa, kc - p.K1, arow);
+              }
+            } else {
+              const uint32_t afull_leader = mapa_shared(afull_bar + 8 * sa, 0);
+              if (elect_one()) {
+                if (kc < p.K1) tma_load_2d_2cta(sA, &tmA, afull_leader, kc, arow);
+                else tma_load_2d_2cta(sA, &tmA2, afull_leader, kc - p.K1, arow);
+                if (crank == 0) mbar_arrive_expect_tx(afull_bar + 8 * sa, 2 * A_CONV_TX);
+                else mbar_arrive_cluster(afull_leader);
+              }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t ib = it_global * 3 + kw;
+              const int sb = ib % stages;
+              mbar_wait(empty_bar + 8 * sb, ((ib / stages) & 1) ^ 1);
+              const uint32_t sB = ring_b + sb * B_STAGE_BYTES;
+              const int bcol = (kh * 3 + kw) * p.K + kc;
+              if constexpr (CG == 1) {
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(full_bar + 8 * sb, B_STAGE_BYTES);
+                  tma_load_2d(sB, &tmB, full_bar + 8 * sb, bcol, n0);
+                }
+              } else {
+                const uint32_t full_leader = mapa_shared(full_bar + 8 * sb, 0);
+                if (elect_one()) {
+                  tma_load_2d_2cta(sB, &tmB, full_leader, bcol, n0 + (int)crank * (BN / 2));
+                  if (crank == 0) mbar_arrive_expect_tx(full_bar + 8 * sb, 2 * B_STAGE_BYTES);
+                  else mbar_arrive_cluster(full_leader);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        } else {
         for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
           const int s = it_global % stages;
           const uint32_t ph = (it_global / stages) & 1;
@@ -206,6 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
         }
       }
+        }
     }
   } else if (warp == 1) {
     // ------------------------------- UMMA issuer --------------------------------
@@ -219,6 +287,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+        const int it_first = wi.it0;
+        if constexpr (CONV) {
+          for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
+            const int sa = it_global % p.a_stages;
+            mbar_wait(afull_bar + 8 * sa, (it_global / p.a_stages) & 1);
+            const uint32_t sA = smem_base + sa * A_CONV_BYTES;
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t ib = it_global * 3 + kw;
+              const int sb = ib % stages;
+              mbar_wait(full_bar + 8 * sb, (ib / stages) & 1);
+              tc_fence_after();
+              // tap kw reads box rows [kw, kw + 128): start address kw * 128 B into the (1024-aligned) slot
+              const uint64_t dA = umma_smem_desc(sA + kw * 128, 16, 1024, 2);
+              const uint64_t dB = umma_smem_desc(ring_b + sb * B_STAGE_BYTES, 16, 1024, 2);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint32_t acc = (it != it_first || kw != 0 || k != 0) ? 1u : 0u;
+                  if constexpr (CG == 2) umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
+                  else umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
+                }
+                if constexpr (CG == 2) umma_commit_2cta(empty_bar + 8 * sb, 3); else umma_commit(empty_bar + 8 * sb);
+                if (kw == 2) {   // the activation box is free once the third tap's UMMAs retire
+                  if constexpr (CG == 2) umma_commit_2cta(aempty_bar + 8 * sa, 3); else umma_commit(aempty_bar + 8 * sa);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        } else {
         const int it_first = wi.it0;
         for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
           const int s = it_global % stages;
@@ -244,6 +343,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           __syncwarp();
         }
+        }
         // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
         if (elect_one()) {
           if constexpr (CG == 2) umma_commit_2cta(tfull_bar + 8 * as, 3); else umma_commit(tfull_bar + 8 * as);
@@ -260,17 +360,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t local_tile = 0;
     const int HW1 = (p.conv_H + 1) * pitch;
-    const uint32_t stage_buf = smem_base + stages * STAGE_BYTES + q * EPI_WARP_BYTES;
+    const uint32_t stage_buf = epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+    const int ehalf = (warp - 2) >> 2;                       // warps 2-5: even 64-column chunks, warps 6-9: odd ones
+    const int n_ehalves = (int)(blockDim.x - 64) / 128;
     const int OUTW = p.geglu ? BN / 2 : BN;
     if (p.tma_epi) {
       // ---------------- TMA epilogue (plain GEMM, bf16 out): everything stays in the row-per-thread domain ----------
       // per 64-column chunk: TMEM -> regs, + bias, + residual tile (TMA-loaded into swizzled smem, prefetched one
       // chunk ahead), activation, bf16 pack -> swizzled smem tile -> TMA store.  No strided global access at all.
-      if constexpr (BN % 64 == 0) {
+      if constexpr (BN % 64 == 0 && !CONV) {
         // TMA mode runs 8 epilogue warps: warps 2-5 take the even 64-column chunks, warps 6-9 the odd ones
         // (two warps per TMEM lane quarter -> two warps per scheduler, hiding each other's TMEM/smem latency).
         const int half = (warp - 2) >> 2;
-        const uint32_t my_stage = smem_base + stages * STAGE_BYTES + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+        const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
         const uint32_t out_stage = my_stage;           // 32 rows x 128 B, SWIZZLE_128B
         const uint32_t r1_stage = my_stage + 4096;
         const uint32_t r1_bar = smem_u32(&bars[20 + (warp - 2)]);
@@ -431,8 +533,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
-      for (int c = 0; c < OUTW; c += 64) {
+      for (int c = ehalf * 64; c < OUTW; c += 64 * n_ehalves) {
         const int width = (OUTW - c) < 64 ? (OUTW - c) : 64;  // 64, or 32 for the last chunk of BN = 32/160
+        const int lpr = width >> 3;           // lanes per row: 8 (or 4)
+        const int rpi = 32 / lpr;             // rows per iteration: 4 (or 8)
+        const int nit = 32 / rpi;             // iterations: 8 (or 4)
+        const int k = lane % lpr;             // 8-column group owned by this lane
+        const int col = nout0 + c + k * 8;    // output column of v[0]
+        const bool vec = col + 8 <= n_store;
+        const bool plain = vec && !p.geglu;
+        // ---- prefetch: row mapping, residual rows and bias of this chunk (their latency hides behind the TMEM drain) ----
+        long long orow_j[8];
+        uint32_t vmask = 0;
+        uint4 r1v[8];
+        float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nit) {
+            const int rr = j * rpi + lane / lpr;
+            orow_j[j] = __shfl_sync(0xffffffffu, orow, rr);
+            const int vj = __shfl_sync(0xffffffffu, valid, rr) && (col < n_store);
+            vmask |= (uint32_t)vj << j;
+            r1v[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (plain && vj) {
+              if (p.res1) r1v[j] = *reinterpret_cast<const uint4*>(p.res1 + orow_j[j] * p.res1_ld + col);
+            }
+          }
+        }
+        if (plain && p.bias) {
+          bia0 = *reinterpret_cast<const float4*>(p.bias + col);
+          bia1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+        }
         // ---- TMEM -> registers -> rotated smem (thread = row) ----
 #pragma unroll 1
         for (int h = 0; h < width; h += 32) {
@@ -466,15 +597,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
         // ---- smem -> registers (8 lanes = one row's 64 columns) -> epilogue math -> coalesced global store ----
-        const int lpr = width >> 3;           // lanes per row: 8 (or 4)
-        const int rpi = 32 / lpr;             // rows per iteration: 4 (or 8)
-        const int k = lane % lpr;             // 8-column group owned by this lane
-        const int col = nout0 + c + k * 8;    // output column of v[0]
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += rpi) {
-          const int rr = r0 + lane / lpr;
-          const long long orow_r = __shfl_sync(0xffffffffu, orow, rr);
-          const int valid_r = __shfl_sync(0xffffffffu, valid, rr);
+        long long rv_img = -1;
+        float4 rv0 = make_float4(0.f, 0.f, 0.f, 0.f), rv1 = rv0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nit) {
+          const int rr = j * rpi + lane / lpr;
+          const long long orow_r = orow_j[j];
           const uint32_t rbase = stage_buf + rr * 256;
           const int u0 = 2 * k, u1 = 2 * k + 1;
           const uint32_t p0 = (uint32_t)((u0 & 8) | (((u0 & 7) + (u0 >> 3) + rr) & 7));
@@ -487,31 +616,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p1 << 4)));
             v[4] = __uint_as_float(t0); v[5] = __uint_as_float(t1); v[6] = __uint_as_float(t2); v[7] = __uint_as_float(t3);
           }
-          if (!valid_r || col >= n_store) continue;
-          if (col + 8 <= n_store) {
+          if ((vmask >> j) & 1u) {
+          if (vec) {
             if (!p.geglu) {
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
+              v[0] += bia0.x; v[1] += bia0.y; v[2] += bia0.z; v[3] += bia0.w;
+              v[4] += bia1.x; v[5] += bia1.y; v[6] += bia1.z; v[7] += bia1.w;
               if (p.rowvec) {
-                const float* rv = p.rowvec + (orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col;
-                const float4 b0 = *reinterpret_cast<const float4*>(rv);
-                const float4 b1 = *reinterpret_cast<const float4*>(rv + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                const long long im = orow_r / p.rows_per_img;
+                if (im != rv_img) {   // rows ascend: the per-image vector is reloaded only when the image changes
+                  const float* rv = p.rowvec + im * (long long)p.rowvec_ld + col;
+                  rv0 = *reinterpret_cast<const float4*>(rv);
+                  rv1 = *reinterpret_cast<const float4*>(rv + 4);
+                  rv_img = im;
+                }
+                v[0] += rv0.x; v[1] += rv0.y; v[2] += rv0.z; v[3] += rv0.w;
+                v[4] += rv1.x; v[5] += rv1.y; v[6] += rv1.z; v[7] += rv1.w;
               }
               if (p.res1) {
-                const uint4 r = *reinterpret_cast<const uint4*>(p.res1 + orow_r * p.res1_ld + col);
                 float2 t;
-                t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
-                t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
-                t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
-                t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+                t = unpack_bf16(r1v[j].x); v[0] += t.x; v[1] += t.y;
+                t = unpack_bf16(r1v[j].y); v[2] += t.x; v[3] += t.y;
+                t = unpack_bf16(r1v[j].z); v[4] += t.x; v[5] += t.y;
+                t = unpack_bf16(r1v[j].w); v[6] += t.x; v[7] += t.y;
               }
-              if (p.res2) {
+              if (p.res2) {   // rare (second residual source): loaded in place
                 const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow_r * p.res2_ld + col);
                 float2 t;
                 t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
@@ -552,6 +680,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   reinterpret_cast<bf16*>(outp)[orow_r * out_ld + col + e] = __float2bfloat16(x);
               }
             }
+          }
+          }
           }
         }
         __syncwarp();
@@ -643,21 +773,38 @@ splitk_reduce_kernel(const GemmDev p, const int BN, const int TILE_M, const int 
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int CG>
+template <int BN, int CG, bool CONV>
 static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                           const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + (BN / CG) * BK * 2;
-  const int epi_warps = p.tma_epi ? 8 : 4;
-  int stages = (227 * 1024 - 3072 - epi_warps * EPI_WARP_BYTES) / STAGE_BYTES;
-  if (stages > 8) stages = 8;
-  const int iters = p.taps * ((p.K + BK - 1) / BK);
-  if (stages > iters && iters >= 2) stages = iters;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * STAGE_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
+  constexpr int B_BYTES = (BN / CG) * BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
+  // register epilogue: 4 or 8 warps (DD_EPI8=0/1, A/B switch); the TMA epilogue always runs 8
+  static const int epi8 = getenv("DD_EPI8") ? atoi(getenv("DD_EPI8")) : 1;
+  const int epi_warps = (p.tma_epi || epi8) ? 8 : 4;
+  const int avail = 227 * 1024 - 3072 - epi_warps * EPI_WARP_BYTES;
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int iters = CONV ? 3 * kchunks : p.taps * kchunks;
+  size_t smem;
+  if constexpr (CONV) {
+    int sb = (avail - 3 * A_CONV_BYTES) / B_BYTES;
+    sb = sb > 8 ? 8 : sb < 2 ? 2 : sb;
+    int sa = (avail - sb * B_BYTES) / A_CONV_BYTES;
+    sa = sa > 4 ? 4 : sa < 2 ? 2 : sa;
+    p.stages = sb;
+    p.a_stages = sa;
+    smem = (size_t)sa * A_CONV_BYTES + (size_t)sb * B_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
+  } else {
+    int stages = avail / STAGE_BYTES;
+    if (stages > 8) stages = 8;
+    if (stages > iters && iters >= 2) stages = iters;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    p.a_stages = 0;
+    smem = (size_t)stages * STAGE_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024 - 2048));
     attr_done = true;
   }
@@ -669,7 +816,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   if (p.sk_chunk > 0) workers = (p.m_tiles * p.n_tiles * iters + p.sk_chunk - 1) / p.sk_chunk;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * CG);
-  cfg.blockDim = dim3(p.tma_epi ? GEMM_THREADS_MAX : GEMM_THREADS);
+  cfg.blockDim = dim3(epi_warps == 8 ? GEMM_THREADS_MAX : GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -679,15 +826,19 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG>, tmA, tmA2, tmB, tmOut, tmR1, p));
+  DD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, CONV>, tmA, tmA2, tmB, tmOut, tmR1, p));
   return 0;
 }
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB,
                        const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream, int cg) {
-  if (cg == 2) return launch_gemm_cg<BN, 2>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
-  return launch_gemm_cg<BN, 1>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+  if (p.taps == 9) {
+    if (cg == 2) return launch_gemm_cg<BN, 2, true>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+    return launch_gemm_cg<BN, 1, true>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+  }
+  if (cg == 2) return launch_gemm_cg<BN, 2, false>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
+  return launch_gemm_cg<BN, 1, false>(tmA, tmA2, tmB, tmOut, tmR1, p, stream);
 }
 
 static int pick_bn_tma(int N, int geglu) {
@@ -766,10 +917,11 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
     const int tile_m = BM * cg;
     const long tiles = (long)((a->M + tile_m - 1) / tile_m) * ((a->N + bn_sk - 1) / bn_sk);
     const long W = num_sms() / cg;
-    const long iters = (long)a->taps * ((a->K + BK - 1) / BK);
+    const long kch = (a->K + BK - 1) / BK;
+    const long iters = a->taps == 9 ? 3 * kch : kch;   // conv: one iteration = a kernel row x 64 channels (12 UMMAs)
     const long waves = (tiles + W - 1) / W;
     const double eff = (double)tiles / (double)(waves * W);
-    if (a->stream_k == 1 || (iters >= 32 && eff < 0.75 && tiles <= 4 * W)) {
+    if (a->stream_k == 1 || (iters * (a->taps == 9 ? 3 : 1) >= 32 && eff < 0.75 && tiles <= 4 * W)) {
       const long total = tiles * iters;
       const long chunk = (total + W - 1) / W;
       const long maxc = (iters + chunk - 2) / chunk + 1;
@@ -788,10 +940,11 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
     DD_CHECK(a->stream_k != 1, -1, "dd_gemm: stream-K needs a workspace, no GEGLU and N %% 4 == 0");
   }
   CUtensorMap tmA, tmA2, tmB, tmOut, tmR1;
-  int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, BM, BK);
+  const uint32_t a_box_rows = a->taps == 9 ? A_CONV_ROWS : BM;   // conv: 128 rows + the kw = -1 / +1 halo rows
+  int rc = make_tmap_2d_bf16(&tmA, a->a, (uint64_t)a->M, (uint64_t)K1, (uint64_t)a->a_ld, a_box_rows, BK);
   if (rc) return rc;
   if (a->a2 != nullptr) {
-    rc = make_tmap_2d_bf16(&tmA2, a->a2, (uint64_t)a->M, (uint64_t)(a->K - K1), (uint64_t)a->a2_ld, BM, BK);
+    rc = make_tmap_2d_bf16(&tmA2, a->a2, (uint64_t)a->M, (uint64_t)(a->K - K1), (uint64_t)a->a2_ld, a_box_rows, BK);
     if (rc) return rc;
   } else {
     tmA2 = tmA;
@@ -841,7 +994,7 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
     const int tile_m = BM * cg;
     p.m_tiles = (p.M + tile_m - 1) / tile_m;
     p.n_tiles = (p.N + bn - 1) / bn;
-    const int iters = p.taps * ((p.K + BK - 1) / BK);
+    const int iters = (p.taps == 9 ? 3 : 1) * ((p.K + BK - 1) / BK);
     splitk_reduce_kernel<<<dim3(p.m_tiles * p.n_tiles, tile_m / 32), 256, 0, stream>>>(p, bn, tile_m, iters);
     DD_CUDA(cudaGetLastError());
     count_launch(1);
