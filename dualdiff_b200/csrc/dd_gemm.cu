@@ -182,18 +182,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // descriptors in uniform registers); one elected lane issues.  Inside `if (lane == 0)` every operand of
     // UTMALDG / UTCHMMA had to be moved vector->uniform (R2UR) per instruction, which made the kernel issue-bound.
     {
-      uint32_t it_global = 0;
+      // ring positions are carried as (slot, parity) counters: no integer division in the steady-state loops
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
       while (wi.next()) {
         const int tile = wi.tile;
         const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
         const int n0 = (tile % p.n_tiles) * BN;
         if constexpr (CONV) {
-          for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
-            const int kh = it / kchunks;
-            const int kc = (it - kh * kchunks) * BK;
-            const int sa = it_global % p.a_stages;
-            mbar_wait(aempty_bar + 8 * sa, ((it_global / p.a_stages) & 1) ^ 1);
+          int kh = wi.it0 / kchunks;
+          int kc = (wi.it0 - kh * kchunks) * BK;
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            mbar_wait(aempty_bar + 8 * sa, pa ^ 1);
             const int arow = m0 + (kh - 1) * pitch - 1;   // box rows [arow, arow + 130): taps kw = 0, 1, 2 start at row kw
             const uint32_t sA = smem_base + sa * A_CONV_BYTES;
             if constexpr (CG == 1) {
@@ -212,11 +212,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
             __syncwarp();
-#pragma unroll 1
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
+#pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t ib = it_global * 3 + kw;
-              const int sb = ib % stages;
-              mbar_wait(empty_bar + 8 * sb, ((ib / stages) & 1) ^ 1);
+              mbar_wait(empty_bar + 8 * sb, pb ^ 1);
               const uint32_t sB = ring_b + sb * B_STAGE_BYTES;
               const int bcol = (kh * 3 + kw) * p.K + kc;
               if constexpr (CG == 1) {
@@ -233,53 +232,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               }
               __syncwarp();
+              if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
             }
+            kc += BK;
+            if (kc >= p.K) { kc = 0; ++kh; }
           }
         } else {
-        for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
-          const int s = it_global % stages;
-          const uint32_t ph = (it_global / stages) & 1;
-          mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          const int tap = it / kchunks;
-          const int kc = (it - tap * kchunks) * BK;
-          int arow = m0;
-          if (p.taps == 9) arow += (tap / 3 - 1) * pitch + (tap % 3 - 1);
-          const uint32_t sA = smem_base + s * STAGE_BYTES;
-          const uint32_t sB = sA + A_STAGE_BYTES;
-          if constexpr (CG == 1) {
-            if (elect_one()) {
-              mbar_arrive_expect_tx(full_bar + 8 * s, STAGE_BYTES);
-              if (kc < p.K1)
-                tma_load_2d(sA, &tmA, full_bar + 8 * s, kc, arow);
-              else
-                tma_load_2d(sA, &tmA2, full_bar + 8 * s, kc - p.K1, arow);
-              tma_load_2d(sB, &tmB, full_bar + 8 * s, tap * p.K + kc, n0);
+          int tap = wi.it0 / kchunks;
+          int kc = (wi.it0 - tap * kchunks) * BK;
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            mbar_wait(empty_bar + 8 * sb, pb ^ 1);
+            const uint32_t sA = smem_base + sb * STAGE_BYTES;
+            const uint32_t sB = sA + A_STAGE_BYTES;
+            if constexpr (CG == 1) {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(full_bar + 8 * sb, STAGE_BYTES);
+                if (kc < p.K1)
+                  tma_load_2d(sA, &tmA, full_bar + 8 * sb, kc, m0);
+                else
+                  tma_load_2d(sA, &tmA2, full_bar + 8 * sb, kc - p.K1, m0);
+                tma_load_2d(sB, &tmB, full_bar + 8 * sb, tap * p.K + kc, n0);
+              }
+            } else {
+              // both CTAs load into their own smem; every byte is credited to the LEADER's full barrier
+              const uint32_t full_leader = mapa_shared(full_bar + 8 * sb, 0);
+              if (elect_one()) {
+                if (kc < p.K1)
+                  tma_load_2d_2cta(sA, &tmA, full_leader, kc, m0);
+                else
+                  tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, m0);
+                tma_load_2d_2cta(sB, &tmB, full_leader, tap * p.K + kc, n0 + (int)crank * (BN / 2));
+                if (crank == 0)
+                  mbar_arrive_expect_tx(full_bar + 8 * sb, 2 * STAGE_BYTES);
+                else
+                  mbar_arrive_cluster(full_leader);
+              }
             }
-          } else {
-            // both CTAs load into their own smem; every byte is credited to the LEADER's full barrier
-            const uint32_t full_leader = mapa_shared(full_bar + 8 * s, 0);
-            if (elect_one()) {
-              if (kc < p.K1)
-                tma_load_2d_2cta(sA, &tmA, full_leader, kc, arow);
-              else
-                tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, arow);
-              tma_load_2d_2cta(sB, &tmB, full_leader, tap * p.K + kc, n0 + (int)crank * (BN / 2));
-              if (crank == 0)
-                mbar_arrive_expect_tx(full_bar + 8 * s, 2 * STAGE_BYTES);
-              else
-                mbar_arrive_cluster(full_leader);
-            }
+            __syncwarp();
+            if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
+            kc += BK;
+            if (kc >= p.K) { kc = 0; ++tap; }
           }
-          __syncwarp();
         }
       }
-        }
     }
   } else if (warp == 1) {
     // ------------------------------- UMMA issuer --------------------------------
     if (crank == 0) {   // CG = 2: only the leader CTA issues (its UMMAs drive both SMs); warp-uniform loop, elected issue
-      uint32_t it_global = 0;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring (slot, parity) counters
       uint32_t local_tile = 0;
+      // descriptor = constant fields | (address >> 4): shared-memory addresses are < 256 KB, so no masking is needed
+      const uint64_t DESC0 = umma_smem_desc(0, 16, 1024, 2);
       WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
       for (; wi.next(); ++local_tile) {
         const uint32_t as = local_tile & 1;
@@ -287,25 +290,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * ACC_COLS;
-        const int it_first = wi.it0;
+        uint32_t fresh = 0;                       // becomes 1 after the first UMMA of this segment
         if constexpr (CONV) {
-          for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
-            const int sa = it_global % p.a_stages;
-            mbar_wait(afull_bar + 8 * sa, (it_global / p.a_stages) & 1);
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            mbar_wait(afull_bar + 8 * sa, pa);
             const uint32_t sA = smem_base + sa * A_CONV_BYTES;
-#pragma unroll 1
+#pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const uint32_t ib = it_global * 3 + kw;
-              const int sb = ib % stages;
-              mbar_wait(full_bar + 8 * sb, (ib / stages) & 1);
+              mbar_wait(full_bar + 8 * sb, pb);
               tc_fence_after();
               // tap kw reads box rows [kw, kw + 128): start address kw * 128 B into the (1024-aligned) slot
-              const uint64_t dA = umma_smem_desc(sA + kw * 128, 16, 1024, 2);
-              const uint64_t dB = umma_smem_desc(ring_b + sb * B_STAGE_BYTES, 16, 1024, 2);
+              const uint64_t dA = DESC0 + ((sA + kw * 128) >> 4);
+              const uint64_t dB = DESC0 + ((ring_b + sb * B_STAGE_BYTES) >> 4);
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                  const uint32_t acc = (it != it_first || kw != 0 || k != 0) ? 1u : 0u;
+                  const uint32_t acc = (k != 0) ? 1u : fresh;
                   if constexpr (CG == 2) umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
                   else umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
                 }
@@ -315,34 +315,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
               }
               __syncwarp();
+              fresh = 1;
+              if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
             }
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
         } else {
-        const int it_first = wi.it0;
-        for (int it = wi.it0; it < wi.it1; ++it, ++it_global) {
-          const int s = it_global % stages;
-          const uint32_t ph = (it_global / stages) & 1;
-          mbar_wait(full_bar + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sA = smem_base + s * STAGE_BYTES;
-          const uint32_t sB = sA + A_STAGE_BYTES;
-          const uint64_t dA = umma_smem_desc(sA, 16, 1024, 2);
-          const uint64_t dB = umma_smem_desc(sB, 16, 1024, 2);
-          if (elect_one()) {
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            mbar_wait(full_bar + 8 * sb, pb);
+            tc_fence_after();
+            const uint32_t sA = smem_base + sb * STAGE_BYTES;
+            const uint64_t dA = DESC0 + (sA >> 4);
+            const uint64_t dB = DESC0 + ((sA + A_STAGE_BYTES) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
-              if constexpr (CG == 2) {
-                umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it != it_first || k != 0) ? 1u : 0u);
-              } else {
-                umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, (it != it_first || k != 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the >>4 address field
+                const uint32_t acc = (k != 0) ? 1u : fresh;
+                if constexpr (CG == 2) umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
+                else umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
               }
+              // frees the smem slot (in both CTAs of a pair) when these UMMAs retire
+              if constexpr (CG == 2) umma_commit_2cta(empty_bar + 8 * sb, 3); else umma_commit(empty_bar + 8 * sb);
             }
-            // frees the smem slot (in both CTAs of a pair) when these UMMAs retire
-            if constexpr (CG == 2) umma_commit_2cta(empty_bar + 8 * s, 3); else umma_commit(empty_bar + 8 * s);
+            __syncwarp();
+            fresh = 1;
+            if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
           }
-          __syncwarp();
-        }
         }
         // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
         if (elect_one()) {
