@@ -499,67 +499,102 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) bulk_wait0();
       }
     } else {
+    // ---------------- register epilogue (conv scatter, fp32 out, per-image vector, stream-K partials) ----------------
+    // Per 64-column chunk: TMEM -> regs -> bank-rotated smem (thread = row) -> regs (8 lanes = one row's 64 columns) ->
+    // bias / per-image vector / residual / activation -> 16-byte row-segment stores.  Residual rows are pulled into L2
+    // one tile ahead (prefetch.global.L2) and into registers one chunk ahead, the first chunk's before the wait on the
+    // accumulator, so their HBM latency never sits on the tile's critical path.
     WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
     const bool sk = p.sk_chunk != 0;
     const int n_store = sk ? BN : p.n_store;
-    const long long out_ld = sk ? (long long)BN : p.out_ld;
+    const int out_ld = sk ? BN : (int)p.out_ld;
     void* const outp = sk ? (void*)p.ws : p.out;
-    for (; wi.next(); ++local_tile) {
-      const int tile = wi.tile;
-      const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
-      const int n0 = (tile % p.n_tiles) * BN;
-      const int nout0 = sk ? 0 : p.geglu ? (n0 / BN) * (BN / 2) : n0;
-      const uint32_t as = local_tile & 1;
-      const uint32_t aph = (local_tile >> 1) & 1;
-      mbar_wait(tfull_bar + 8 * as, aph);
-      tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      int valid = m < p.M;
-      long long orow = m;
+    const bool has_r1 = p.res1 != nullptr && !p.geglu;
+    const int rowt = (int)crank * BM + q * 32 + lane;   // row of this thread inside the tile
+
+    // padded-pixel row m -> (valid, compact output row)
+    auto map_row = [&](int tile, int& valid, int& orow) {
+      const int m = (tile / p.n_tiles) * TILE_M + rowt;
+      valid = m < p.M;
+      orow = m;
       if (sk) {
         // raw partial accumulator -> workspace slot of (tile, contributor); every row of the tile is written
         const int slot = tile * p.sk_maxc + (worker - (tile * iters) / p.sk_chunk);
         valid = 1;
-        orow = (long long)slot * TILE_M + (int)crank * BM + q * 32 + lane;
+        orow = slot * TILE_M + rowt;
       } else if (p.taps == 9) {
         const int img = m / HW1;
         const int rem = m - img * HW1;
         const int hp = rem / pitch;
         const int wp = rem - hp * pitch;
         valid = valid && (hp < p.conv_H) && (wp < p.conv_W);
-        orow = ((long long)img * p.conv_H + hp) * p.conv_W + wp;
+        orow = (img * p.conv_H + hp) * p.conv_W + wp;
       }
+    };
+    // chunk geometry of this lane: 8 lanes own the 64 columns of one row (4 lanes for a 32-column tail chunk)
+    struct Chunk { int lpr, rpi, nit, col; bool vec; };
+    auto chunk_of = [&](int nout0, int c) {
+      Chunk g;
+      const int width = (OUTW - c) < 64 ? (OUTW - c) : 64;
+      g.lpr = width >> 3;
+      g.rpi = 32 / g.lpr;
+      g.nit = 32 / g.rpi;
+      g.col = nout0 + c + (lane % g.lpr) * 8;
+      g.vec = g.col + 8 <= n_store;
+      return g;
+    };
+    int orow_j[8];
+    uint32_t vmask = 0;
+    uint4 r1v[8];
+    auto prefetch_chunk = [&](const Chunk& g, int valid, int orow) {
+      vmask = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < g.nit) {
+          const int rr = j * g.rpi + lane / g.lpr;
+          orow_j[j] = __shfl_sync(0xffffffffu, orow, rr);
+          const int vj = __shfl_sync(0xffffffffu, valid, rr) && (g.col < n_store);
+          vmask |= (uint32_t)vj << j;
+          r1v[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_r1 && g.vec && vj) r1v[j] = *reinterpret_cast<const uint4*>(p.res1 + (long long)orow_j[j] * p.res1_ld + g.col);
+        }
+      }
+    };
+
+    bool have = wi.next();
+    int valid = 0, orow = 0;
+    if (have) map_row(wi.tile, valid, orow);
+    for (; have; ++local_tile) {
+      const int tile = wi.tile;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const int nout0 = sk ? 0 : p.geglu ? (n0 / BN) * (BN / 2) : n0;
+      const uint32_t as = local_tile & 1;
+      const uint32_t aph = (local_tile >> 1) & 1;
+      Chunk g = chunk_of(nout0, ehalf * 64);
+      if (ehalf * 64 < OUTW) prefetch_chunk(g, valid, orow);          // first chunk's residual rows: before the wait
+      // next tile: row mapping now, residual rows into L2 (one tile = several microseconds ahead)
+      have = wi.next();
+      int valid_n = 0, orow_n = 0;
+      if (have) {
+        map_row(wi.tile, valid_n, orow_n);
+        if (has_r1 && valid_n) {
+          const int nn0 = (wi.tile % p.n_tiles) * BN;
+          const bf16* rp = p.res1 + (long long)orow_n * p.res1_ld + nn0;
+          for (int cc = ehalf * 64; cc < OUTW && nn0 + cc < n_store; cc += 64 * n_ehalves)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + cc));
+        }
+      }
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
       const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
       for (int c = ehalf * 64; c < OUTW; c += 64 * n_ehalves) {
         const int width = (OUTW - c) < 64 ? (OUTW - c) : 64;  // 64, or 32 for the last chunk of BN = 32/160
-        const int lpr = width >> 3;           // lanes per row: 8 (or 4)
-        const int rpi = 32 / lpr;             // rows per iteration: 4 (or 8)
-        const int nit = 32 / rpi;             // iterations: 8 (or 4)
-        const int k = lane % lpr;             // 8-column group owned by this lane
-        const int col = nout0 + c + k * 8;    // output column of v[0]
-        const bool vec = col + 8 <= n_store;
-        const bool plain = vec && !p.geglu;
-        // ---- prefetch: row mapping, residual rows and bias of this chunk (their latency hides behind the TMEM drain) ----
-        long long orow_j[8];
-        uint32_t vmask = 0;
-        uint4 r1v[8];
+        const int k = lane % g.lpr;
+        const int col = g.col;
         float4 bia0 = make_float4(0.f, 0.f, 0.f, 0.f), bia1 = bia0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nit) {
-            const int rr = j * rpi + lane / lpr;
-            orow_j[j] = __shfl_sync(0xffffffffu, orow, rr);
-            const int vj = __shfl_sync(0xffffffffu, valid, rr) && (col < n_store);
-            vmask |= (uint32_t)vj << j;
-            r1v[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (plain && vj) {
-              if (p.res1) r1v[j] = *reinterpret_cast<const uint4*>(p.res1 + orow_j[j] * p.res1_ld + col);
-            }
-          }
-        }
-        if (plain && p.bias) {
+        if (g.vec && !p.geglu && p.bias) {
           bia0 = *reinterpret_cast<const float4*>(p.bias + col);
           bia1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
         }
@@ -569,12 +604,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t a[32];
           tmem_ld_32x32(tmem_acc + c + h, a);
           if (p.geglu) {
-            uint32_t g[32];
-            tmem_ld_32x32(tmem_acc + BN / 2 + c + h, g);
+            uint32_t gt[32];
+            tmem_ld_32x32(tmem_acc + BN / 2 + c + h, gt);
             tmem_ld_wait();
-#pragma unroll
+#pragma unroll 4
             for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(a[j]), gg = __uint_as_float(g[j]);
+              float v = __uint_as_float(a[j]), gg = __uint_as_float(gt[j]);
               if (p.bias) {
                 v += p.bias[n0 + c + h + j];
                 gg += p.bias[n0 + BN / 2 + c + h + j];
@@ -596,94 +631,106 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
         // ---- smem -> registers (8 lanes = one row's 64 columns) -> epilogue math -> coalesced global store ----
-        long long rv_img = -1;
-        float4 rv0 = make_float4(0.f, 0.f, 0.f, 0.f), rv1 = rv0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nit) {
-          const int rr = j * rpi + lane / lpr;
-          const long long orow_r = orow_j[j];
-          const uint32_t rbase = stage_buf + rr * 256;
-          const int u0 = 2 * k, u1 = 2 * k + 1;
-          const uint32_t p0 = (uint32_t)((u0 & 8) | (((u0 & 7) + (u0 >> 3) + rr) & 7));
-          const uint32_t p1 = (uint32_t)((u1 & 8) | (((u1 & 7) + (u1 >> 3) + rr) & 7));
-          float v[8];
-          {
-            uint32_t t0, t1, t2, t3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p0 << 4)));
-            v[0] = __uint_as_float(t0); v[1] = __uint_as_float(t1); v[2] = __uint_as_float(t2); v[3] = __uint_as_float(t3);
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p1 << 4)));
-            v[4] = __uint_as_float(t0); v[5] = __uint_as_float(t1); v[6] = __uint_as_float(t2); v[7] = __uint_as_float(t3);
-          }
-          if ((vmask >> j) & 1u) {
-          if (vec) {
-            if (!p.geglu) {
-              v[0] += bia0.x; v[1] += bia0.y; v[2] += bia0.z; v[3] += bia0.w;
-              v[4] += bia1.x; v[5] += bia1.y; v[6] += bia1.z; v[7] += bia1.w;
-              if (p.rowvec) {
-                const long long im = orow_r / p.rows_per_img;
-                if (im != rv_img) {   // rows ascend: the per-image vector is reloaded only when the image changes
-                  const float* rv = p.rowvec + im * (long long)p.rowvec_ld + col;
-                  rv0 = *reinterpret_cast<const float4*>(rv);
-                  rv1 = *reinterpret_cast<const float4*>(rv + 4);
-                  rv_img = im;
-                }
-                v[0] += rv0.x; v[1] += rv0.y; v[2] += rv0.z; v[3] += rv0.w;
-                v[4] += rv1.x; v[5] += rv1.y; v[6] += rv1.z; v[7] += rv1.w;
-              }
-              if (p.res1) {
-                float2 t;
-                t = unpack_bf16(r1v[j].x); v[0] += t.x; v[1] += t.y;
-                t = unpack_bf16(r1v[j].y); v[2] += t.x; v[3] += t.y;
-                t = unpack_bf16(r1v[j].z); v[4] += t.x; v[5] += t.y;
-                t = unpack_bf16(r1v[j].w); v[6] += t.x; v[7] += t.y;
-              }
-              if (p.res2) {   // rare (second residual source): loaded in place
-                const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow_r * p.res2_ld + col);
-                float2 t;
-                t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
-                t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
-                t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
-                t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
-              }
-              if (p.act == 1) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
-              }
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(outp) + orow_r * out_ld + col;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(outp) + orow_r * out_ld + col;
-              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                        pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            }
-          } else {
-            // ragged right edge (N not a multiple of 8, e.g. conv_out N = 4): scalar path
-#pragma unroll
+        if (nout0 + c + width > n_store) {
+          // ragged right edge inside this chunk (N not a multiple of 8, e.g. conv_out N = 4): every lane takes a compact
+          // scalar loop straight from the staging rows (warp-uniform branch; rare)
+#pragma unroll 1
+          for (int j = 0; j < g.nit; ++j) {
+            const int rr = j * g.rpi + lane / g.lpr;
+            const long long orow_r = __shfl_sync(0xffffffffu, orow, rr);
+            const int vr = __shfl_sync(0xffffffffu, valid, rr);
+#pragma unroll 1
             for (int e = 0; e < 8; ++e) {
-              if (col + e < n_store) {
-                float x = v[e];
-                if (!p.geglu) {
-                  if (p.bias) x += p.bias[col + e];
-                  if (p.rowvec) x += p.rowvec[(orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col + e];
-                  if (p.res1) x += __bfloat162float(p.res1[orow_r * p.res1_ld + col + e]);
-                  if (p.res2) x += __bfloat162float(p.res2[orow_r * p.res2_ld + col + e]);
-                  if (p.act == 1) x = silu_f(x);
-                }
-                if (p.out_f32)
-                  reinterpret_cast<float*>(outp)[orow_r * out_ld + col + e] = x;
-                else
-                  reinterpret_cast<bf16*>(outp)[orow_r * out_ld + col + e] = __float2bfloat16(x);
+              const int ci = k * 8 + e, uu = ci >> 2;
+              if (!vr || col + e >= n_store) continue;
+              const uint32_t pu = (uint32_t)((uu & 8) | (((uu & 7) + (uu >> 3) + rr) & 7));
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage_buf + rr * 256 + (pu << 4) + (ci & 3) * 4));
+              if (!p.geglu) {
+                if (p.bias) x += p.bias[col + e];
+                if (p.rowvec) x += p.rowvec[(orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col + e];
+                if (p.res1) x += __bfloat162float(p.res1[orow_r * p.res1_ld + col + e]);
+                if (p.res2) x += __bfloat162float(p.res2[orow_r * p.res2_ld + col + e]);
+                if (p.act == 1) x = silu_f(x);
               }
+              if (p.out_f32)
+                reinterpret_cast<float*>(outp)[orow_r * out_ld + col + e] = x;
+              else
+                reinterpret_cast<bf16*>(outp)[orow_r * out_ld + col + e] = __float2bfloat16(x);
             }
           }
-          }
+        } else if (g.vec) {
+          int rv_img = -1;
+          float4 rv0 = make_float4(0.f, 0.f, 0.f, 0.f), rv1 = rv0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < g.nit && ((vmask >> j) & 1u)) {
+              const int rr = j * g.rpi + lane / g.lpr;
+              const long long orow_r = orow_j[j];
+              const uint32_t rbase = stage_buf + rr * 256;
+              const int u0 = 2 * k, u1 = 2 * k + 1;
+              const uint32_t p0 = (uint32_t)((u0 & 8) | (((u0 & 7) + (u0 >> 3) + rr) & 7));
+              const uint32_t p1 = (uint32_t)((u1 & 8) | (((u1 & 7) + (u1 >> 3) + rr) & 7));
+              float v[8];
+              {
+                uint32_t t0, t1, t2, t3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p0 << 4)));
+                v[0] = __uint_as_float(t0); v[1] = __uint_as_float(t1); v[2] = __uint_as_float(t2); v[3] = __uint_as_float(t3);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3) : "r"(rbase + (p1 << 4)));
+                v[4] = __uint_as_float(t0); v[5] = __uint_as_float(t1); v[6] = __uint_as_float(t2); v[7] = __uint_as_float(t3);
+              }
+              if (!p.geglu) {
+                v[0] += bia0.x; v[1] += bia0.y; v[2] += bia0.z; v[3] += bia0.w;
+                v[4] += bia1.x; v[5] += bia1.y; v[6] += bia1.z; v[7] += bia1.w;
+                if (p.rowvec) {
+                  const int im = (int)(orow_r / p.rows_per_img);
+                  if (im != rv_img) {   // rows ascend: the per-image vector is reloaded only when the image changes
+                    const float* rv = p.rowvec + (long long)im * p.rowvec_ld + col;
+                    rv0 = *reinterpret_cast<const float4*>(rv);
+                    rv1 = *reinterpret_cast<const float4*>(rv + 4);
+                    rv_img = im;
+                  }
+                  v[0] += rv0.x; v[1] += rv0.y; v[2] += rv0.z; v[3] += rv0.w;
+                  v[4] += rv1.x; v[5] += rv1.y; v[6] += rv1.z; v[7] += rv1.w;
+                }
+                if (p.res1) {
+                  float2 t;
+                  t = unpack_bf16(r1v[j].x); v[0] += t.x; v[1] += t.y;
+                  t = unpack_bf16(r1v[j].y); v[2] += t.x; v[3] += t.y;
+                  t = unpack_bf16(r1v[j].z); v[4] += t.x; v[5] += t.y;
+                  t = unpack_bf16(r1v[j].w); v[6] += t.x; v[7] += t.y;
+                }
+                if (p.res2) {   // rare (second residual source): loaded in place
+                  const uint4 r = *reinterpret_cast<const uint4*>(p.res2 + orow_r * p.res2_ld + col);
+                  float2 t;
+                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+                }
+                if (p.act == 1) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+                }
+              }
+              if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(outp) + orow_r * out_ld + col;
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                bf16* o = reinterpret_cast<bf16*>(outp) + orow_r * out_ld + col;
+                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                          pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              }
+            }
           }
         }
         __syncwarp();
+        // next chunk of this warp: its residual rows go to registers now
+        if (c + 64 * n_ehalves < OUTW) {
+          g = chunk_of(nout0, c + 64 * n_ehalves);
+          prefetch_chunk(g, valid, orow);
+        }
       }
       // release the accumulator buffer back to the MMA warp
       tc_fence_before();
@@ -692,6 +739,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (crank == 0) mbar_arrive(tempty_bar + 8 * as);
         else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
       }
+      valid = valid_n;
+      orow = orow_n;
     }
     }
   }
