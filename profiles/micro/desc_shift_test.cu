@@ -7,14 +7,15 @@
 #include <cstdlib>
 #include <vector>
 
+#include <cuda_fp16.h>
 #include "dd_common.cuh"
 
 namespace dd { void set_error(const char*, ...) {} }
 using namespace dd;
 
-constexpr int ROWS = 144, N = 64, K = 64, NMODE = 16;
+constexpr int ROWS = 144, N = 64, K = 64, NMODE = 17;   // mode 16: A = fp16, B = bf16 (mixed operand formats)
 
-__global__ void __launch_bounds__(128) k(const bf16* A, const bf16* B, float* out) {
+__global__ void __launch_bounds__(128) k(const bf16* A, const bf16* B, float* out, const __half* A16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -45,13 +46,22 @@ __global__ void __launch_bounds__(128) k(const bf16* A, const bf16* B, float* ou
   const uint32_t tmem = tptr;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, N, 0, 0);
   for (int mode = 0; mode < NMODE; ++mode) {
-    const int d = mode >> 1;
+    const int d = mode == 16 ? 0 : mode >> 1;
     const uint64_t bo = (mode & 1) ? (uint64_t)d : 0ull;
+    if (mode == 16) {   // refill A with fp16 data
+      for (int i = threadIdx.x; i < ROWS * 8; i += blockDim.x) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(gen + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(A16 + r * K + c * 8);
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+    }
+    const uint32_t idesc = mode == 16 ? (IDESC & ~(7u << 7)) : IDESC;   // a_format: 1 = bf16, 0 = f16
     if (threadIdx.x == 0) {
       for (int kk = 0; kk < K / 16; ++kk) {
         const uint64_t dA = umma_smem_desc(sA + d * 128, 16, 1024, 2) | (bo << 49);
         const uint64_t dB = umma_smem_desc(sB, 16, 1024, 2);
-        umma_bf16(tmem, dA + 2 * kk, dB + 2 * kk, IDESC, kk != 0 ? 1u : 0u);
+        umma_bf16(tmem, dA + 2 * kk, dB + 2 * kk, idesc, kk != 0 ? 1u : 0u);
       }
       umma_commit(smem_u32(&bar));
     }
@@ -77,19 +87,24 @@ int main() {
   for (size_t i = 0; i < hA.size(); ++i) { fA[i] = (float)(rand() % 17 - 8); hA[i] = __float2bfloat16(fA[i]); }
   for (size_t i = 0; i < hB.size(); ++i) { fB[i] = (float)(rand() % 9 - 4); hB[i] = __float2bfloat16(fB[i]); }
   bf16 *dA, *dB;
+  std::vector<__half> hA16(ROWS * K);
+  for (size_t i = 0; i < hA16.size(); ++i) hA16[i] = __float2half(fA[i]);
+  __half* dA16;
+  cudaMalloc(&dA16, hA16.size() * 2);
+  cudaMemcpy(dA16, hA16.data(), hA16.size() * 2, cudaMemcpyHostToDevice);
   float* dO;
   cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dO, (size_t)NMODE * 128 * N * 4);
   cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice);
   const int smem = (ROWS + N) * 128 + 1024;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k<<<1, 128, smem>>>(dA, dB, dO);
+  k<<<1, 128, smem>>>(dA, dB, dO, dA16);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
   std::vector<float> hO((size_t)NMODE * 128 * N);
   cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost);
   for (int mode = 0; mode < NMODE; ++mode) {
-    const int d = mode >> 1;
+    const int d = mode == 16 ? 0 : mode >> 1;
     int bad = 0;
     for (int r = 0; r < 128; ++r)
       for (int n = 0; n < N; ++n) {
@@ -97,7 +112,8 @@ int main() {
         for (int kk = 0; kk < K; ++kk) ref += fA[(r + d) * K + kk] * fB[n * K + kk];
         if (ref != hO[((size_t)mode * 128 + r) * N + n]) ++bad;
       }
-    printf("row shift %d, base_offset %d: %s (%d / %d mismatches)\n", d, (mode & 1) ? d : 0, bad ? "WRONG" : "exact", bad, 128 * N);
+    if (mode == 16) printf("A = fp16, B = bf16 (mixed formats): %s (%d / %d mismatches)\n", bad ? "WRONG" : "exact", bad, 128 * N);
+    else printf("row shift %d, base_offset %d: %s (%d / %d mismatches)\n", d, (mode & 1) ? d : 0, bad ? "WRONG" : "exact", bad, 128 * N);
   }
   return 0;
 }
