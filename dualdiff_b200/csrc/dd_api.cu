@@ -100,4 +100,9 @@ int dd_attention(const dd_attention_args* args, void* stream) {
   if (rc == 0) dd::count_launch();
   return rc;
 }
+int dd_temporal_attention(const dd_temporal_attention_args* args, void* stream) {
+  int rc = dd::temporal_attention_run(args, reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) dd::count_launch();
+  return rc;
+}
 }

@@ -10,5 +10,6 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream);
 long long groupnorm_scratch_floats(int n_img, int C, int HW);
 int layernorm_run(const dd_layernorm_args* a, cudaStream_t stream);
 int attention_run(const dd_attention_args* a, cudaStream_t stream);
+int temporal_attention_run(const dd_temporal_attention_args* a, cudaStream_t stream);
 void count_launch(int n = 1);
 }  // namespace dd

@@ -114,6 +114,10 @@ class Packer:
             wc, bc = f("connector.weight").double(), f("connector.bias").double()
             self.put(p + ".attn4.oc.w", (wc @ wo).float().to(BF))          # connector o to_out, fused
             self.put(p + ".attn4.oc.b", self.f32(2.0 * (wc @ bo) + bc))    # bias counted twice (blocks.py:203-217)
+        if (p + ".attn_temp.to_q.weight") in self.sd:   # temporal block of the video configuration (BASELINE config 5)
+            self.norm(p + ".norm_temp")
+            self.attn_self(p + ".attn_temp", d)
+            self.lin(p + ".attn_temp.to_out.0")
         wg, bg = pack_geglu(f("ff.net.0.proj.weight"), f("ff.net.0.proj.bias"))
         self.put(p + ".ff.geglu.w", wg); self.put(p + ".ff.geglu.b", bg)
         self.lin(p + ".ff.net.2")
@@ -228,6 +232,9 @@ class StepCtx:
     kv_map: Optional[torch.Tensor] = None
     view_shard: Optional[object] = None   # sharding.ViewShard when camera views are split across ranks
     n_outer: int = 0                      # scenes x CFG halves (sharded mode)
+    n_frames: int = 1                     # video clips: local frames per clip; images are ordered [clip][frame][view]
+    n_view: int = 6
+    frame_shard: Optional[object] = None  # sharding.FrameShard when the frames of a clip are split across ranks
 
 
 def time_embedding(P, t: torch.Tensor):
@@ -298,10 +305,38 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
             a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=vs.kv_rows(ctx.n_outer), lq=T, lk=T, heads=HEADS,
                               head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
+    # 3b. temporal attention over the frames of the clip (no reference code: defined in csrc/dd_temporal.cu and
+    #     oracle/dualdiff_oracle.py:temporal_attention); only packed for the video configuration
+    if (p + ".attn_temp.qkv.w") in P and (ctx.n_frames > 1 or ctx.frame_shard is not None):
+        h = temporal_step(P, p, h, n, T, ctx)
     # 4. GEGLU feed-forward (blocks.py:225-236)
     ln = ops.layernorm(h, P[p + ".norm3.g"], P[p + ".norm3.b"])
     ff = ops.gemm(ln, P[p + ".ff.geglu.w"], bias=P[p + ".ff.geglu.b"], geglu=True)
     return ops.gemm(ff, P[p + ".ff.net.2.w"], bias=P[p + ".ff.net.2.b"], res1=h)
+
+
+def temporal_step(P, p, h, n, T, ctx: StepCtx):
+    """h += to_out(MHA over frames) for every (clip, view, token); images are ordered [clip][frame][view]."""
+    C = h.shape[1]
+    d = C // HEADS
+    dp = _dp(d)
+    F_loc, V = ctx.n_frames, ctx.n_view
+    n_clip = n // (F_loc * V)
+    assert n_clip * F_loc * V == n, (n, F_loc, V)
+    ln = ops.layernorm(h, P[p + ".norm_temp.g"], P[p + ".norm_temp.b"])
+    qkv = ops.gemm(ln, P[p + ".attn_temp.qkv.w"])
+    kw = dict(n_outer=n_clip, n_view=V, tokens=T, heads=HEADS, head_dim=d, frames_q=F_loc, q_col0=0,
+              k_col0=HEADS * dp, v_col0=2 * HEADS * dp)
+    fs = ctx.frame_shard
+    if fs is None or fs.world == 1:
+        a = ops.temporal_attention(qkv, qkv, qkv, **kw)
+    else:
+        # frames sharded over ranks: the one exchange step is an all-gather of the projected rows (K and V columns are
+        # used, Q columns ride along); rank blocks are addressed in place
+        allkv = fs.gather(qkv)
+        a = ops.temporal_attention(qkv, allkv, allkv, frames_kv=F_loc * fs.world, frames_per_rank=F_loc,
+                                   kv_rank_stride=n, **kw)
+    return ops.gemm(a, P[p + ".attn_temp.to_out.0.w"], bias=P[p + ".attn_temp.to_out.0.b"], res1=h)
 
 
 def transformer_2d(P, p, x: Act, ctx: StepCtx, multiview: bool) -> Act:

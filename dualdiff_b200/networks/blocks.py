@@ -24,7 +24,8 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
                  upcast_attention: bool = False, norm_elementwise_affine: bool = True,
                  norm_type: str = "layer_norm", final_dropout: bool = False,
                  neighboring_view_pair: Optional[Dict[int, List[int]]] = None,
-                 neighboring_attn_type: Optional[str] = "add", zero_module_type="zero_linear"):
+                 neighboring_attn_type: Optional[str] = "add", zero_module_type="zero_linear",
+                 temporal_frames: int = 0):
         if (activation_fn != "geglu" or num_embeds_ada_norm is not None or attention_bias or only_cross_attention
                 or double_self_attention or norm_type != "layer_norm" or not norm_elementwise_affine):
             raise NotImplementedError("dualdiff_b200 implements the SDv1.5 block configuration the reference uses")
@@ -40,6 +41,14 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         self.connector = nn.Linear(dim, dim)
         nn.init.zeros_(self.connector.weight)  # zero_module (blocks.py:83)
         nn.init.zeros_(self.connector.bias)
+        # video configuration (BASELINE config 5; no reference code -- csrc/dd_temporal.cu defines the block):
+        # temporal attention over the `temporal_frames` frames of a clip, zero-initialised output projection
+        self.temporal_frames = int(temporal_frames)
+        if self.temporal_frames > 1:
+            self.norm_temp = nn.LayerNorm(dim)
+            self.attn_temp = _tree.Attention(dim, dim, num_attention_heads, attention_head_dim)
+            nn.init.zeros_(self.attn_temp.to_out[0].weight)
+            nn.init.zeros_(self.attn_temp.to_out[0].bias)
         self._packed = None
 
     @property
@@ -59,8 +68,10 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         return self
 
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
-                timestep=None, cross_attention_kwargs=None, class_labels=None):
-        """hidden_states (b*n_cam, T, C), encoder_hidden_states (b*n_cam, Lk, 768) -> (b*n_cam, T, C)"""
+                timestep=None, cross_attention_kwargs=None, class_labels=None, frame_shard=None):
+        """hidden_states (b*n_cam, T, C), encoder_hidden_states (b*n_cam, Lk, 768) -> (b*n_cam, T, C).
+        With temporal_frames > 1 the batch is ordered (clip, frame, view); `frame_shard` (sharding.FrameShard) marks
+        the frames of a clip as split across ranks (this rank then holds temporal_frames / world of them)."""
         from .. import engine, ops
         if attention_mask is not None or encoder_attention_mask is not None:
             raise NotImplementedError("attention masks are not used on the reference path (attention_mask=None)")
@@ -73,6 +84,10 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         lk = enc.shape[1]
         ctx = engine.StepCtx(n=n, temb=None, temb_rows_per_img_factor=1, lk=lk,
                              kv_map=engine.make_kv_map(n, self.n_cam, h.device))
+        if self.temporal_frames > 1:
+            ctx.n_view = self.n_cam
+            ctx.frame_shard = frame_shard
+            ctx.n_frames = self.temporal_frames // (frame_shard.world if frame_shard is not None else 1)
         ctx.text_kv["b.attn2"] = engine.text_kv(P, "b.attn2", enc.reshape(n * lk, enc.shape[2]).contiguous())
         out = engine.transformer_block(P, "b", h, n, T, ctx, True)
         return out.reshape(n, T, C).to(hidden_states.dtype)

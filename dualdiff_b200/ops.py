@@ -144,7 +144,8 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
 
 
 # ---------------------------------------------------------------------------------------------------
-from ._lib import AttentionArgs, GroupNormArgs, LayerNormArgs, LinearF32Args, ToPaddedArgs  # noqa: E402
+from ._lib import (AttentionArgs, GroupNormArgs, LayerNormArgs, LinearF32Args, TemporalAttentionArgs,  # noqa: E402
+                   ToPaddedArgs)
 
 _L = C.c_longlong
 _I = C.c_int
@@ -215,6 +216,36 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
     with _Rec("attn_tcgen05", 4.0 * n_img * lq * lk * heads * head_dim * n_src,
               2.0 * heads * head_dim * (2 * n_img * lq + 2 * n_kv_img * lk), f"d{head_dim}_Lq{lq}_Lk{lk}_s{n_src}"):
         check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")
+    return out
+
+
+def temporal_attention(q, k, v, *, n_outer, n_view, tokens, heads, head_dim, frames_q, frames_kv=None,
+                       frames_per_rank=None, kv_rank_stride=0, out=None, q_col0=0, k_col0=0, v_col0=0,
+                       q_hs=None, k_hs=None, v_hs=None, scale=None):
+    """attention over the frames of a clip at every (outer, view, token).  q: [n_outer*frames_q*n_view*tokens, *];
+    k/v: frames_kv frames as blocks of [n_outer, frames_per_rank, n_view] images (kv_rank_stride images apart)."""
+    _req(q, torch.bfloat16, "q")
+    _req(k, torch.bfloat16, "k")
+    hs_qk = 48 if head_dim == 40 else head_dim
+    frames_kv = frames_q if frames_kv is None else frames_kv
+    frames_per_rank = frames_kv if frames_per_rank is None else frames_per_rank
+    n_img = n_outer * frames_q * n_view
+    if out is None:
+        out = torch.empty((n_img * tokens, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = TemporalAttentionArgs()
+    a.q = _ptr(q); a.k = _ptr(k); a.v = _ptr(v); a.out = _ptr(out)
+    a.q_ld = q.stride(0); a.k_ld = k.stride(0); a.v_ld = v.stride(0); a.out_ld = out.stride(0)
+    a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0
+    a.q_head_stride = hs_qk if q_hs is None else q_hs
+    a.k_head_stride = hs_qk if k_hs is None else k_hs
+    a.v_head_stride = head_dim if v_hs is None else v_hs
+    a.n_outer = n_outer; a.n_view = n_view; a.tokens = tokens; a.heads = heads; a.head_dim = head_dim
+    a.frames_q = frames_q; a.frames_kv = frames_kv; a.frames_per_rank = frames_per_rank
+    a.kv_rank_stride = kv_rank_stride
+    a.scale = float(head_dim) ** -0.5 if scale is None else scale
+    nb = 2.0 * heads * head_dim * tokens * n_outer * n_view * (2 * frames_q + 2 * frames_kv)
+    with _Rec("temporal_attn", 0.0, nb, f"d{head_dim}_F{frames_q}of{frames_kv}_T{tokens}"):
+        check(_lib.lib().dd_temporal_attention(C.byref(a), _stream()), "dd_temporal_attention")
     return out
 
 

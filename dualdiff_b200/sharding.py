@@ -89,6 +89,44 @@ class ViewShard:
             r.wait()
 
 
+class FrameShard:
+    """Frame sharding of a video clip (BASELINE config 5: 16 frames x 6 views, frames split over the GPUs).
+
+    Rank r owns the F_loc = n_frames / world consecutive frames [r*F_loc, (r+1)*F_loc) of every clip, with all six camera
+    views of those frames: convolutions, norms, self-, text- and CROSS-VIEW attention stay rank-local.  The one exchange
+    step is the temporal attention, which needs the keys and values of every frame: each rank contributes the projected
+    rows of its frames to an all-gather (NCCL over NVLink; `dist.all_gather_into_tensor`), and the kernel addresses the
+    gathered [world][clip][F_loc][view] blocks in place (dd_temporal_attention's kv_rank_stride).  The reference has no
+    temporal block or frame sharding: this design is dualdiff_b200's own.
+    """
+
+    def __init__(self, rank: int, world: int, n_frames: int = 16, group=None):
+        if n_frames % world != 0:
+            raise ValueError(f"world size {world} must divide the number of frames {n_frames}")
+        self.rank, self.world, self.n_frames, self.group = rank, world, n_frames, group
+        self.f_loc = n_frames // world
+
+    @property
+    def frames(self):
+        return list(range(self.rank * self.f_loc, (self.rank + 1) * self.f_loc))
+
+    def gather(self, rows: torch.Tensor) -> torch.Tensor:
+        """rows: this rank's projection rows [n_loc_img*T, W] -> [world * n_loc_img*T, W], rank-major"""
+        import torch.distributed as dist
+        if self.world == 1:
+            return rows
+        out = torch.empty((self.world * rows.shape[0], rows.shape[1]), device=rows.device, dtype=rows.dtype)
+        dist.all_gather_into_tensor(out, rows.contiguous(), group=self.group)
+        return out
+
+
+def slice_frames(x: torch.Tensor, frames, n_frames: int, n_view: int = 6) -> torch.Tensor:
+    """x: [(clip, frame, view), ...] image-major tensor -> the images of `frames` (same ordering)"""
+    n_clip = x.shape[0] // (n_frames * n_view)
+    idx = torch.as_tensor(list(frames))
+    return x.reshape(n_clip, n_frames, n_view, *x.shape[1:])[:, idx].reshape(n_clip * len(idx) * n_view, *x.shape[1:]).contiguous()
+
+
 def slice_views(inputs: dict, views, n_cam: int = 6) -> dict:
     """select the camera views of one rank from full-scene step inputs (layouts of synthetic.make_inputs /
     dataset/utils.py:390-445): per-view tensors are sliced, view-shared ones kept."""
@@ -105,3 +143,10 @@ def slice_views(inputs: dict, views, n_cam: int = 6) -> dict:
     B = cf.shape[0] // n_cam
     out["cond_fg"] = cf.reshape(B, n_cam, *cf.shape[1:])[:, idx].reshape(B * len(views), *cf.shape[1:]).contiguous()
     return out
+
+
+def gathered_kv_image(clip: int, frame: int, view: int, n_clip: int, f_loc: int, n_view: int = 6) -> int:
+    """image index of (clip, global frame, view) inside FrameShard.gather's rank-major buffer -- the address arithmetic
+    of csrc/dd_temporal.cu (kv_rank_stride = n_clip * f_loc * n_view images)"""
+    rank, fl = divmod(frame, f_loc)
+    return rank * (n_clip * f_loc * n_view) + (clip * f_loc + fl) * n_view + view

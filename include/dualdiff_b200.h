@@ -118,6 +118,26 @@ typedef struct dd_attention_args {
 } dd_attention_args;
 DD_API int dd_attention(const dd_attention_args* args, void* stream);
 
+/* ---- temporal attention over the frames of a clip (BASELINE.json configs[4], "DualDiff+ video") ------------
+ * The reference repository has NO temporal block; dualdiff_b200 defines it as
+ *   x_f += W_o MHA(q = LN(x_f), k = v = LN(x_f'), f' over all frames) + b_o     per (scene, view, token), bidirectional,
+ * inserted after the cross-view attention of BasicMultiviewTransformerBlock (networks/blocks.py:190-222 is the sibling it
+ * is modelled on).  Images are ordered [outer][frame][view]; q holds the frames_q local frames, k/v hold frames_kv frames
+ * laid out as frames_kv / frames_per_rank blocks of [outer][frames_per_rank][view] images, kv_rank_stride images apart
+ * (= the NCCL all-gather layout when frames are sharded over ranks; one block when they are not).
+ * out[img, token, h*head_dim + c] = sum_f' softmax_f'(q k_f'^T * scale) v_f'. */
+typedef struct dd_temporal_attention_args {
+  const void* q; const void* k; const void* v; void* out;
+  long long q_ld, k_ld, v_ld, out_ld;
+  int q_col0, k_col0, v_col0;
+  int q_head_stride, k_head_stride, v_head_stride;
+  int n_outer, n_view, tokens, heads, head_dim;
+  int frames_q, frames_kv, frames_per_rank;
+  long long kv_rank_stride;
+  float scale;
+} dd_temporal_attention_args;
+DD_API int dd_temporal_attention(const dd_temporal_attention_args* args, void* stream);
+
 /* ---- layout / gather kernels feeding the implicit-GEMM convolution ---------------------------------- */
 /* NCHW (fp32 or bf16, arbitrary outer strides) -> padded channels-last bf16 with channel zero-padding to cp.
  * Image index = outer * n_view + view; source offset = outer*stride_outer + view*stride_view + c*stride_c +

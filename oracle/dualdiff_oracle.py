@@ -96,7 +96,24 @@ def resnet(sd: SD, p: str, x, emb):
 # ---------------------------------------------------------------------------------------------------
 # networks/blocks.py:144-238 — BasicMultiviewTransformerBlock (multiview=True) / stock block (False)
 # ---------------------------------------------------------------------------------------------------
-def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6):
+def temporal_attention(sd: SD, p: str, x, n_frames: int, n_cam=6):
+    """Temporal block of the video configuration (BASELINE config 5).  NO REFERENCE CODE exists for it
+    (SURVEY.md §8d): this function is the definition dualdiff_b200 builds to -- parity unpinned by construction.
+    x: [(clip, frame, view), T, C].  For every (clip, view, token) the frames of the clip attend to each other
+    (bidirectional, 8 heads, scale (C/8)^-0.5): out = to_out(MHA(q, k, v = to_{q,k,v}(LN(x)))); to_out is zero-initialised
+    in a fresh model ('zero_linear', like the cross-view connector, blocks.py:83)."""
+    h = _ln(sd, p + ".norm_temp", x)
+    n, T, C = h.shape
+    n_clip = n // (n_frames * n_cam)
+    hv = h.reshape(n_clip, n_frames, n_cam, T, C).permute(0, 2, 3, 1, 4).reshape(n_clip * n_cam * T, n_frames, C)
+    q = _lin(sd, p + ".attn_temp.to_q", hv, False)
+    k = _lin(sd, p + ".attn_temp.to_k", hv, False)
+    v = _lin(sd, p + ".attn_temp.to_v", hv, False)
+    o = _lin(sd, p + ".attn_temp.to_out.0", mha(q, k, v, HEADS))
+    return o.reshape(n_clip, n_cam, T, n_frames, C).permute(0, 3, 1, 2, 4).reshape(n, T, C)
+
+
+def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames: int = 1):
     x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x))             # blocks.py:163-172
     x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), enc)        # blocks.py:175-188
     if multiview:
@@ -117,6 +134,8 @@ def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6):
         out = F.linear(acc, w_o) + 2.0 * b_o
         out = _lin(sd, p + ".connector", out).reshape(bn, T, C)                # zero_linear connector, blocks.py:83,220
         x = x + out
+    if n_frames > 1 and (p + ".attn_temp.to_q.weight") in sd:
+        x = x + temporal_attention(sd, p, x, n_frames, n_cam)
     x = x + feed_forward(sd, p + ".ff", _ln(sd, p + ".norm3", x))             # blocks.py:225-236
     return x
 

@@ -1,0 +1,58 @@
+"""torchrun entry: the frames of a video clip sharded over WORLD_SIZE GPUs with the temporal K/V all-gather over NCCL
+(BASELINE config 5) must reproduce the single-GPU multi-view + temporal transformer block.  Rank 0 prints
+'FRAMESHARD OK ...' on success."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dualdiff_b200 import synthetic as S  # noqa: E402
+from dualdiff_b200.networks import BasicMultiviewTransformerBlock  # noqa: E402
+from dualdiff_b200.sharding import FrameShard, slice_frames  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    F, n_clip = int(os.environ.get("FRAMES", "16")), int(os.environ.get("CLIPS", "1"))
+    h, w = (int(x) for x in os.environ.get("LATENT", "28x50").split("x"))
+    T, C = h * w, 320
+    nb = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}
+    with torch.device("meta"):
+        blk = BasicMultiviewTransformerBlock(C, 8, C // 8, cross_attention_dim=768, neighboring_view_pair=nb, temporal_frames=F)
+    blk.load_state_dict(S.init_state_dict(S.manifest_of(blk), seed=11), strict=True, assign=True)
+    blk = blk.to(dev)
+    g = torch.Generator().manual_seed(5)
+    n = n_clip * F * 6
+    x = (torch.randn(n, T, C, generator=g)).to(torch.bfloat16).to(dev)
+    enc = torch.randn(n, 83, 768, generator=g).to(torch.bfloat16).to(dev)
+    full = blk(x, encoder_hidden_states=enc)                                # all frames on this GPU
+    fs = FrameShard(rank, world, F)
+    xs, es = slice_frames(x, fs.frames, F), slice_frames(enc, fs.frames, F)
+    for _ in range(2):
+        part = blk(xs, encoder_hidden_states=es, frame_shard=fs)            # this rank's frames + NCCL all-gather of K/V
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    part = blk(xs, encoder_hidden_states=es, frame_shard=fs)
+    e1.record()
+    torch.cuda.synchronize()
+    want = slice_frames(full, fs.frames, F)
+    rel = ((part.float() - want.float()).norm() / want.float().norm()).item()
+    t = torch.tensor([rel, e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ok = float(t[0]) < 1e-2
+        print(f"FRAMESHARD {'OK' if ok else 'FAIL'} world={world} frames={F} clips={n_clip} latent={h}x{w} "
+              f"rel_l2(max over ranks)={float(t[0]):.3e} block ms(max over ranks)={float(t[1]):.2f}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

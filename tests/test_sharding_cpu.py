@@ -137,3 +137,63 @@ def test_view_shard_kv_map_and_slicing():
     assert torch.equal(loc["cond_bg"][..., :48], inp["cond_bg"][..., 2 * 48:3 * 48])
     assert torch.equal(loc["cond_fg"].reshape(2, 2, 320, 4, 6)[:, 1], inp["cond_fg"].reshape(2, 6, 320, 4, 6)[:, 3])
     assert loc["boxes_fg"]["bboxes"].shape[1] == 1   # view-shared map vectors stay whole
+
+
+# ---------------------------------------------------------------------------------------------------
+# frame sharding of a video clip (BASELINE config 5): all-gather of the projected rows + the rank-major address
+# arithmetic of dd_temporal_attention reproduce the unsharded temporal attention (oracle.temporal_attention's core)
+# ---------------------------------------------------------------------------------------------------
+def _frame_worker(rank, world, port, q_out):
+    from dualdiff_b200.sharding import FrameShard, slice_frames, gathered_kv_image
+    from oracle.dualdiff_oracle import mha
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_clip, F, V, T, C, heads = 2, 4, 3, 5, 16, 2
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(n_clip * F * V, T, C, generator=g) for _ in range(3))
+    # unsharded reference: sequences over frames at every (clip, view, token)
+    def seq(t):
+        return t.reshape(n_clip, F, V, T, C).permute(0, 2, 3, 1, 4).reshape(n_clip * V * T, F, C)
+    ref = mha(seq(q), seq(k), seq(v), heads).reshape(n_clip, V, T, F, C).permute(0, 3, 1, 2, 4).reshape(n_clip * F * V, T, C)
+    fs = FrameShard(rank, world, F)
+    loc = [slice_frames(t, fs.frames, F, V) for t in (q, k, v)]
+    rows = torch.cat(loc, dim=-1).reshape(-1, 3 * C)                     # this rank's fused projection rows
+    allkv = fs.gather(rows).reshape(-1, T, 3 * C)                        # [world * n_loc_img, T, 3C]
+    n_loc = n_clip * fs.f_loc * V
+    out = torch.zeros(n_loc, T, C)
+    for c in range(n_clip):
+        for view in range(V):
+            idx = torch.tensor([gathered_kv_image(c, f, view, n_clip, fs.f_loc, V) for f in range(F)])
+            kk = allkv[idx][:, :, C:2 * C].permute(1, 0, 2)              # [T, F, C]
+            vv = allkv[idx][:, :, 2 * C:].permute(1, 0, 2)
+            for fl in range(fs.f_loc):
+                img = (c * fs.f_loc + fl) * V + view
+                qq = loc[0][img][:, None, :]                             # [T, 1, C]
+                out[img] = mha(qq, kk, vv, heads)[:, 0]
+    want = slice_frames(ref, fs.frames, F, V)
+    q_out.put((rank, (out - want).abs().max().item()))
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_temporal_attention_two_ranks_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_frame_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-5, (rank, err)
+
+
+def test_frame_shard_partition():
+    from dualdiff_b200.sharding import FrameShard
+    import pytest
+    assert sum((FrameShard(r, 8, 16).frames for r in range(8)), []) == list(range(16))
+    with pytest.raises(ValueError):
+        FrameShard(0, 3, 16)
