@@ -360,7 +360,7 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, fl
   r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-template <int DQK, int DV, int DVP, int BN, int STAGES, int MINB, int POLY>
+template <int DQK, int DV, int DVP, int BN, int STAGES, int MINB, int POLY, bool PIPE>
 __global__ void __launch_bounds__(ATT_THREADS, MINB)
 attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
@@ -511,6 +511,220 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     bf16* orow = p.out + ((long long)img * p.Lq + q_row) * p.out_ld + head * p.o_hs;
     constexpr int NC = BN / 2;                  // S columns per pass (P is published in two passes)
     int g = 0;
+    if constexpr (PIPE) {
+      // ------------------------------------------------------------------------------------------------------------
+      // Pipelined softmax (opt-in variant, DD_ATTN_PIPE=1; slower than the classic loop on B200 as measured -- kept for A/B).
+      // The classic loop below reads the whole S tile, then reduces its maximum, then runs the exponentials: the TMEM
+      // read port and the MUFU pipe are used one after the other (MUFU ~60 % busy).  Here the exponent reference m is the
+      // running maximum of the PREVIOUS tiles (exact for the first tile via a max-only prepass), so a 32-column chunk can
+      // be exponentiated as soon as it is in registers while tcgen05.ld fetches the next chunk.  m is advanced at the end
+      // of a tile when the tile maximum grew by more than 2^8 (O is rescaled at the start of the next tile, after P V of
+      // this tile retired); a chunk whose maximum exceeds m by more than 2^64 (fp32 / bf16 range guard, practically never)
+      // takes an in-place rescale of l, the P chunks already published, and O.
+      // ------------------------------------------------------------------------------------------------------------
+      constexpr int NCH = BN / 32;
+      for (int src = 0; src < p.n_src; ++src) {
+        float m = -INFINITY, l = 0.f, alpha_pend = 1.f;
+        bool pend = false;
+#pragma unroll 1
+        for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
+          mbar_wait(s_full, g & 1);
+          tc_fence_after();
+          const int nvalid = p.Lk - jt * BN;         // keys >= nvalid in this tile are padding (warp-uniform)
+          uint32_t buf[2][32];
+          auto chunk_max = [&](uint32_t (&t)[32], int c) {
+            if (nvalid < BN) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) t[j] = (c * 32 + j < nvalid) ? t[j] : 0xff800000u;   // -inf
+            }
+            float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              a0 = fmax3(a0, __uint_as_float(t[j]), __uint_as_float(t[j + 1]));
+              a1 = fmax3(a1, __uint_as_float(t[j + 2]), __uint_as_float(t[j + 3]));
+              a2 = fmax3(a2, __uint_as_float(t[j + 4]), __uint_as_float(t[j + 5]));
+              a3 = fmax3(a3, __uint_as_float(t[j + 6]), __uint_as_float(t[j + 7]));
+            }
+            return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+          };
+          if (jt == 0) {   // first tile of a source: exact maximum (max-only prepass over the tile)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              tmem_ld_32x32(tmem_S + lane_sel + c * 32, buf[0]);
+              tmem_ld_wait();
+              mx = fmaxf(mx, chunk_max(buf[0], c));
+            }
+            m = mx * sl2;
+          }
+          uint64_t NEGM = pack_f32x2(-m, -m);
+          uint64_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+          float tmax = -INFINITY;
+          bool o_ready = false;
+          auto ensure_o = [&]() {   // P V of the previous tile retired: P may be overwritten, O may be rescaled
+            if (o_ready) return;
+            o_ready = true;
+            if (g > 0) {
+              mbar_wait(o_full, (g - 1) & 1);
+              tc_fence_after();
+            }
+            if (pend) {             // warp-uniform: the reference maximum moved at the end of the previous tile
+#pragma unroll
+              for (int c = 0; c < DVP; c += 16) {
+                uint32_t ov[16];
+                tmem_ld_32x16(tmem_O + lane_sel + c, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha_pend);
+                tmem_st_32x16(tmem_O + lane_sel + c, ov);
+              }
+              pend = false;
+            }
+          };
+          constexpr int HOLD = NCH >= 4 ? 2 : 1;
+          uint32_t pk_hold[HOLD][16], pk_cur[16];
+          tmem_ld_32x32(tmem_S + lane_sel, buf[0]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t (&cur)[32] = buf[c & 1];
+            if (c + 1 < NCH) tmem_ld_32x32(tmem_S + lane_sel + (c + 1) * 32, buf[(c + 1) & 1]);   // overlaps the exponentials
+            const float cm = chunk_max(cur, c);
+            tmax = fmaxf(tmax, cm);
+            if (__any_sync(0xffffffffu, cm * sl2 > m + 64.f)) {
+              // range guard (rare): move the reference now and rescale everything accumulated under the old one
+              const float m_new = fmaxf(m, cm * sl2);
+              const float a = fast_exp2(m - m_new);
+              const uint64_t A2 = pack_f32x2(a, a);
+              l *= a;
+              acc0 = fma_f32x2(acc0, A2, 0ull); acc1 = fma_f32x2(acc1, A2, 0ull);
+              acc2 = fma_f32x2(acc2, A2, 0ull); acc3 = fma_f32x2(acc3, A2, 0ull);
+              ensure_o();
+              tmem_st_wait();
+#pragma unroll
+              for (int cp = 0; cp < NCH; ++cp) {
+                if (cp < c) {
+                  if (c < HOLD) {            // still held in registers
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float2 f = unpack_bf16(pk_hold[cp < HOLD ? cp : 0][j]);
+                      pk_hold[cp < HOLD ? cp : 0][j] = pack_bf16(f.x * a, f.y * a);
+                    }
+                  } else {
+                    uint32_t pv[16];
+                    tmem_ld_32x16(tmem_P + lane_sel + cp * 16, pv);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float2 f = unpack_bf16(pv[j]);
+                      pv[j] = pack_bf16(f.x * a, f.y * a);
+                    }
+                    tmem_st_32x16(tmem_P + lane_sel + cp * 16, pv);
+                  }
+                }
+              }
+              if (jt > 0 || c > 0) {
+#pragma unroll
+                for (int cc = 0; cc < DVP; cc += 16) {
+                  uint32_t ov[16];
+                  tmem_ld_32x16(tmem_O + lane_sel + cc, ov);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * a);
+                  tmem_st_32x16(tmem_O + lane_sel + cc, ov);
+                }
+              }
+              m = m_new;
+              NEGM = pack_f32x2(-m, -m);
+            }
+            // P of the first HOLD chunks stays in registers: the wait for P V of the previous tile (which still reads the
+            // P buffer) is pushed as late as possible
+            uint32_t (&pk)[16] = (c < HOLD) ? pk_hold[c < HOLD ? c : 0] : pk_cur;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 2) {
+              const uint64_t X = fma_f32x2(pack_f32x2(__uint_as_float(cur[jj]), __uint_as_float(cur[jj + 1])), SL2, NEGM);
+              float x0, x1;
+              unpack_f32x2(X, x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              const uint64_t PP = pack_f32x2(p0, p1);
+              const int u = (jj >> 1) & 3;
+              if (u == 0) acc0 = add_f32x2(acc0, PP);
+              if (u == 1) acc1 = add_f32x2(acc1, PP);
+              if (u == 2) acc2 = add_f32x2(acc2, PP);
+              if (u == 3) acc3 = add_f32x2(acc3, PP);
+              pk[jj >> 1] = pack_bf16(p0, p1);
+            }
+            if (c == HOLD - 1) {
+              ensure_o();
+#pragma unroll
+              for (int cp = 0; cp < HOLD; ++cp) tmem_st_32x16(tmem_P + lane_sel + cp * 16, pk_hold[cp]);
+            } else if (c >= HOLD) {
+              tmem_st_32x16(tmem_P + lane_sel + c * 16, pk_cur);
+            }
+            if (c + 1 < NCH) {
+              tmem_ld_wait();
+              if (c + 2 == NCH) {      // the last chunk of S is in registers -> the issuer may start S(g+1) = Q K(g+1)^T
+                tc_fence_before();
+                mbar_arrive(s_free);
+              }
+            }
+          }
+          if (NCH == 1) {
+            tc_fence_before();
+            mbar_arrive(s_free);
+          }
+          {
+            float s0, s1;
+            unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
+            l += s0 + s1;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_full);
+          // lazy reference update for the following tiles
+          if (jt + 1 < p.n_kv_tiles) {
+            const float m_cand = fmaxf(m, tmax * sl2);
+            if (__any_sync(0xffffffffu, m_cand > m + 8.f)) {
+              alpha_pend = fast_exp2(m - m_cand);
+              l *= alpha_pend;
+              m = m_cand;
+              pend = true;
+            }
+          }
+        }
+        // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first)
+        mbar_wait(o_full, (g - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int c = 0; c < DVP; c += 16) {
+          uint32_t ov[16];
+          tmem_ld_32x16(tmem_O + lane_sel + c, ov);
+          tmem_ld_wait();
+          if (q_row < p.Lq) {
+#pragma unroll
+            for (int hh = 0; hh < 16; hh += 8) {
+              if (c + hh + 8 <= DV) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(ov[hh + e]) * inv;
+                if (src > 0) {
+                  const uint4 r = *reinterpret_cast<const uint4*>(orow + c + hh);
+                  float2 t;
+                  t = unpack_bf16(r.x); v[0] += t.x; v[1] += t.y;
+                  t = unpack_bf16(r.y); v[2] += t.x; v[3] += t.y;
+                  t = unpack_bf16(r.z); v[4] += t.x; v[5] += t.y;
+                  t = unpack_bf16(r.w); v[6] += t.x; v[7] += t.y;
+                }
+                *reinterpret_cast<uint4*>(orow + c + hh) =
+                    make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              }
+            }
+          }
+        }
+        tc_fence_before();
+      }
+    } else
     for (int src = 0; src < p.n_src; ++src) {
       float m = -INFINITY, l = 0.f;
 #pragma unroll 1
@@ -648,7 +862,7 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DQK, int DV, int DVP, int BN, int STAGES, int MINB, int POLY>
+template <int DQK, int DV, int DVP, int BN, int STAGES, int MINB, int POLY, bool PIPE>
 static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t stream) {
   constexpr int QCH = (DQK + 63) / 64, VCH = (DVP + 63) / 64;
   constexpr size_t smem = (size_t)QCH * ATT_BM * 128 + (size_t)STAGES * (QCH + VCH) * BN * 128 + 128;
@@ -667,12 +881,12 @@ static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t st
   p.n_kv_tiles = (a->lk + BN - 1) / BN;
   static bool attr_done = false;
   if (!attr_done) {
-    DD_CUDA(cudaFuncSetAttribute(attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB, POLY>,
+    DD_CUDA(cudaFuncSetAttribute(attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB, POLY, PIPE>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   dim3 grid((a->lq + ATT_BM - 1) / ATT_BM, a->heads, a->n_img);
-  attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB, POLY><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB, POLY, PIPE><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
   DD_CUDA(cudaGetLastError());
   return 0;
 }
@@ -726,16 +940,25 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   // per 8 evaluated on the FMA pipe at head_dim 40 (0, 2, 3 or 4; default 3)
   static const int impl = getenv("DD_ATTN_IMPL") ? atoi(getenv("DD_ATTN_IMPL")) : 3;
   static const int poly = getenv("DD_ATTN_POLY") ? atoi(getenv("DD_ATTN_POLY")) : 0;
+  // DD_ATTN_PIPE=1 selects the chunk-pipelined softmax (exponent reference = running maximum of the previous tiles, 32-column
+  // chunks exponentiated while the next chunk is read).  Measured on B200 (profiles/attn_one.py, 96 images, d = 40,
+  // L = 1400): 665 us against 585 us for the read-all / max / exponentiate loop, so it stays an opt-in A/B variant.
+  static const int pipe = getenv("DD_ATTN_PIPE") ? atoi(getenv("DD_ATTN_PIPE")) : 0;
   if (impl != 1) {
     switch (a->head_dim) {
       case 40: {
         DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
                  "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
-        if (poly == 2) return launch_attn_v2<48, 40, 48, 128, 3, 2, 2>(a, p, stream);
-        return launch_attn_v2<48, 40, 48, 128, 3, 2, 0>(a, p, stream);
+        if (poly == 2) return launch_attn_v2<48, 40, 48, 128, 3, 2, 2, false>(a, p, stream);
+        if (pipe) return launch_attn_v2<48, 40, 48, 128, 3, 2, 0, true>(a, p, stream);
+        return launch_attn_v2<48, 40, 48, 128, 3, 2, 0, false>(a, p, stream);
       }
-      case 80: return launch_attn_v2<80, 80, 80, 64, 2, 2, 0>(a, p, stream);
-      case 160: return launch_attn_v2<160, 160, 160, 64, 1, 2, 0>(a, p, stream);
+      case 80:
+        if (pipe) return launch_attn_v2<80, 80, 80, 64, 2, 2, 0, true>(a, p, stream);
+        return launch_attn_v2<80, 80, 80, 64, 2, 2, 0, false>(a, p, stream);
+      case 160:
+        if (pipe) return launch_attn_v2<160, 160, 160, 64, 1, 2, 0, true>(a, p, stream);
+        return launch_attn_v2<160, 160, 160, 64, 1, 2, 0, false>(a, p, stream);
     }
   }
   switch (a->head_dim) {

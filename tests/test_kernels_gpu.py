@@ -47,6 +47,29 @@ def test_self_attention_fused_qkv(d, L, n):
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("d,L,peak", [(40, 1400, 40.0), (40, 1400, 400.0), (40, 1400, 4000.0), (80, 350, 900.0), (160, 300, 2500.0)])
+def test_self_attention_rising_logits(d, L, peak):
+    """keys ordered so that the logits of every query rise steadily along the sequence: every KV tile raises the running
+    maximum (lazy reference update + deferred O rescale of the pipelined softmax); at the larger peaks a single 32-key
+    chunk jumps by more than 2^64, which exercises the in-place range-guard rescale of l, P and O."""
+    from dualdiff_b200 import ops
+    n, heads, C = 2, 8, 8 * d
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(n * L, C, generator=g) * 0.1 + 1.0
+    ramp = (torch.arange(L, dtype=torch.float32) / L).repeat(n)[:, None]
+    k = (torch.randn(n * L, C, generator=g) * 0.05 + ramp) * (peak / (d ** 0.5))
+    v = torch.randn(n * L, C, generator=g)
+    q, k, v = (t.to(torch.bfloat16).cuda() for t in (q, k, v))
+    dp = 48 if d == 40 else d
+    fused = torch.cat([_heads_pad(q, heads, d, dp), _heads_pad(k, heads, d, dp), v], dim=1).contiguous()
+    out = ops.attention(fused, fused, fused, n_img=n, lq=L, lk=L, heads=heads, head_dim=d,
+                        q_col0=0, k_col0=heads * dp, v_col0=2 * heads * dp)
+    qh, kh, vh = _ref_attn(q, k, v, n, L, L, heads, d)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(n * L, C)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
 @pytest.mark.parametrize("d,L,lk", [(40, 1400, 106), (80, 350, 110), (160, 91, 78), (40, 1400, 77)])
 def test_cross_attention_text(d, L, lk):
     from dualdiff_b200 import ops
