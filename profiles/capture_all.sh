@@ -1,0 +1,11 @@
+set -x
+python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r01_bench_reference.json 2>gpurun_out/ref.err
+DD_BENCH_SHAPES=gpurun_out/r01_step_shapes.txt python bench.py --steps 10 --warmup 3 > gpurun_out/r01_bench.json 2>gpurun_out/bench.err
+EAGER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/r01_launches.csv python profiles/step_once.py > gpurun_out/step_once.log 2>&1
+LEVEL=0 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/r01_conv_l0 python profiles/conv_one.py > /dev/null 2>&1
+LEVEL=2 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/r01_conv_l2 python profiles/conv_one.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/r01_gemm_n320_k320 python profiles/gemm_one.py > /dev/null 2>&1
+GN=2560 GRES=0 ncu --set full --clock-control none -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/r01_gemm_n2560_k320 python profiles/gemm_one.py > /dev/null 2>&1
+N_IMG=96 ncu --set full --clock-control none --import-source on -k regex:attn_v2 -s 2 -c 1 -o gpurun_out/r01_attn_l0 python profiles/attn_one.py > /dev/null 2>&1
+ncu --set full --clock-control none -k regex:gn_ -s 20 -c 2 -o gpurun_out/r01_gn_c320 python profiles/gn_one.py > /dev/null 2>&1
+ls -la gpurun_out | tail -20
