@@ -42,7 +42,8 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
                  addition_embed_type_num_heads=64,
                  trainable_state="only_new", neighboring_view_pair: Optional[dict] = None,
                  neighboring_attn_type: str = "add", zero_module_type: str = "zero_linear",
-                 crossview_attn_type: str = "basic", img_size: Optional[Tuple[int, int]] = None):
+                 crossview_attn_type: str = "basic", img_size: Optional[Tuple[int, int]] = None,
+                 temporal_frames: int = 0):
         super().__init__()
         cfg = {k: v for k, v in locals().items() if k not in ("self", "__class__")}
         self.config = _tree.AttrDict(cfg)
@@ -62,7 +63,13 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
         ch, heads, temb, cad = tuple(block_out_channels), attention_head_dim, block_out_channels[0] * 4, cross_attention_dim
         tf = dict(block_cls=BasicMultiviewTransformerBlock,
                   block_kwargs=dict(neighboring_view_pair=neighboring_view_pair,
-                                    neighboring_attn_type=neighboring_attn_type, zero_module_type=zero_module_type))
+                                    neighboring_attn_type=neighboring_attn_type, zero_module_type=zero_module_type,
+                                    temporal_frames=temporal_frames))
+        # video configuration (BASELINE config 5, no reference code): every multi-view block gets a temporal attention
+        # over the `temporal_frames` frames of a clip; the batch is then ordered (clip, frame, view).  `frame_shard`
+        # (sharding.FrameShard) marks the frames of a clip as split across ranks.
+        self.temporal_frames = int(temporal_frames)
+        self.frame_shard = None
         self.conv_in = nn.Conv2d(in_channels, ch[0], 3, padding=1)
         self.time_proj = _tree.Timesteps(ch[0], flip_sin_to_cos, freq_shift)
         self.time_embedding = _tree.TimestepEmbedding(ch[0], temb)
@@ -131,6 +138,15 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
         self._packed = engine.pack_unet(self.state_dict(), device)
         return self
 
+    def video_ctx(self, ctx):
+        """fill the clip geometry of a StepCtx (no-op for the single-frame configuration)"""
+        if self.temporal_frames > 1:
+            world = self.frame_shard.world if self.frame_shard is not None else 1
+            ctx.n_frames, ctx.n_view, ctx.frame_shard = self.temporal_frames // world, self.n_cam, self.frame_shard
+            if ctx.n % (ctx.n_frames * ctx.n_view) != 0:
+                raise ValueError(f"batch {ctx.n} is not a multiple of frames x views = {ctx.n_frames} x {ctx.n_view}")
+        return ctx
+
     def release_master_weights(self):
         """drop the fp32 diffusers-layout parameters once packed (inference-only deployments)"""
         for p in self.parameters():
@@ -166,6 +182,7 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
         ctx = engine.StepCtx(n=n, temb=temb, temb_rows_per_img_factor=n // t.numel(), lk=lk,
                              kv_map=engine.make_kv_map(n, self.n_cam, sample.device),
                              text_kv=engine.prepare_text(P, engine.ATTN2_LAYERS_UNET, enc_rows))
+        self.video_ctx(ctx)
         lat = sample.contiguous() if sample.dtype in (torch.float32, torch.bfloat16) else sample.float().contiguous()
         down = mid = None
         if down_block_additional_residuals is not None:

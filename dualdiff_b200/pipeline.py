@@ -29,7 +29,8 @@ class DualDiffDenoiser:
         self.scheduler = scheduler if scheduler is not None else UniPCMultistepScheduler()
         self.scheduler.guidance_scale = guidance_scale
         self.view_shard = view_shard               # sharding.ViewShard: camera views split across ranks (config 4)
-        self.use_cuda_graph = use_cuda_graph and view_shard is None   # the K/V exchange runs eagerly on NCCL
+        # the K/V exchanges of the view- / frame-sharded configurations run eagerly on NCCL
+        self.use_cuda_graph = use_cuda_graph and view_shard is None and getattr(unet, "frame_shard", None) is None
         self._graph = None
         self.device = None
         # The two condition branches and the UNet encoder are mutually independent until the skip/mid residual adds
@@ -113,6 +114,7 @@ class DualDiffDenoiser:
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
                                  lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
+            self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
             eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
         else:
             main = torch.cuda.current_stream()
@@ -130,6 +132,7 @@ class DualDiffDenoiser:
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
                                  lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
+            self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
 
             def join():
                 for st in self._side:

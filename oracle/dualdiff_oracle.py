@@ -140,24 +140,24 @@ def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames
     return x
 
 
-def transformer_2d(sd: SD, p: str, x, enc, multiview: bool):
+def transformer_2d(sd: SD, p: str, x, enc, multiview: bool, n_frames: int = 1):
     n, c, h, w = x.shape
     r = x
     y = _conv(sd, p + ".proj_in", _gn(sd, p + ".norm", x, 1e-6), padding=0)
     y = y.permute(0, 2, 3, 1).reshape(n, h * w, c)
-    y = transformer_block(sd, p + ".transformer_blocks.0", y, enc, multiview)
+    y = transformer_block(sd, p + ".transformer_blocks.0", y, enc, multiview, n_frames=n_frames)
     y = y.reshape(n, h, w, c).permute(0, 3, 1, 2)
     return _conv(sd, p + ".proj_out", y, padding=0) + r
 
 
-def _down_path(sd: SD, x, emb, enc, multiview: bool):
+def _down_path(sd: SD, x, emb, enc, multiview: bool, n_frames: int = 1):
     """3x CrossAttnDownBlock2D + DownBlock2D; returns (x, 12 skips) — Appendix A.1."""
     skips = [x]
     for i in range(4):
         for j in range(2):
             x = resnet(sd, f"down_blocks.{i}.resnets.{j}", x, emb)
             if i < 3:
-                x = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", x, enc, multiview)
+                x = transformer_2d(sd, f"down_blocks.{i}.attentions.{j}", x, enc, multiview, n_frames)
             skips.append(x)
         if i < 3:
             x = _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", x, stride=2, padding=1)
@@ -165,24 +165,27 @@ def _down_path(sd: SD, x, emb, enc, multiview: bool):
     return x, skips
 
 
-def _mid(sd: SD, x, emb, enc, multiview: bool):
+def _mid(sd: SD, x, emb, enc, multiview: bool, n_frames: int = 1):
     x = resnet(sd, "mid_block.resnets.0", x, emb)
-    x = transformer_2d(sd, "mid_block.attentions.0", x, enc, multiview)
+    x = transformer_2d(sd, "mid_block.attentions.0", x, enc, multiview, n_frames)
     return resnet(sd, "mid_block.resnets.1", x, emb)
 
 
 # ---------------------------------------------------------------------------------------------------
 # networks/unet_2d_condition_multiview.py:327-527
 # ---------------------------------------------------------------------------------------------------
-def unet_forward(sd: SD, sample, timestep, enc, down_res: Optional[List[torch.Tensor]] = None, mid_res=None):
+def unet_forward(sd: SD, sample, timestep, enc, down_res: Optional[List[torch.Tensor]] = None, mid_res=None,
+                 n_frames: int = 1):
+    """n_frames > 1: video configuration (batch ordered (clip, frame, view); temporal attention after the cross-view
+    attention of every block whose state dict holds `attn_temp` -- defined by this repo, no reference code)"""
     n = sample.shape[0]
     t = torch.as_tensor(timestep).reshape(-1).expand(n) if torch.as_tensor(timestep).numel() == 1 else timestep
     emb = time_embedding(sd, t)                                                 # :386-411
     x = _conv(sd, "conv_in", sample)                                            # :443
-    x, skips = _down_path(sd, x, emb, enc, True)                                # :446-462
+    x, skips = _down_path(sd, x, emb, enc, True, n_frames)                      # :446-462
     if down_res is not None:
         skips = [s + r for s, r in zip(skips, down_res)]                        # :464-473
-    x = _mid(sd, x, emb, enc, True)                                             # :476-485
+    x = _mid(sd, x, emb, enc, True, n_frames)                                   # :476-485
     if mid_res is not None:
         x = x + mid_res                                                         # :487-488
     for i in range(4):                                                          # :491-516
@@ -190,7 +193,7 @@ def unet_forward(sd: SD, sample, timestep, enc, down_res: Optional[List[torch.Te
             x = torch.cat([x, skips.pop()], dim=1)
             x = resnet(sd, f"up_blocks.{i}.resnets.{j}", x, emb)
             if i > 0:
-                x = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", x, enc, True)
+                x = transformer_2d(sd, f"up_blocks.{i}.attentions.{j}", x, enc, True, n_frames)
         if i < 3:
             size = skips[-1].shape[2:]  # forward_upsample_size: explicit target (:363-374,500-501)
             x = F.interpolate(x, size=tuple(size), mode="nearest")

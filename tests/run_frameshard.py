@@ -51,7 +51,46 @@ def main():
         ok = float(t[0]) < 1e-2
         print(f"FRAMESHARD {'OK' if ok else 'FAIL'} world={world} frames={F} clips={n_clip} latent={h}x{w} "
               f"rel_l2(max over ranks)={float(t[0]):.3e} block ms(max over ranks)={float(t[1]):.2f}", flush=True)
+    if os.environ.get("VIDEO_UNET", "0") == "1":
+        video_unet(rank, world, dev, F, h, w)
     dist.destroy_process_group()
+
+
+def video_unet(rank, world, dev, F, h, w):
+    """whole multi-view UNet with temporal blocks: one clip of F frames x 6 views, frames sharded over the ranks; every
+    rank's noise prediction must equal its slice of the single-GPU forward.  Prints 'VIDEOUNET OK ...'."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from dualdiff_b200.networks import UNet2DConditionModelMultiview
+    with torch.device("meta"):
+        unet = UNet2DConditionModelMultiview(cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS, temporal_frames=F)
+    unet.load_state_dict(S.init_state_dict(S.manifest_of(unet), seed=0), strict=True, assign=True)
+    unet = unet.to(dev)
+    g = torch.Generator().manual_seed(9)
+    n = F * 6
+    x = torch.randn(n, 4, h, w, generator=g).to(dev)
+    enc = torch.randn(n, 83, 768, generator=g).to(dev)
+    full = unet(x, 500, enc).sample
+    fs = FrameShard(rank, world, F)
+    unet.frame_shard = fs
+    xs, es = slice_frames(x, fs.frames, F), slice_frames(enc, fs.frames, F)
+    for _ in range(2):
+        part = unet(xs, 500, es).sample
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    part = unet(xs, 500, es).sample
+    e1.record()
+    torch.cuda.synchronize()
+    want = slice_frames(full, fs.frames, F)
+    rel = ((part.float() - want.float()).norm() / want.float().norm()).item()
+    t = torch.tensor([rel, e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ok = float(t[0]) < 1e-2
+        print(f"VIDEOUNET {'OK' if ok else 'FAIL'} world={world} frames={F} views=6 latent={h}x{w} rel_l2(max over ranks)="
+              f"{float(t[0]):.3e} UNet forward ms(max over ranks, eager launches + NCCL all-gathers)={float(t[1]):.2f}", flush=True)
 
 
 if __name__ == "__main__":

@@ -75,3 +75,30 @@ def test_frame_sharded_block_matches_single_gpu():
            "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "run_frameshard.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "FRAMESHARD OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_video_unet_forward_matches_oracle():
+    """UNet2DConditionModelMultiview(temporal_frames=2): 1 clip x 2 frames x 6 views at 16x24 latents through the drop-in
+    forward against oracle.unet_forward(n_frames=2) (fp32 CPU).  Tolerance: cosine >= 0.999, rel-L2 <= 2e-2."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from dualdiff_b200 import synthetic as S
+    from dualdiff_b200.networks import UNet2DConditionModelMultiview
+    from oracle import dualdiff_oracle as O
+    F = 2
+    with torch.device("meta"):
+        unet = UNet2DConditionModelMultiview(cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS, temporal_frames=F)
+    sd = S.init_state_dict(S.manifest_of(unet), seed=0)
+    assert any(".attn_temp." in k for k in sd)
+    unet.load_state_dict(sd, strict=True, assign=True)
+    g = torch.Generator().manual_seed(9)
+    n, h, w = F * 6, 16, 24
+    x = torch.randn(n, 4, h, w, generator=g)
+    enc = torch.randn(n, 83, 768, generator=g)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, 500, enc, n_frames=F)
+        base = O.unet_forward(sd, x, 500, enc, n_frames=1)
+    assert (ref - base).abs().max() > 1e-3 * ref.abs().max()
+    out = unet.to("cuda:0")(x.cuda(), 500, enc.cuda()).sample.float().cpu()
+    m = common.metrics(out, ref)
+    assert m["cos"] > 0.999 and m["rel_l2"] < 2e-2, m
