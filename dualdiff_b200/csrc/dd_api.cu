@@ -100,6 +100,14 @@ int dd_attention(const dd_attention_args* args, void* stream) {
   if (rc == 0) dd::count_launch();
   return rc;
 }
+int dd_ors_project(const float* origins, const float* dirs, const unsigned char* sem, unsigned char* ids, void* rows,
+                   long long n_pix, int sample_point, float sample_step, int D, int H, int W, int keep_fg, int keep_bg,
+                   void* stream) {
+  int rc = dd::ors_project_run(origins, dirs, sem, ids, rows, n_pix, sample_point, sample_step, D, H, W, keep_fg, keep_bg,
+                               reinterpret_cast<cudaStream_t>(stream));
+  if (rc == 0) dd::count_launch();
+  return rc;
+}
 int dd_temporal_attention(const dd_temporal_attention_args* args, void* stream) {
   int rc = dd::temporal_attention_run(args, reinterpret_cast<cudaStream_t>(stream));
   if (rc == 0) dd::count_launch();

@@ -165,6 +165,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_ptr_smem;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of the previous kernel in the stream; its results are only visible after this wait (no-op without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int kchunks = (p.K + BK - 1) / BK;
   // conv mode: an iteration = one (kernel row kh, 64-channel chunk): 1 activation box + 3 weight boxes, 12 UMMAs
@@ -867,13 +870,16 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   cfg.blockDim = dim3(epi_warps == 8 ? GEMM_THREADS_MAX : GEMM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  static const int pdl = getenv("DD_PDL") ? atoi(getenv("DD_PDL")) : 1;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   DD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, CONV>, tmA, tmA2, tmB, tmOut, tmR1, p));
   return 0;
 }

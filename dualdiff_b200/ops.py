@@ -249,6 +249,25 @@ def temporal_attention(q, k, v, *, n_outer, n_view, tokens, heads, head_dim, fra
     return out
 
 
+def ors_project(origins, dirs, semantics, *, sample_point, sample_step=0.2, want_ids=True, want_rows=False,
+                keep_fg=True, keep_bg=True):
+    """origins / dirs: fp32 [n_pix, 3]; semantics: uint8 [D, H, W] -> (ids uint8 [n_pix, S] | None, rows bf16 [n_pix, S] | None)"""
+    _req(origins, torch.float32, "origins")
+    _req(dirs, torch.float32, "dirs")
+    _req(semantics, torch.uint8, "semantics")
+    assert origins.is_contiguous() and dirs.is_contiguous() and semantics.is_contiguous()
+    n_pix = origins.shape[0]
+    D, H, W = semantics.shape
+    ids = torch.empty((n_pix, sample_point), device=origins.device, dtype=torch.uint8) if want_ids else None
+    rows = torch.empty((n_pix, sample_point), device=origins.device, dtype=torch.bfloat16) if want_rows else None
+    with _Rec("ors_project", 0.0, n_pix * sample_point * ((1 if want_ids else 0) + (2 if want_rows else 0)) + n_pix * 24,
+              f"pix{n_pix}_S{sample_point}"):
+        check(_lib.lib().dd_ors_project(_ptr(origins), _ptr(dirs), _ptr(semantics), _ptr(ids), _ptr(rows),
+                                        _L(n_pix), _I(sample_point), C.c_float(sample_step), _I(D), _I(H), _I(W),
+                                        _I(1 if keep_fg else 0), _I(1 if keep_bg else 0), _stream()), "dd_ors_project")
+    return ids, rows
+
+
 def nchw_to_padded(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_view, stride_c, stride_h, out=None):
     assert src.is_cuda and src.dtype in (torch.float32, torch.bfloat16)
     n = n_outer * n_view

@@ -138,6 +138,18 @@ typedef struct dd_temporal_attention_args {
 } dd_temporal_attention_args;
 DD_API int dd_temporal_attention(const dd_temporal_attention_args* args, void* stream);
 
+/* ---- Occupancy Ray-shape Sampling projector (networks/occ3d_proj.py:50-113, OccupancyRay.project) ---------------
+ * origins / dirs: fp32 [n_pix, 3] ray origin and unit direction per (camera, y, x) pixel of the compressed image grid
+ * (occ3d_proj.py:26-42, computed on the host exactly as the reference does); sem: uint8 Occ3D labels [D, H, W]
+ * (200 x 200 x 16).  For sample s of pixel p the label of the voxel nearest to origin + s*sample_step*dir is looked up
+ * (grid_sample 'nearest', align_corners=False semantics; class 17 outside the volume).
+ * ids (optional): uint8 [n_pix, sample_point] = the reference's output.  rows (optional): bf16 [n_pix, sample_point] =
+ * filter(ids) / 17, the channels-last form of the (B*6, 320, h, w) tensor the foreground branch consumes
+ * (dataset/utils.py:412-420; keep_fg = 0 maps classes <= 10 to 17, keep_bg = 0 maps classes >= 11 to 17). */
+DD_API int dd_ors_project(const float* origins, const float* dirs, const unsigned char* sem, unsigned char* ids, void* rows,
+                          long long n_pix, int sample_point, float sample_step, int D, int H, int W, int keep_fg,
+                          int keep_bg, void* stream);
+
 /* ---- layout / gather kernels feeding the implicit-GEMM convolution ---------------------------------- */
 /* NCHW (fp32 or bf16, arbitrary outer strides) -> padded channels-last bf16 with channel zero-padding to cp.
  * Image index = outer * n_view + view; source offset = outer*stride_outer + view*stride_view + c*stride_c +
