@@ -399,6 +399,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int nout0 = geglu ? (n0 / BN) * (BN / 2) : n0;
           const uint32_t as = local_tile & 1;
           const uint32_t aph = (local_tile >> 1) & 1;
+          // residual boxes of this warp's chunks of the NEXT tile -> L2 now (a whole tile ahead of their TMA loads)
+          if (has_r1 && lane == 0 && tile + n_workers < total_tiles) {
+            const int t2 = tile + n_workers;
+            const int tm2 = (t2 / p.n_tiles) * TILE_M + (int)crank * BM + q * 32;
+            for (int ch = half; ch < nch; ch += n_epi_halves) tma_prefetch_2d(&tmR1, (t2 % p.n_tiles) * BN + ch * 64, tm2);
+          }
           mbar_wait(tfull_bar + 8 * as, aph);
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
