@@ -108,7 +108,7 @@ EXPORTS = [
     "dd_version", "dd_last_error", "dd_launch_count", "dd_gemm", "dd_groupnorm", "dd_groupnorm_scratch_floats", "dd_layernorm", "dd_attention", "dd_temporal_attention", "dd_ors_project",
     "dd_nchw_to_padded", "dd_im2col_s2", "dd_upsample_pad", "dd_pad_rows", "dd_linear_f32",
     "dd_timestep_embedding", "dd_fourier_embed", "dd_box_features", "dd_silu_to_bf16", "dd_add_bf16",
-    "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step",
+    "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step", "dd_softmax_rows",
 ]
 
 

@@ -314,6 +314,26 @@ __global__ void cfg_sched_kernel(const float* __restrict__ eps, float* __restric
   }
 }
 
+// softmax over the rows of an fp32 score matrix -> bf16 probabilities: one warp per row (row read once into registers
+// for up to 2048 columns, otherwise re-read).  Used by the single-head, 512-wide mid-block attention of the VAE decoder,
+// whose head dimension does not fit the flash kernel's TMEM budget (S 128 + O 512 + P 64 columns > 512).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, long long x_ld, bf16* __restrict__ out, long long out_ld, int rows, int cols,
+                    float scale_log2e) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (long long)row * x_ld;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c]);
+  m = warp_max(m);
+  float l = 0.f;
+  for (int c = lane; c < cols; c += 32) l += exp2f((xr[c] - m) * scale_log2e);
+  l = warp_sum(l);
+  const float inv = 1.f / l;
+  bf16* orow = out + (long long)row * out_ld;
+  for (int c = lane; c < cols; c += 32) orow[c] = __float2bfloat16(exp2f((xr[c] - m) * scale_log2e) * inv);
+}
 }  // namespace dd
 
 using namespace dd;
@@ -363,6 +383,15 @@ int dd_box_features(const float* boxes, const long long* classes, const unsigned
 int dd_silu_to_bf16(const float* x, void* out, long long n, void* stream) {
   silu_to_bf16_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<bf16*>(out), n);
   if (cudaGetLastError() != cudaSuccess) { set_error("dd_silu_to_bf16 launch failed"); return -2; }
+  count_launch();
+  return 0;
+}
+int dd_softmax_rows(const float* x, long long x_ld, void* out, long long out_ld, int rows, int cols, float scale,
+                    void* stream) {
+  if (rows <= 0 || cols <= 0) { set_error("dd_softmax_rows: bad shape"); return -1; }
+  softmax_rows_kernel<<<(unsigned)(((long long)rows * 32 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, x_ld, reinterpret_cast<bf16*>(out), out_ld, rows, cols, scale * 1.4426950408889634f);
+  if (cudaGetLastError() != cudaSuccess) { set_error("dd_softmax_rows launch failed"); return -2; }
   count_launch();
   return 0;
 }

@@ -152,7 +152,7 @@ gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(rows_img, r_begin + rows_per_cta);
   bf16* obase = out + (long long)img * rows_img * out_ld + c0;
-  const uint32_t wp_magic = (uint32_t)((0x100000000ull + (uint32_t)Wp - 1) / (uint32_t)Wp);   // rr / Wp for rr < 2^16
+  const uint32_t wp_magic = (uint32_t)((0x100000000ull + (uint32_t)Wp - 1) / (uint32_t)Wp);   // rr / Wp, exact for rr * Wp < 2^32
   for (int r = r_begin + sub; r < r_end; r += GN_UA * rpi) {
     uint4 v[GN_UA];
     bool live[GN_UA];
@@ -233,7 +233,8 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
   DD_CHECK(C % a->groups == 0 && a->groups <= 512, -1, "dd_groupnorm: C=%d not divisible by groups=%d (<= 512)", C, a->groups);
   DD_CHECK(C <= 4096, -1, "dd_groupnorm: C=%d too large (max 4096)", C);
   DD_CHECK(a->c2 == 0 || a->x2 != nullptr, -1, "dd_groupnorm: x2 missing");
-  DD_CHECK((a->h + 1) * (a->w + 1) < 65536, -1, "dd_groupnorm: image too large (%d x %d)", a->h, a->w);
+  // padded-row index / (W+1) by multiply-high is exact while rows * (W+1) < 2^32
+  DD_CHECK((long long)(a->h + 1) * (a->w + 1) * (a->w + 1) < (1LL << 32), -1, "dd_groupnorm: image too large (%d x %d)", a->h, a->w);
   const int HW = a->h * a->w;
   int rpi = 0;
   const int threads = groupnorm_threads(C, &rpi);

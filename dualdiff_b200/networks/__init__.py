@@ -5,3 +5,4 @@ from .output_cls import BEVControlNetOutput, UNet2DConditionOutput  # noqa: F401
 from .unet_2d_condition_multiview import UNet2DConditionModelMultiview  # noqa: F401
 from .unet_addon_rawbox import BEVControlNetModel  # noqa: F401
 from .occ3d_proj import OccupancyRay  # noqa: F401
+from .vae import AutoencoderKLDecoder  # noqa: F401

@@ -371,6 +371,18 @@ def add_bf16(a, b, c=None, out=None):
     return out
 
 
+def softmax_rows(x, scale, out=None):
+    """fp32 scores [rows, cols] -> bf16 softmax(x * scale) along the columns"""
+    _req(x, torch.float32, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
+    with _Rec("elementwise", 0.0, 6.0 * rows * cols):
+        check(_lib.lib().dd_softmax_rows(_ptr(x), _L(x.stride(0)), _ptr(out), _L(out.stride(0)), _I(rows), _I(cols),
+                                         C.c_float(scale), _stream()), "dd_softmax_rows")
+    return out
+
+
 def nchw_to_rows(src, out=None):
     """[n, C, H, W] fp32/bf16 contiguous -> [n*H*W, C] bf16"""
     assert src.is_cuda and src.is_contiguous()

@@ -193,6 +193,10 @@ DD_API int dd_box_features(const float* boxes, const long long* classes, const u
 DD_API int dd_silu_to_bf16(const float* x, void* out, long long n, void* stream);
 /* out = a + b (+ c) elementwise over bf16, n elements (multiple of 8) */
 DD_API int dd_add_bf16(const void* a, const void* b, const void* c, void* out, long long n, void* stream);
+/* out[r, c] = softmax_c(x[r, :] * scale) (fp32 scores -> bf16 probabilities), one warp per row: the single-head 512-wide
+ * attention of the VAE decoder's mid block (diffusers AutoencoderKL, called at pipeline_bev_controlnet.py:101-113) */
+DD_API int dd_softmax_rows(const float* x, long long x_ld, void* out, long long out_ld, int rows, int cols, float scale,
+                           void* stream);
 /* fp32 -> bf16 / bf16 -> fp32 NCHW<->channels-last conversions at the module boundary */
 DD_API int dd_nchw_to_rows(const void* src, int src_f32, void* out, int n_img, int c, int hw, void* stream);
 DD_API int dd_rows_to_nchw(const void* rows, int rows_f32, long long ld, void* out, int out_f32, int n_img, int c,
