@@ -949,6 +949,8 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
       case 40: {
         DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
                  "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
+        static const int bn64 = getenv("DD_ATTN_BN64") ? atoi(getenv("DD_ATTN_BN64")) : 0;   // A/B: 64-key tiles at d = 40
+        if (bn64) return launch_attn_v2<48, 40, 48, 64, 3, 2, 0, false>(a, p, stream);
         if (poly == 2) return launch_attn_v2<48, 40, 48, 128, 3, 2, 2, false>(a, p, stream);
         if (pipe) return launch_attn_v2<48, 40, 48, 128, 3, 2, 0, true>(a, p, stream);
         return launch_attn_v2<48, 40, 48, 128, 3, 2, 0, false>(a, p, stream);
