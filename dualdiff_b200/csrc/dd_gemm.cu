@@ -10,13 +10,18 @@
 //                                                            conv_out.  The activation is stored in a
 //                                                            zero-haloed "padded pixel" layout
 //                                                            [img][H+1][W+1][C], so tap (kh,kw) is the same
-//                                                            2-D TMA box shifted by (kh-1)*(W+1)+(kw-1) rows.
+//                                                            rows shifted by (kh-1)*(W+1)+(kw-1); one staged
+//                                                            box of 128+2 rows serves the three kw taps of a
+//                                                            kernel row (row-shifted UMMA descriptors).
 //   * channel concat of two sources along K (skip connections of the up blocks) without torch.cat.
 // Epilogues (fused): +bias[n], +per-image vector (time-embedding), +residual(s), GEGLU, fp32/bf16 out,
 // padded-pixel -> compact-row scatter for the conv mode.
 //
-// Roles: warp0 = TMA producer, warp1 = UMMA issuer (+TMEM alloc), warps2-5 = epilogue (TMEM -> regs -> HBM).
-// Pipelines: smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty).
+// Roles: warp0 = TMA producer, warp1 = UMMA issuer (+TMEM alloc), warps2-9 = epilogue (TMEM -> regs -> HBM; a TMA
+// load/store epilogue for plain bf16 GEMMs, a register epilogue for conv scatter / fp32 / stream-K partials).
+// Pipelines: smem rings (full/empty mbarriers; conv mode keeps separate activation and weight rings) and a 2-deep TMEM
+// accumulator ring (tmem_full/tmem_empty).  Work: one tile per CTA pair, or stream-K ranges of the flattened
+// (tile, k-iteration) space when the tiles fill the last wave badly (second pass: splitk_reduce_kernel).
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,8 +33,8 @@ namespace dd {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-static constexpr int GEMM_THREADS = 192;      // 2 + 4 epilogue warps (register / smem-transpose epilogue)
-static constexpr int GEMM_THREADS_MAX = 320;  // 2 + 8 epilogue warps (TMA epilogue)
+static constexpr int GEMM_THREADS = 192;      // 2 + 4 epilogue warps (DD_EPI8=0 A/B switch of the register epilogue)
+static constexpr int GEMM_THREADS_MAX = 320;  // 2 + 8 epilogue warps (default for both epilogues)
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARP_BYTES = 32 * 64 * 4;  // per-epilogue-warp transpose buffer (32 rows x 64 fp32)
 // 3x3 conv mode: one staged activation box of 128 + 2 halo rows serves the three kw taps of a kernel row (the UMMA
