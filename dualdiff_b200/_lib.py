@@ -69,6 +69,16 @@ class TemporalAttentionArgs(C.Structure):
     ]
 
 
+class SeqAttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("v", _vp), ("out", _vp),
+        ("q_ld", _ll), ("k_ld", _ll), ("v_ld", _ll), ("out_ld", _ll),
+        ("q_col0", _i), ("k_col0", _i), ("v_col0", _i),
+        ("q_head_stride", _i), ("k_head_stride", _i), ("v_head_stride", _i),
+        ("n_seq", _i), ("seq_len", _i), ("heads", _i), ("head_dim", _i), ("causal", _i), ("scale", _f),
+    ]
+
+
 class ToPaddedArgs(C.Structure):
     _fields_ = [("src", _vp), ("out", _vp), ("stride_outer", _ll), ("stride_view", _ll), ("stride_c", _ll),
                 ("stride_h", _ll), ("n_outer", _i), ("n_view", _i), ("c", _i), ("h", _i), ("w", _i), ("cp", _i),
@@ -109,6 +119,7 @@ EXPORTS = [
     "dd_nchw_to_padded", "dd_im2col_s2", "dd_upsample_pad", "dd_pad_rows", "dd_linear_f32",
     "dd_timestep_embedding", "dd_fourier_embed", "dd_box_features", "dd_silu_to_bf16", "dd_add_bf16",
     "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step", "dd_softmax_rows",
+    "dd_clip_embed", "dd_seq_attention", "dd_quick_gelu",
 ]
 
 

@@ -14,5 +14,6 @@ int temporal_attention_run(const dd_temporal_attention_args* a, cudaStream_t str
 int ors_project_run(const float* origins, const float* dirs, const unsigned char* sem, unsigned char* ids, void* rows,
                     long long n_pix, int sample_point, float sample_step, int D, int H, int W, int keep_fg, int keep_bg,
                     cudaStream_t stream);
+int seq_attention_run(const dd_seq_attention_args* a, cudaStream_t stream);
 void count_launch(int n = 1);
 }  // namespace dd

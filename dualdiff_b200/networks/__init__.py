@@ -6,3 +6,4 @@ from .unet_2d_condition_multiview import UNet2DConditionModelMultiview  # noqa: 
 from .unet_addon_rawbox import BEVControlNetModel  # noqa: F401
 from .occ3d_proj import OccupancyRay  # noqa: F401
 from .vae import AutoencoderKLDecoder  # noqa: F401
+from .clip_text import CLIPTextConfig, CLIPTextModel  # noqa: F401

@@ -144,8 +144,8 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
 
 
 # ---------------------------------------------------------------------------------------------------
-from ._lib import (AttentionArgs, GroupNormArgs, LayerNormArgs, LinearF32Args, TemporalAttentionArgs,  # noqa: E402
-                   ToPaddedArgs)
+from ._lib import (AttentionArgs, GroupNormArgs, LayerNormArgs, LinearF32Args, SeqAttentionArgs,  # noqa: E402
+                   TemporalAttentionArgs, ToPaddedArgs)
 
 _L = C.c_longlong
 _I = C.c_int
@@ -380,6 +380,60 @@ def softmax_rows(x, scale, out=None):
     with _Rec("elementwise", 0.0, 6.0 * rows * cols):
         check(_lib.lib().dd_softmax_rows(_ptr(x), _L(x.stride(0)), _ptr(out), _L(out.stride(0)), _I(rows), _I(cols),
                                          C.c_float(scale), _stream()), "dd_softmax_rows")
+    return out
+
+
+def clip_embed(ids, tok_emb, pos_emb, out=None):
+    """CLIPTextEmbeddings: ids int64 [n_seq, L] -> bf16 rows [n_seq*L, C] = tok_emb[ids] + pos_emb[position]"""
+    _req(ids, torch.int64, "ids")
+    _req(tok_emb, torch.float32, "tok_emb")
+    _req(pos_emb, torch.float32, "pos_emb")
+    assert ids.is_contiguous() and tok_emb.is_contiguous() and pos_emb.is_contiguous()
+    n_seq, L = ids.shape
+    vocab, c = tok_emb.shape
+    if L > pos_emb.shape[0] or pos_emb.shape[1] != c:
+        raise ValueError(f"sequence length {L} exceeds the {pos_emb.shape[0]} position embeddings")
+    if out is None:
+        out = torch.empty((n_seq * L, c), device=ids.device, dtype=torch.bfloat16)
+    with _Rec("elementwise", 0.0, n_seq * L * (8.0 + 10.0 * c)):
+        check(_lib.lib().dd_clip_embed(_ptr(ids), _ptr(tok_emb), _ptr(pos_emb), _ptr(out), _L(out.stride(0)),
+                                       _L(n_seq * L), _I(L), _I(c), _I(vocab), _stream()), "dd_clip_embed")
+    return out
+
+
+def seq_attention(q, k, v, *, n_seq, seq_len, heads, head_dim, causal=True, out=None, q_col0=0, k_col0=0, v_col0=0,
+                  q_hs=None, k_hs=None, v_hs=None, scale=None):
+    """attention over short sequences (seq_len <= 128, head_dim 64) with an optional causal mask.
+    q/k/v: bf16 [n_seq*seq_len, *] (may be column views of one fused projection output)."""
+    _req(q, torch.bfloat16, "q")
+    _req(k, torch.bfloat16, "k")
+    _req(v, torch.bfloat16, "v")
+    if out is None:
+        out = torch.empty((n_seq * seq_len, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = SeqAttentionArgs()
+    a.q = _ptr(q); a.k = _ptr(k); a.v = _ptr(v); a.out = _ptr(out)
+    a.q_ld = q.stride(0); a.k_ld = k.stride(0); a.v_ld = v.stride(0); a.out_ld = out.stride(0)
+    a.q_col0 = q_col0; a.k_col0 = k_col0; a.v_col0 = v_col0
+    a.q_head_stride = head_dim if q_hs is None else q_hs
+    a.k_head_stride = head_dim if k_hs is None else k_hs
+    a.v_head_stride = head_dim if v_hs is None else v_hs
+    a.n_seq = n_seq; a.seq_len = seq_len; a.heads = heads; a.head_dim = head_dim
+    a.causal = 1 if causal else 0
+    a.scale = float(head_dim) ** -0.5 if scale is None else scale
+    with _Rec("seq_attention", 4.0 * n_seq * seq_len * seq_len * heads * head_dim * (0.5 if causal else 1.0),
+              8.0 * n_seq * seq_len * heads * head_dim, f"d{head_dim}_L{seq_len}"):
+        check(_lib.lib().dd_seq_attention(C.byref(a), _stream()), "dd_seq_attention")
+    return out
+
+
+def quick_gelu(x, out=None):
+    """x * sigmoid(1.702 x) over bf16 (in place when out is x)"""
+    _req(x, torch.bfloat16, "x")
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    with _Rec("elementwise", 0.0, 4.0 * x.numel()):
+        check(_lib.lib().dd_quick_gelu(_ptr(x), _ptr(out), _L(x.numel()), _stream()), "dd_quick_gelu")
     return out
 
 

@@ -76,26 +76,41 @@ class DualDiffDenoiser:
             text = prompt_embeds[-B:]
         # condition image / ORS tensor are identical in both CFG halves (pipeline:351-373 skips the uncond map)
         conds = [torch.cat([images[0]] * G) if G > 1 else images[0], torch.cat([images[1]] * G) if G > 1 else images[1]]
-        self.preps = [net.prepare_condition(cam, text, boxes[i], conds[i], H, W) for i, net in enumerate(self.nets)]
+        preps = [net.prepare_condition(cam, text, boxes[i], conds[i], H, W) for i, net in enumerate(self.nets)]
         Pu = self.unet._packed
-        self.unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, self.preps[0].enc_rows)  # tokens of branch 0
+        unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, preps[0].enc_rows)  # tokens of branch 0
         if self.view_shard is None:
-            self.kv_map = engine.make_kv_map(n, n_cam, dev)
+            kv_map = engine.make_kv_map(n, n_cam, dev)
         else:
             assert self.view_shard.v_loc == n_cam
-            self.kv_map = self.view_shard.kv_map(G * B, dev)
+            kv_map = self.view_shard.kv_map(G * B, dev)
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         self.coef_table = self.scheduler.coef_table(dev)
         self.t_table = self.scheduler.timesteps.to(device=dev, dtype=torch.float32)
         # state (fp32, NCHW-flat): latents, last corrected sample, x0 history
-        self.latents = latents.reshape(B * n_cam, c, H, W).float().contiguous().clone()
-        self.last = torch.zeros_like(self.latents)
-        self.m0 = torch.zeros_like(self.latents)
-        self.m1 = torch.zeros_like(self.latents)
-        self.t_cur = torch.zeros(1, device=dev, dtype=torch.float32)
-        self.coef_cur = torch.zeros(16, device=dev, dtype=torch.float32)
+        lat = latents.reshape(B * n_cam, c, H, W).float().contiguous()
+        # every tensor the captured step reads: when a graph of the same geometry exists (the pipeline calling again with
+        # another prompt / scene), the new values are copied into the buffers it was captured on and the graph is kept
+        sig = (self.cfg, B, n_cam, c, H, W, tuple(p.lk for p in preps), str(dev))
+        new_in = _graph_inputs(preps, unet_text_kv, kv_map)
+        if self._graph is not None and getattr(self, "_sig", None) == sig and \
+                [(t.shape, t.dtype) for t in new_in] == [(t.shape, t.dtype) for t in self._static_in]:
+            for dst, src in zip(self._static_in, new_in):
+                dst.copy_(src)
+            self.latents.copy_(lat)
+            for t in (self.last, self.m0, self.m1):
+                t.zero_()
+        else:
+            self.preps, self.unet_text_kv, self.kv_map = preps, unet_text_kv, kv_map
+            self._static_in, self._sig = new_in, sig
+            self.latents = lat.clone()
+            self.last = torch.zeros_like(self.latents)
+            self.m0 = torch.zeros_like(self.latents)
+            self.m1 = torch.zeros_like(self.latents)
+            self.t_cur = torch.zeros(1, device=dev, dtype=torch.float32)
+            self.coef_cur = torch.zeros(16, device=dev, dtype=torch.float32)
+            self._graph = None
         self.eps_rows = None
-        self._graph = None
         self.step_index = 0
         return self
 
@@ -178,6 +193,16 @@ class DualDiffDenoiser:
         for i in range(len(self.scheduler.timesteps)):
             self.step(i)
         return self.latents.reshape(self.B, self.n_cam, 4, self.H, self.W)
+
+
+def _graph_inputs(preps, unet_text_kv, kv_map):
+    """the tensors prepare() produces and the step kernels read, in a fixed order"""
+    ts = []
+    for p in preps:
+        ts += [p.enc_rows, p.cond] + [p.text_kv[k] for k in sorted(p.text_kv)]
+    ts += [unet_text_kv[k] for k in sorted(unet_text_kv)]
+    ts.append(kv_map)
+    return ts
 
 
 def _launches():

@@ -42,7 +42,9 @@ def init_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tensor
         return torch.randn(shape, generator=g)
     if "null_" in key:
         return torch.randn(shape, generator=g) * 0.02
-    is_norm = ".norm" in key or key.startswith("conv_norm_out") or ".norm." in key
+    if key.endswith("_embedding.weight"):   # CLIP token / position tables (transformers init: N(0, 0.02))
+        return torch.randn(shape, generator=g) * 0.02
+    is_norm = ".norm" in key or key.startswith("conv_norm_out") or ".norm." in key or "layer_norm" in key
     if is_norm and len(shape) == 1:
         if leaf == "weight":
             return 1.0 + 0.05 * torch.randn(shape, generator=g)

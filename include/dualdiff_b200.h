@@ -150,6 +150,30 @@ DD_API int dd_ors_project(const float* origins, const float* dirs, const unsigne
                           long long n_pix, int sample_point, float sample_step, int D, int H, int W, int keep_fg,
                           int keep_bg, void* stream);
 
+/* ---- prompt encoder pieces -----------------------------------------------------------------
+ * The pipeline encodes the prompt once per sample with transformers' CLIPTextModel through diffusers' `_encode_prompt`
+ * (pipeline/pipeline_bev_controlnet.py:273-281).  Projections / MLP run on dd_gemm and the LayerNorms on dd_layernorm;
+ * these are the remaining pieces (dualdiff_b200/networks/clip_text.py strings them together). */
+/* CLIPTextEmbeddings: out[r, :] = tok_emb[ids[r], :] + pos_emb[r % seq_len, :]   (fp32 tables [vocab, c] / [seq_len, c],
+ * int64 ids [n_tok], bf16 rows out).  An id outside [0, vocab) yields a NaN row (the host wrapper validates first). */
+DD_API int dd_clip_embed(const long long* ids, const float* tok_emb, const float* pos_emb, void* out, long long out_ld,
+                         long long n_tok, int seq_len, int c, int vocab, void* stream);
+/* attention over short sequences (seq_len <= 128, head_dim 64), optionally causal -- CLIPAttention with the causal mask of
+ * the text model: out[s*L + i, h*64 + c] = sum_{j <= i} softmax_j(q_i k_j * scale) v_j.  q/k/v are bf16 row-major
+ * [n_seq*seq_len, ld] matrices addressed like dd_attention (column offset + head stride: a fused QKV output in place). */
+typedef struct dd_seq_attention_args {
+  const void* q; const void* k; const void* v; void* out;
+  long long q_ld, k_ld, v_ld, out_ld;
+  int q_col0, k_col0, v_col0;
+  int q_head_stride, k_head_stride, v_head_stride;
+  int n_seq, seq_len, heads, head_dim;
+  int causal;
+  float scale;
+} dd_seq_attention_args;
+DD_API int dd_seq_attention(const dd_seq_attention_args* args, void* stream);
+/* out = x * sigmoid(1.702 x) over bf16 (CLIP `quick_gelu`), n elements (multiple of 8); in place allowed */
+DD_API int dd_quick_gelu(const void* x, void* out, long long n, void* stream);
+
 /* ---- layout / gather kernels feeding the implicit-GEMM convolution ---------------------------------- */
 /* NCHW (fp32 or bf16, arbitrary outer strides) -> padded channels-last bf16 with channel zero-padding to cp.
  * Image index = outer * n_view + view; source offset = outer*stride_outer + view*stride_view + c*stride_c +

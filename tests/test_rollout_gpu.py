@@ -99,3 +99,80 @@ def test_hd_resolution_runs_and_is_deterministic(world):
     a = _cuda_rollout(world, inp, SCH.UniPCMultistepScheduler(), 2, 2.0, graph=True)
     b = _cuda_rollout(world, inp, SCH.UniPCMultistepScheduler(), 2, 2.0, graph=False)
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_pipeline_call_matches_oracle(world):
+    """StableDiffusionBEVControlNetPipeline.__call__ end to end (prompt strings -> CLIP -> 3 UniPC steps with CFG -> VAE
+    decode) against the oracle chain clip_oracle.encode_prompt -> dualdiff_oracle.denoise_step x 3 -> vae_oracle.
+    Tolerances: prompt embeddings / final latents cosine >= 0.99, decoded images max-abs <= 0.1 of the
+    [0, 1] range and mean-abs <= 0.02."""
+    from dualdiff_b200 import scheduler as SCH, synthetic as S
+    from dualdiff_b200.networks import AutoencoderKLDecoder, CLIPTextModel
+    from dualdiff_b200.pipeline_bev_controlnet import BEVStableDiffusionPipelineOutput, StableDiffusionBEVControlNetPipeline
+    from oracle import clip_oracle as CO, dualdiff_oracle as O, vae_oracle as V
+    clip_cfg = dict(vocab_size=1000, hidden_size=768, intermediate_size=3072, num_hidden_layers=2, num_attention_heads=12,
+                    max_position_embeddings=77)
+    tok = CO.HashTokenizer(vocab_size=1000)
+    sd_clip = S.init_state_dict(CO.manifest(**clip_cfg), seed=3)
+    enc = CLIPTextModel(**clip_cfg, eos_token_id=tok.eos_token_id)
+    enc.load_state_dict(sd_clip, strict=True)
+    sd_vae = S.init_state_dict(V.manifest(), seed=4)
+    with torch.device("meta"):
+        vae = AutoencoderKLDecoder()
+    vae.load_state_dict(sd_vae, strict=True, assign=True)
+    pipe = StableDiffusionBEVControlNetPipeline(vae, enc, world["unet"], world["nets"], SCH.UniPCMultistepScheduler(), tok)
+    pipe.to("cuda:0")
+    pipe.set_progress_bar_config(disable=True)
+    pipe.enable_xformers_memory_efficient_attention()
+    inp = S.make_inputs(2, 8, 12, seed=5, L_bg=7, L_fg=3)
+    prompts = ["a driving scene image at singapore-onenorth. rain, many pedestrians", "a driving scene image at boston-seaport. night"]
+    kwargs = dict(prompt=prompts, image=[inp["cond_bg"], inp["cond_fg"]], camera_param=inp["camera_param"], height=64,
+                  width=96, num_inference_steps=3, guidance_scale=2.0,
+                  bev_controlnet_kwargs={"bboxes_3d_data": [inp["boxes_bg"], inp["boxes_fg"]], "use_aug_text": False})
+    seen = []
+    out = pipe(**kwargs, generator=torch.Generator().manual_seed(7), output_type="latent",
+               callback=lambda i, t, lat: seen.append((i, int(t), tuple(lat.shape))))
+    assert isinstance(out, BEVStableDiffusionPipelineOutput) and out.nsfw_content_detected is None
+    lat = out.images.float().cpu()
+    assert lat.shape == (2, 6, 4, 8, 12) and [s[0] for s in seen] == [0, 1, 2] and seen[0][2] == (2, 6, 4, 8, 12)
+    # ---- the oracle chain on the host ----
+    with torch.no_grad():
+        pe = CO.encode_prompt(sd_clip, tok, prompts)
+        pe_cuda = pipe._encode_prompt(prompts, pipe.device, 1, True).float().cpu()
+        m = common.metrics(pe_cuda, pe)
+        assert pe.shape == (4, 77, 768) and m["cos"] > 0.999 and m["rel_l2"] < 2e-2, m
+        lat0 = torch.randn(2, 4, 8, 12, generator=torch.Generator().manual_seed(7))
+        ref_inp = dict(inp)
+        ref_inp["latents"] = torch.stack([lat0] * 6, dim=1)
+        ref_inp["prompt_embeds"] = pe
+        osch = O.UniPC()
+        osch.set_timesteps(3)
+        ref = _oracle_rollout(world["sds"], ref_inp, osch, 3, True, 2.0)
+        ref_img = V.decode_latents(sd_vae, ref.reshape(12, 4, 8, 12)).reshape(2, 6, 3, 64, 96).permute(0, 1, 3, 4, 2)
+    m = common.metrics(lat, ref)
+    print("pipeline latents vs oracle:", m)
+    assert torch.isfinite(lat).all() and m["cos"] >= 0.99 and m["rel_l2"] <= 5e-2, m
+    # ---- decoded output, both output types ----
+    res = pipe(**kwargs, generator=torch.Generator().manual_seed(7), output_type="np", return_dict=False)
+    img = torch.from_numpy(res[0])
+    assert img.shape == (2, 6, 64, 96, 3) and img.min() >= 0 and img.max() <= 1 and res[1] is None
+    d = (img - ref_img).abs()
+    print("pipeline images vs oracle: max", d.max().item(), "mean", d.mean().item())
+    assert d.max() <= 0.1 and d.mean() <= 0.02
+    pil = pipe(**kwargs, generator=torch.Generator().manual_seed(7), num_images_per_prompt=1).images
+    assert len(pil) == 2 and len(pil[0]) == 6 and pil[0][0].size == (96, 64)
+
+
+def test_pipeline_rejects_unbuilt_options(world):
+    from dualdiff_b200 import scheduler as SCH
+    from dualdiff_b200.pipeline_bev_controlnet import StableDiffusionBEVControlNetPipeline
+    pipe = StableDiffusionBEVControlNetPipeline(None, None, world["unet"], world["nets"], SCH.UniPCMultistepScheduler(), None)
+    base = dict(prompt=None, image=[None, None], camera_param=None, height=64, width=96)
+    with pytest.raises(NotImplementedError, match="guess_mode"):
+        pipe(**base, guess_mode=True)
+    with pytest.raises(NotImplementedError, match="use_aug_text"):
+        pipe(**base, bev_controlnet_kwargs={"use_aug_text": True})
+    with pytest.raises(ValueError, match="bboxes_3d_data"):
+        pipe(**base, bev_controlnet_kwargs={"use_aug_text": False})
+    with pytest.raises(AssertionError):
+        StableDiffusionBEVControlNetPipeline(None, None, None, None, None, None, safety_checker=object())
