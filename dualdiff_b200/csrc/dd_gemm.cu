@@ -445,9 +445,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               } else {
                 tmem_ld_wait();
                 if (bias) {
+                  // columns of the last tile beyond N are never stored, but their bias must not be READ either: the
+                  // overhang (e.g. N = 320 on 192-wide tiles) would run up to 512 B past the end of the bias vector
+                  const int ncol = p.N - (n0 + c + h);
 #pragma unroll
                   for (int j = 0; j < 32; j += 4) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < ncol) b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
                     a[j] = __float_as_uint(__uint_as_float(a[j]) + b.x);
                     a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + b.y);
                     a[j + 2] = __float_as_uint(__uint_as_float(a[j + 2]) + b.z);

@@ -24,6 +24,9 @@ with torch.device("meta"):
     enc, vae = CLIPTextModel(), AutoencoderKLDecoder()
 enc.load_state_dict(S.init_state_dict(CO.manifest(), seed=3), strict=True, assign=True)
 vae.load_state_dict(S.init_state_dict(V.manifest(), seed=4), strict=True, assign=True)
+if os.environ.get("PACK_FIRST"):      # diagnostic: pack from the host copies of the weights before moving the modules
+    for m in [unet] + nets:
+        m.pack(torch.device("cuda", 0))
 pipe = StableDiffusionBEVControlNetPipeline(vae, enc, unet, nets, SCH.UniPCMultistepScheduler(), CO.HashTokenizer()).to("cuda:0")
 pipe.set_progress_bar_config(disable=True)
 inp = S.make_inputs(B, 28, 50, seed=1, L_bg=28, L_fg=32)
