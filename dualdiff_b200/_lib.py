@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdualdiff_sm100.so")
+# DUALDIFF_LIB: A/B measurements against another build of the same C ABI (never a fallback: the file must exist)
+LIB_PATH = os.environ.get("DUALDIFF_LIB") or os.path.join(_HERE, "libdualdiff_sm100.so")
 
 
 class DDError(RuntimeError):
