@@ -88,6 +88,58 @@ class CLIPTextModel(nn.Module):
             node.register_parameter(leaf, nn.Parameter(torch.empty(shape)))
         self._packed = None
 
+    # ---- checkpoints (transformers layout: config.json + model.safetensors | pytorch_model.bin) -------------------
+    config_name = "config.json"
+    weights_names = ("model.safetensors", "pytorch_model.bin")
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """load `<sd-v1-5>/text_encoder` the way `pipe_cls.from_pretrained` does for the reference (misc/test_utils.py:
+        150-156).  Keys outside the text model (`position_ids` buffers of older transformers) are ignored; a missing or
+        mis-shaped text-model tensor raises."""
+        import json
+        import os
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(root, cls.config_name)) as fh:
+            cfg = {k: v for k, v in json.load(fh).items() if not k.startswith("_")}
+        model = cls(CLIPTextConfig(**cfg))
+        sd = None
+        for name in cls.weights_names:
+            path = os.path.join(root, name)
+            if os.path.exists(path):
+                if name.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(path)
+                else:
+                    sd = torch.load(path, map_location="cpu", weights_only=True)
+                break
+        if sd is None:
+            raise FileNotFoundError(f"no {' / '.join(cls.weights_names)} under {root}")
+        own = model.state_dict()
+        missing = [k for k in own if k not in sd or tuple(sd[k].shape) != tuple(own[k].shape)]
+        if missing:
+            raise KeyError(f"{root}: text-model tensors missing or mis-shaped: {missing[:4]}{' ...' if len(missing) > 4 else ''}")
+        model.load_state_dict({k: sd[k].float() for k in own}, strict=True)
+        return model.eval()
+
+    def save_pretrained(self, save_directory, safe_serialization=True, **kwargs):
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        c = self.config
+        cfg = dict(architectures=["CLIPTextModel"], model_type="clip_text_model", vocab_size=c.vocab_size,
+                   hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_hidden_layers=c.num_hidden_layers,
+                   num_attention_heads=c.num_attention_heads, max_position_embeddings=c.max_position_embeddings,
+                   hidden_act=c.hidden_act, layer_norm_eps=c.layer_norm_eps, eos_token_id=c.eos_token_id)
+        with open(os.path.join(save_directory, self.config_name), "w") as fh:
+            json.dump(cfg, fh, indent=2)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, self.weights_names[0]))
+        else:
+            torch.save(sd, os.path.join(save_directory, self.weights_names[1]))
+
     @property
     def dtype(self):
         return BF

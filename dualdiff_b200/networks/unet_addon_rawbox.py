@@ -151,6 +151,12 @@ class BEVControlNetModel(_tree.ModelBase):
         ret.update(kwargs)
         return ret
 
+    def add_uncond_to_emb(self, prompt_embeds, N_cam, encoder_hidden_states_with_cam):
+        """reference :771-789.  Only reachable through `guess_mode` with classifier-free guidance
+        (pipeline_bev_controlnet.py:452-456), which this path does not build; the reference's own body goes through a
+        non-existent `self.controlnet` attribute and cannot run either."""
+        raise NotImplementedError("add_uncond_to_emb belongs to guess_mode, which is not on the dual-branch path")
+
     def prepare(self, cfg, **kwargs):
         self.bbox_embedder.prepare(cfg, **kwargs)
 

@@ -90,6 +90,71 @@ class AutoencoderKLDecoder(nn.Module):
             node.register_parameter(leaf, nn.Parameter(torch.empty(shape)))
         self._packed = None
 
+    # ---- checkpoints (diffusers layout: config.json + diffusion_pytorch_model.safetensors | .bin) -----------------
+    config_name = "config.json"
+    weights_names = ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")
+    # diffusers <= 0.17 AttentionBlock names (the SD-v1.5 VAE files on disk) -> Attention names kept by this mirror
+    _OLD_ATTN = ((".query.", ".to_q."), (".key.", ".to_k."), (".value.", ".to_v."), (".proj_attn.", ".to_out.0."))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """load `<sd-v1-5>/vae` (an `AutoencoderKL` checkpoint) and keep its decode half: `decoder.*` and
+        `post_quant_conv.*`; `encoder.*` / `quant_conv.*` are ignored.  Old-style attention keys are renamed."""
+        import json
+        import os
+        root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        with open(os.path.join(root, cls.config_name)) as fh:
+            cfg = json.load(fh)
+        want = dict(block_out_channels=list(BLOCK_OUT), latent_channels=4, out_channels=3, layers_per_block=2,
+                    norm_num_groups=32, act_fn="silu")
+        for k, v in want.items():
+            have = cfg.get(k, v)
+            have = list(have) if isinstance(have, (list, tuple)) else have
+            if have != v:
+                raise NotImplementedError(f"AutoencoderKLDecoder: {k}={have!r}; only the SD-v1.5 VAE geometry ({v!r}) is built")
+        model = cls(scaling_factor=cfg.get("scaling_factor", SCALING_FACTOR))
+        sd = None
+        for name in cls.weights_names:
+            path = os.path.join(root, name)
+            if os.path.exists(path):
+                if name.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(path)
+                else:
+                    sd = torch.load(path, map_location="cpu", weights_only=True)
+                break
+        if sd is None:
+            raise FileNotFoundError(f"no {' / '.join(cls.weights_names)} under {root}")
+        ren = {}
+        for k, v in sd.items():
+            if ".attentions." in k:
+                for old, new in cls._OLD_ATTN:
+                    k = k.replace(old, new)
+            ren[k] = v
+        own = model.state_dict()
+        missing = [k for k in own if k not in ren or ren[k].numel() != own[k].numel()]
+        if missing:
+            raise KeyError(f"{root}: decoder tensors missing or mis-shaped: {missing[:4]}{' ...' if len(missing) > 4 else ''}")
+        # (old AttentionBlock checkpoints store the projections as [C, C]; 1x1-conv variants as [C, C, 1, 1])
+        model.load_state_dict({k: ren[k].float().reshape(own[k].shape) for k in own}, strict=True)
+        return model.eval()
+
+    def save_pretrained(self, save_directory, safe_serialization=True, **kwargs):
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = dict(_class_name="AutoencoderKL", _diffusers_version="0.17.1", act_fn="silu", block_out_channels=list(BLOCK_OUT),
+                   in_channels=3, out_channels=3, latent_channels=4, layers_per_block=2, norm_num_groups=32,
+                   scaling_factor=self.scaling_factor)
+        with open(os.path.join(save_directory, self.config_name), "w") as fh:
+            json.dump(cfg, fh, indent=2)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, self.weights_names[0]))
+        else:
+            torch.save(sd, os.path.join(save_directory, self.weights_names[1]))
+
     # ---- packing ----------------------------------------------------------------------------------------
     def pack(self, device=None):
         from .. import engine

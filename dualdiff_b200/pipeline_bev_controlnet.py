@@ -68,6 +68,37 @@ class StableDiffusionBEVControlNetPipeline:
         self._denoiser = None
         self._device = None
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, unet=None, controlnet=None, safety_checker=None,
+                        feature_extractor=None, torch_dtype=None, tokenizer=None, **kwargs):
+        """`pipe_cls.from_pretrained(cfg.model.pretrained_model_name_or_path, controlnet=..., unet=..., safety_checker=None,
+        feature_extractor=None, torch_dtype=...)` (misc/test_utils.py:150-156): the VAE decoder, the text encoder, the
+        tokenizer and the scheduler config come from the Stable-Diffusion-v1.5 directory (`vae/`, `text_encoder/`,
+        `tokenizer/`, `scheduler/scheduler_config.json`); `unet` and `controlnet` are the already-loaded DualDiff modules.
+        The scheduler is built as UniPC straight away (the reference replaces the checkpoint's scheduler by
+        `UniPCMultistepScheduler.from_config(pipe.scheduler.config)` on the next line, :162).  `torch_dtype` is accepted and
+        ignored: the kernels compute in bf16 with fp32 accumulation whatever the storage type of the checkpoint."""
+        import json
+        import os
+        from .networks import AutoencoderKLDecoder, CLIPTextModel
+        from .scheduler import UniPCMultistepScheduler
+        if unet is None or controlnet is None:
+            raise ValueError("pass the loaded DualDiff modules: unet=UNet2DConditionModelMultiview, controlnet=[bg, fg]")
+        root = pretrained_model_name_or_path
+        vae = AutoencoderKLDecoder.from_pretrained(root, subfolder="vae")
+        text_encoder = CLIPTextModel.from_pretrained(root, subfolder="text_encoder")
+        if tokenizer is None:
+            from transformers import CLIPTokenizer       # host-side BPE, used as is
+            tokenizer = CLIPTokenizer.from_pretrained(os.path.join(root, "tokenizer"))
+        sched_cfg = {}
+        sched_path = os.path.join(root, "scheduler", "scheduler_config.json")
+        if os.path.exists(sched_path):
+            with open(sched_path) as fh:
+                sched_cfg = json.load(fh)
+        scheduler = UniPCMultistepScheduler.from_config({k: v for k, v in sched_cfg.items() if k != "_class_name"})
+        return cls(vae, text_encoder, unet, controlnet, scheduler, tokenizer, safety_checker=safety_checker,
+                   feature_extractor=feature_extractor)
+
     # ---- diffusers DiffusionPipeline plumbing the callers use (misc/test_utils.py:157-171) -------------------------
     def to(self, device):
         device = torch.device(device)

@@ -116,15 +116,49 @@ class SchedulerOutput:
     prev_sample: torch.Tensor
 
 
+class _SchedulerConfig(dict):
+    """`scheduler.config` with attribute access (diffusers FrozenDict behaviour)"""
+    __getattr__ = dict.__getitem__
+
+
+# the Stable Diffusion v1.5 noise schedule (scheduler/scheduler_config.json of the checkpoint the reference loads,
+# misc/test_utils.py:148-162): the only one the coefficient tables are derived and checked for
+_SD_SCHEDULE = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                    trained_betas=None, prediction_type="epsilon")
+
+
 class _FusedScheduler:
     order = 1
     init_noise_sigma = 1.0
+    _extra_config = {}
 
     def __init__(self, guidance_scale=1.0):
         self.guidance_scale = guidance_scale
         self.timesteps = None
         self._coef = None
         self._state = None
+
+    @property
+    def config(self):
+        return _SchedulerConfig(_class_name=type(self).__name__, **_SD_SCHEDULE, **self._extra_config)
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        """`UniPCMultistepScheduler.from_config(pipe.scheduler.config)` (misc/test_utils.py:162): accepts the config of
+        any scheduler of the SD-v1.5 checkpoint (PNDM / DDIM / UniPC ...) and checks that it describes the schedule the
+        fused kernel's tables are built for; keys of other scheduler classes are ignored as diffusers does."""
+        cfg = dict(config) if not isinstance(config, dict) else config
+        cfg = {**cfg, **kwargs}
+        for k, want in _SD_SCHEDULE.items():
+            have = cfg.get(k, want)
+            same = (abs(have - want) < 1e-12) if isinstance(want, float) else (have == want)
+            if not same:
+                raise NotImplementedError(f"{cls.__name__}: {k}={have!r} is not the SD-v1.5 schedule ({want!r}) this "
+                                          "scheduler's coefficient tables are built for")
+        for k, want in cls._extra_config.items():
+            if k in cfg and cfg.get("_class_name", cls.__name__) == cls.__name__ and cfg[k] != want:
+                raise NotImplementedError(f"{cls.__name__}: {k}={cfg[k]!r} (built: {want!r})")
+        return cls()
 
     def _tables(self, n):
         raise NotImplementedError
@@ -172,12 +206,16 @@ class _FusedScheduler:
 
 
 class UniPCMultistepScheduler(_FusedScheduler):
+    _extra_config = dict(solver_order=2, solver_type="bh2", predict_x0=True, lower_order_final=True, thresholding=False)
+
     def _tables(self, n):
         ts = unipc_timesteps(n)
         return ts, unipc_coefficients(ts, self.guidance_scale)
 
 
 class DDIMScheduler(_FusedScheduler):
+    _extra_config = dict(steps_offset=1, set_alpha_to_one=False, clip_sample=False)
+
     def _tables(self, n):
         ts = ddim_timesteps(n)
         return ts, ddim_coefficients(ts, self.guidance_scale)
