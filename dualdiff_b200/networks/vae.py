@@ -2,7 +2,8 @@
 
 Reference call site: pipeline/pipeline_bev_controlnet.py:101-113 (`decode_latents`: `latents / 0.18215`,
 `self.vae.decode(latents).sample`, `(image / 2 + 0.5).clamp(0, 1)`); the network is diffusers' `AutoencoderKL`
-(SD-v1.5 VAE), which is not vendored in the reference tree -- oracle/vae_oracle.py restates it (parity unpinned).
+(SD-v1.5 VAE), which is not vendored in the reference tree -- oracle/vae_oracle.py restates it (pinned to an
+independent LDM decoder implementation, see its header).
 This module keeps the decode half: same state-dict keys (`post_quant_conv.*`, `decoder.*`, attention as
 `to_q / to_k / to_v / to_out.0 / group_norm`), `decode(z).sample`, `decode_latents(latents)`.
 

@@ -4,8 +4,12 @@ The reference calls diffusers' `AutoencoderKL.decode` (pipeline/pipeline_bev_con
 `latents = 1 / 0.18215 * latents; image = vae.decode(latents).sample; image = (image / 2 + 0.5).clamp(0, 1)`).  diffusers
 (0.17.1, MagicDrive fork) is not vendored under /root/reference, so this restates the public library code
 (models/autoencoder_kl.py, models/vae.py:Decoder, unet_2d_blocks.py:UNetMidBlock2D / UpDecoderBlock2D, resnet.py,
-attention_processor.py:Attention) for the SD-v1.5 VAE configuration: **parity unpinned** against the real library; the
-structure is pinned by the parameter count of the SD VAE decoder + post_quant_conv (49,490,199).
+attention_processor.py:Attention) for the SD-v1.5 VAE configuration.  Pinning: diffusers itself cannot be run here, but
+AutoencoderKL's decoder is a port of the CompVis/LDM decoder, and an INDEPENDENT implementation of that architecture is
+installed in this image (torchtitan's flux autoencoder `Decoder`): with the SD geometry (ch 128, ch_mult (1,2,4,4), 3 resnets
+per level, z_channels 4) and the same weights through the diffusers<->LDM key map it reproduces this oracle to 2e-7
+(oracle/make_golden_vae.py -> tests/golden/vae_small.pt; tests/test_vae.py, live and against the golden).  `post_quant_conv`
+and the 0.18215 scaling are diffusers-specific and restated; the parameter count (49,490,179 + 20) is a second structure pin.
 State-dict keys are the diffusers ones (post_quant_conv.*, decoder.conv_in.*, decoder.mid_block.*, decoder.up_blocks.*,
 decoder.conv_norm_out.*, decoder.conv_out.*; attention as to_q / to_k / to_v / to_out.0 / group_norm)."""
 from typing import Dict
