@@ -93,7 +93,11 @@ class DualDiffDenoiser:
         # another prompt / scene), the new values are copied into the buffers it was captured on and the graph is kept
         sig = (self.cfg, B, n_cam, c, H, W, tuple(p.lk for p in preps), str(dev))
         new_in = _graph_inputs(preps, unet_text_kv, kv_map)
-        if self._graph is not None and getattr(self, "_sig", None) == sig and \
+        # the graph also reads the packed weights: a re-pack (weights reloaded) must re-capture.  The references held here
+        # keep the buffers a kept graph points at alive.
+        packs = [m._packed for m in [self.unet] + self.nets]
+        same_weights = len(packs) == len(getattr(self, "_packs", [])) and all(a is b for a, b in zip(packs, self._packs))
+        if self._graph is not None and same_weights and getattr(self, "_sig", None) == sig and \
                 [(t.shape, t.dtype) for t in new_in] == [(t.shape, t.dtype) for t in self._static_in]:
             for dst, src in zip(self._static_in, new_in):
                 dst.copy_(src)
@@ -102,7 +106,7 @@ class DualDiffDenoiser:
                 t.zero_()
         else:
             self.preps, self.unet_text_kv, self.kv_map = preps, unet_text_kv, kv_map
-            self._static_in, self._sig = new_in, sig
+            self._static_in, self._sig, self._packs = new_in, sig, packs
             self.latents = lat.clone()
             self.last = torch.zeros_like(self.latents)
             self.m0 = torch.zeros_like(self.latents)
