@@ -68,6 +68,65 @@ int nchw_to_padded_run(const dd_to_padded_args* a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// 3x3 stride-1 pad-1 patch rows of a few-channel NCHW image (conv_in on the 4-channel latents):
+// out[(img, y, x), tap*C + c] = src[img, c, y+kh-1, x+kw-1] (zero outside the image), columns [9C, cp) zero.
+// One thread per (row, 8-column group).  With C = 4 a row is 36 + 4 columns: the convolution becomes ONE plain GEMM with
+// K = 40 on the TMA epilogue instead of nine 8-channel taps through the conv path, whose register epilogue is fully exposed
+// when the K loop is this short (conv_in: 177 us measured against a ~40 us HBM floor).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_patches_kernel(const T* __restrict__ src, bf16* __restrict__ out, long long so, long long sv,
+                                    long long sc, long long sh, int n_outer, int n_view, int C, int H, int W, int Cp) {
+  const long long rows = (long long)n_outer * n_view * H * W;
+  const int vec = Cp >> 3;
+  const long long total = rows * vec;
+  const int K9 = 9 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec;
+    const int v = (int)(i - r * vec);
+    const int img = (int)(r / (H * W));
+    const int rem = (int)(r - (long long)img * (H * W));
+    const int y = rem / W, x = rem - y * W;
+    const int outer = img / n_view, view = img - outer * n_view;
+    const T* base = src + outer * so + view * sv;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = v * 8 + e;
+      float val = 0.f;
+      if (col < K9) {
+        const int tap = col / C, c = col - tap * C;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = (float)base[c * sc + (long long)yy * sh + xx];
+      }
+      f[e] = val;
+    }
+    *reinterpret_cast<uint4*>(out + r * Cp + v * 8) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
+int nchw_patches_run(const dd_to_padded_args* a, cudaStream_t stream) {
+  DD_CHECK(a && a->c > 0 && a->cp % 8 == 0 && a->cp >= 9 * a->c, -1,
+           "dd_nchw_patches: cp must be a multiple of 8 and >= 9*c");
+  DD_CHECK((long long)a->h * a->w < (1LL << 31), -1, "dd_nchw_patches: image too large");
+  const long long total = (long long)a->n_outer * a->n_view * a->h * a->w * (a->cp >> 3);
+  const int grid = grid_for(total, 256);
+  if (a->src_f32)
+    nchw_patches_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(a->src), reinterpret_cast<bf16*>(a->out),
+                                                         a->stride_outer, a->stride_view, a->stride_c, a->stride_h,
+                                                         a->n_outer, a->n_view, a->c, a->h, a->w, a->cp);
+  else
+    nchw_patches_kernel<bf16><<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(a->src), reinterpret_cast<bf16*>(a->out),
+                                                        a->stride_outer, a->stride_view, a->stride_c, a->stride_h,
+                                                        a->n_outer, a->n_view, a->c, a->h, a->w, a->cp);
+  DD_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 im2col: out[(img, ho, wo), tap*C + c] = x[(img, 2ho+kh-1, 2wo+kw-1), c]
 // ---------------------------------------------------------------------------------------------------
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ out, int n_img,
@@ -340,6 +399,9 @@ using namespace dd;
 extern "C" {
 int dd_nchw_to_padded(const dd_to_padded_args* args, void* stream) {
   return nchw_to_padded_run(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int dd_nchw_patches(const dd_to_padded_args* args, void* stream) {
+  return nchw_patches_run(args, reinterpret_cast<cudaStream_t>(stream));
 }
 int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream) {
   return im2col_s2_run(x, x_ld, out, n_img, h, w, c, reinterpret_cast<cudaStream_t>(stream));

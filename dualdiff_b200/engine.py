@@ -22,11 +22,16 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .packing import pack_conv1x1, pack_conv3x3, pack_geglu, pack_linear
+from .packing import pack_conv1x1, pack_conv3x3, pack_conv3x3_patch, pack_geglu, pack_linear
 
 HEADS = 8
 NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  # configs/dataset/Nuscenes.yaml:27-33
 BF = torch.bfloat16
+
+
+# EXPERIMENTAL A/B switch (default off: not yet measured / parity-checked on a GPU): conv_in as ONE K = 40 GEMM over an
+# explicit 3x3 patch matrix of the 4-channel latents instead of nine 8-channel taps through the conv path
+_CONV_IN_PATCH = bool(int(__import__("os").environ.get("DD_CONV_IN_PATCH", "0")))
 
 
 def _dp(d):
@@ -129,6 +134,8 @@ class Packer:
     def encoder(self, multiview, temb_list):
         """conv_in, time embedding, 4 down blocks, mid block — shared by the UNet and the ControlNet branches"""
         self.conv3("conv_in", pad_cin_to=8)
+        if _CONV_IN_PATCH:   # experimental K = 40 form, packed only when the switch is on
+            self.put("conv_in.wp", pack_conv3x3_patch(self.sd["conv_in.weight"].detach().float()))
         self.lin32("time_embedding.linear_1"); self.lin32("time_embedding.linear_2")
         for i in range(4):
             for j in range(2):
@@ -361,6 +368,11 @@ def upsample(P, p, x: Act, hw2) -> Act:
 def conv_in(P, latents, n_outer, n_view, H, W, res1=None) -> Act:
     """latents: fp32/bf16 NCHW storage of n_view images, logically repeated n_outer times (CFG halves)"""
     assert latents.is_contiguous()
+    if _CONV_IN_PATCH and "conv_in.wp" in P:
+        cols = ops.nchw_patches(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=P["conv_in.wp"].shape[1],
+                                stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
+                                stride_view=4 * H * W, stride_c=H * W, stride_h=W)
+        return Act(ops.gemm(cols, P["conv_in.wp"], bias=P["conv_in.b"], res1=res1), n_outer * n_view, H, W)
     pad = ops.nchw_to_padded(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=8,
                              stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
                              stride_view=4 * H * W, stride_c=H * W, stride_h=W)

@@ -282,6 +282,22 @@ def nchw_to_padded(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_vi
     return out
 
 
+def nchw_patches(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_view, stride_c, stride_h, out=None):
+    """EXPERIMENTAL: 3x3 stride-1 pad-1 patch rows [n*h*w, cp] (tap-major, channel-minor, zero tail) of an NCHW image"""
+    assert src.is_cuda and src.dtype in (torch.float32, torch.bfloat16)
+    n = n_outer * n_view
+    if out is None:
+        out = torch.empty((n * h * w, cp), device=src.device, dtype=torch.bfloat16)
+    a = ToPaddedArgs()
+    a.src = _ptr(src); a.out = _ptr(out)
+    a.stride_outer = stride_outer; a.stride_view = stride_view; a.stride_c = stride_c; a.stride_h = stride_h
+    a.n_outer = n_outer; a.n_view = n_view; a.c = c; a.h = h; a.w = w; a.cp = cp
+    a.src_f32 = 1 if src.dtype == torch.float32 else 0
+    with _Rec("layout", 0.0, 4.0 * n * c * h * w + 2.0 * out.numel()):
+        check(_lib.lib().dd_nchw_patches(C.byref(a), _stream()), "dd_nchw_patches")
+    return out
+
+
 def im2col_s2(x, *, n_img, hw, out=None):
     _req(x, torch.bfloat16, "x")
     H, W = hw

@@ -9,6 +9,18 @@ def pack_conv3x3(w):
     return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous().to(torch.bfloat16)
 
 
+def pack_conv3x3_patch(w):
+    """OIHW [Cout, Cin, 3, 3] -> [Cout, cp] bf16 for the explicit patch-matrix form (dd_nchw_patches): columns tap-major,
+    channel-minor like pack_conv3x3, zero-padded to the next multiple of 8 (Cin = 4: 36 -> 40)."""
+    co, ci, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    k = 9 * ci
+    cp = (k + 7) // 8 * 8
+    out = w.new_zeros((co, cp))
+    out[:, :k] = w.permute(0, 2, 3, 1).reshape(co, k)
+    return out.contiguous().to(torch.bfloat16)
+
+
 def pack_conv1x1(w):
     co, ci = w.shape[:2]
     return w.reshape(co, ci).contiguous().to(torch.bfloat16)

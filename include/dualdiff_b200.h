@@ -186,6 +186,10 @@ typedef struct dd_to_padded_args {
   int src_f32;
 } dd_to_padded_args;
 DD_API int dd_nchw_to_padded(const dd_to_padded_args* args, void* stream);
+/* EXPERIMENTAL (not on the default path yet): 3x3 stride-1 pad-1 patch rows of a few-channel NCHW
+ * image, same addressing arguments as dd_nchw_to_padded: out[(img, y, x), tap*c + ch] = src[img, ch, y+kh-1, x+kw-1] (zero
+ * outside), row length cp >= 9*c (multiple of 8, tail zero).  Turns conv_in on the 4-channel latents into one K = 40 GEMM. */
+DD_API int dd_nchw_patches(const dd_to_padded_args* args, void* stream);
 /* 3x3 stride-2 pad-1 patches of a compact activation -> [n_img*Ho*Wo, 9*C] (diffusers Downsample2D.conv and the
  * stride-2 convs of ControlNetConditioningEmbedding) */
 DD_API int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
