@@ -29,7 +29,7 @@ NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  
 BF = torch.bfloat16
 
 
-# EXPERIMENTAL A/B switch (default off: not yet measured / parity-checked on a GPU): conv_in as ONE K = 40 GEMM over an
+# EXPERIMENTAL A/B switch (default off: op-level parity checked on a B200, not yet measured): conv_in as ONE K = 40 GEMM over an
 # explicit 3x3 patch matrix of the 4-channel latents instead of nine 8-channel taps through the conv path
 _CONV_IN_PATCH = bool(int(__import__("os").environ.get("DD_CONV_IN_PATCH", "0")))
 

@@ -186,7 +186,7 @@ typedef struct dd_to_padded_args {
   int src_f32;
 } dd_to_padded_args;
 DD_API int dd_nchw_to_padded(const dd_to_padded_args* args, void* stream);
-/* EXPERIMENTAL (not on the default path yet): 3x3 stride-1 pad-1 patch rows of a few-channel NCHW
+/* EXPERIMENTAL (parity-checked, not on the default path yet): 3x3 stride-1 pad-1 patch rows of a few-channel NCHW
  * image, same addressing arguments as dd_nchw_to_padded: out[(img, y, x), tap*c + ch] = src[img, ch, y+kh-1, x+kw-1] (zero
  * outside), row length cp >= 9*c (multiple of 8, tail zero).  Turns conv_in on the 4-channel latents into one K = 40 GEMM. */
 DD_API int dd_nchw_patches(const dd_to_padded_args* args, void* stream);
