@@ -26,6 +26,62 @@ def reduce_max_ms(ms: float, device=None) -> float:
     return float(t[0])
 
 
+def slice_scenes(obj, scenes: range, total_scenes: int, n_cam: int = 6):
+    """this rank's scenes of a batched pipeline input: tensors whose leading dimension is `total_scenes` (or
+    `total_scenes * n_cam`, the '(b n) ...' layout of the ORS tensor) are cut, lists of per-scene prompts are cut, dicts /
+    lists / tuples are walked, everything else is passed through"""
+    if torch.is_tensor(obj):
+        if obj.dim() > 0 and obj.shape[0] == total_scenes:
+            return obj[scenes.start:scenes.stop]
+        if obj.dim() > 0 and obj.shape[0] == total_scenes * n_cam:
+            return obj[scenes.start * n_cam:scenes.stop * n_cam]
+        return obj
+    if isinstance(obj, dict):
+        return {k: slice_scenes(v, scenes, total_scenes, n_cam) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        if len(obj) == total_scenes and all(isinstance(x, (str, torch.Generator)) for x in obj):
+            return type(obj)(obj[scenes.start:scenes.stop])
+        return type(obj)(slice_scenes(v, scenes, total_scenes, n_cam) for v in obj)
+    return obj
+
+
+def run_scene_sharded(pipe, *, prompt, image, camera_param, bev_controlnet_kwargs, gather: bool = True, n_cam: int = 6,
+                      **call_kwargs):
+    """BASELINE config 3 at the pipeline level: every rank runs `pipe(...)` on its contiguous share of the scenes
+    (weights replicated, no data-path collective); with `gather`, rank 0 receives the per-scene results of all ranks in
+    scene order (one gather of the finished outputs, the only communication) and the other ranks get None.
+    Mirrors how the reference shards generation (`accelerator.prepare(val_dataloader)`, val_set_gen.py:121)."""
+    import torch.distributed as dist
+    ready = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if ready else (0, 1)
+    total = len(prompt)
+    mine = shard_scenes(total, rank, world)
+    local = None
+    if len(mine) > 0:
+        out = pipe(prompt=slice_scenes(list(prompt), mine, total, n_cam), image=slice_scenes(image, mine, total, n_cam),
+                   camera_param=slice_scenes(camera_param, mine, total, n_cam),
+                   bev_controlnet_kwargs=slice_scenes(bev_controlnet_kwargs, mine, total, n_cam),
+                   **slice_scenes(call_kwargs, mine, total, n_cam))
+        local = out.images if hasattr(out, "images") else out[0]
+        if torch.is_tensor(local):
+            local = local.cpu()
+    if not gather or world == 1:
+        return local
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(local, parts, dst=0)
+    if rank != 0:
+        return None
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        return None
+    if torch.is_tensor(parts[0]):
+        return torch.cat(parts)
+    if hasattr(parts[0], "shape"):                     # numpy images
+        import numpy as np
+        return np.concatenate(parts)
+    return [scene for part in parts for scene in part]  # PIL: [scene][view]
+
+
 class ViewShard:
     """Camera-view sharding inside a scene (BASELINE config 4).
 

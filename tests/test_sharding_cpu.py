@@ -56,6 +56,52 @@ def test_shard_scenes_properties():
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
 
 
+class _StubPipe:
+    """records what it was called with and returns one 'image' per scene that encodes the scene's inputs"""
+
+    def __call__(self, prompt, image, camera_param, bev_controlnet_kwargs, generator=None, **kw):
+        from types import SimpleNamespace
+        b = len(prompt)
+        assert camera_param.shape[0] == b and image[0].shape[0] == b and image[1].shape[0] == 6 * b
+        assert bev_controlnet_kwargs["bboxes_3d_data"][0]["bboxes"].shape[0] == b and len(generator) == b
+        assert kw == {"height": 64, "num_inference_steps": 3}
+        ids = torch.tensor([float(p.split()[-1]) for p in prompt])
+        assert torch.equal(camera_param[:, 0, 0, 0], ids) and torch.equal(image[1][::6, 0, 0, 0], ids)
+        return SimpleNamespace(images=ids[:, None].repeat(1, 6))
+
+
+def _pipe_worker(rank, world, port, total, q):
+    from dualdiff_b200.sharding import run_scene_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ids = torch.arange(total, dtype=torch.float32)
+    out = run_scene_sharded(
+        _StubPipe(), prompt=[f"scene {i}" for i in range(total)],
+        image=[ids.view(-1, 1, 1, 1).expand(total, 3, 2, 12), ids.repeat_interleave(6).view(-1, 1, 1, 1).expand(6 * total, 320, 1, 2)],
+        camera_param=ids.view(-1, 1, 1, 1).expand(total, 6, 3, 7),
+        bev_controlnet_kwargs={"bboxes_3d_data": [{"bboxes": torch.zeros(total, 6, 2, 8, 3)}, {"bboxes": torch.zeros(total, 1, 2, 8, 3)}],
+                               "use_aug_text": False},
+        generator=[torch.Generator().manual_seed(i) for i in range(total)], height=64, num_inference_steps=3)
+    q.put((rank, None if out is None else out.tolist()))
+    dist.destroy_process_group()
+
+
+def test_pipeline_scene_sharding_two_ranks_gloo():
+    """config 3 at the pipeline level: each rank runs the pipeline on its scenes, rank 0 gathers the results in scene order"""
+    world, total = 2, 5
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[1] is None and res[0] == [[float(i)] * 6 for i in range(total)]
+
+
 # ---------------------------------------------------------------------------------------------------
 # camera-view sharding: halo exchange + kv_map reproduce the unsharded cross-view attention (blocks.py:190-222)
 # ---------------------------------------------------------------------------------------------------
