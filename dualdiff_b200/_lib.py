@@ -120,7 +120,7 @@ EXPORTS = [
     "dd_nchw_to_padded", "dd_im2col_s2", "dd_upsample_pad", "dd_pad_rows", "dd_linear_f32",
     "dd_timestep_embedding", "dd_fourier_embed", "dd_box_features", "dd_silu_to_bf16", "dd_add_bf16",
     "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step", "dd_softmax_rows",
-    "dd_clip_embed", "dd_seq_attention", "dd_quick_gelu", "dd_nchw_patches",
+    "dd_clip_embed", "dd_seq_attention", "dd_quick_gelu", "dd_nchw_patches", "dd_im2col_s1",
 ]
 
 

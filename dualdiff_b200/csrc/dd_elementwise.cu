@@ -151,6 +151,31 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ld, bf16*
   }
 }
 
+// 3x3 stride-1 pad-1 im2col of a compact activation (EXPERIMENTAL): same column order as the stride-2 version,
+// so the tap-major conv weights serve unchanged.  For the 4x7-pixel level the zero-haloed implicit-GEMM layout spends 30 % of
+// its UMMA rows on halo pixels; an explicit patch matrix (L2-resident at that size) has none.
+__global__ void im2col_s1_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ out, int n_img, int H, int W,
+                                 int C) {
+  const int vec = C >> 3;
+  const long long total = (long long)n_img * H * W * 9 * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    long long t = i / vec;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int xo = (int)(t % W);
+    t /= W;
+    const int yo = (int)(t % H);
+    const int img = (int)(t / H);
+    const int y = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && xx >= 0 && xx < W)
+      val = *reinterpret_cast<const uint4*>(x + (((long long)img * H + y) * W + xx) * ld + v * 8);
+    *reinterpret_cast<uint4*>(out + (((long long)img * H + yo) * W + xo) * (9LL * C) + tap * C + v * 8) = val;
+  }
+}
+
 // nearest resize -> padded layout
 __global__ void upsample_pad_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ out, int n_img,
                                     int H, int W, int C, int H2, int W2) {
@@ -182,6 +207,17 @@ int im2col_s2_run(const void* x, long long ld, void* out, int n_img, int h, int 
   const long long total = (long long)n_img * ho * wo * 9 * (c >> 3);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld,
                                                              reinterpret_cast<bf16*>(out), n_img, h, w, c, ho, wo);
+  DD_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int im2col_s1_run(const void* x, long long ld, void* out, int n_img, int h, int w, int c, cudaStream_t stream) {
+  DD_CHECK(x != nullptr && out != nullptr && n_img > 0 && h > 0 && w > 0, -1, "dd_im2col_s1: bad arguments");
+  DD_CHECK(c > 0 && c % 8 == 0 && ld % 8 == 0, -1, "dd_im2col_s1: C and the row pitch must be multiples of 8");
+  const long long total = (long long)n_img * h * w * 9 * (c >> 3);
+  im2col_s1_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld,
+                                                             reinterpret_cast<bf16*>(out), n_img, h, w, c);
   DD_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -405,6 +441,9 @@ int dd_nchw_patches(const dd_to_padded_args* args, void* stream) {
 }
 int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream) {
   return im2col_s2_run(x, x_ld, out, n_img, h, w, c, reinterpret_cast<cudaStream_t>(stream));
+}
+int dd_im2col_s1(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream) {
+  return im2col_s1_run(x, x_ld, out, n_img, h, w, c, reinterpret_cast<cudaStream_t>(stream));
 }
 int dd_upsample_pad(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, int h2, int w2,
                     void* stream) {

@@ -34,6 +34,12 @@ BF = torch.bfloat16
 _CONV_IN_PATCH = bool(int(__import__("os").environ.get("DD_CONV_IN_PATCH", "0")))
 
 
+# EXPERIMENTAL A/B switch (default 0 = off, not yet run on a GPU): 3x3 convolutions of the ResNet blocks on feature maps of at
+# most this many pixels go through an explicit stride-1 patch matrix + plain GEMM instead of the zero-haloed implicit GEMM
+# (DD_SMALL_CONV_IM2COL=28 covers the 4x7 level, where 30 % of the implicit-GEMM rows are halo)
+_SMALL_CONV_IM2COL = int(__import__("os").environ.get("DD_SMALL_CONV_IM2COL", "0"))
+
+
 def _dp(d):
     """Q/K head stride: head_dim 40 is zero-padded to 48 so the UMMA K extent is a multiple of 16"""
     return 48 if d == 40 else d
@@ -258,19 +264,27 @@ def time_embedding(P, t: torch.Tensor):
 
 def resnet(P, p, x: Act, ctx: StepCtx, x2: Optional[torch.Tensor] = None) -> Act:
     n, hw = x.n, x.hw
-    g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True,
-                       padded_out=True)
     off, cout = P["temb_offsets"][p]
-    h = ops.gemm(g1, P[p + ".conv1.w"], bias=P[p + ".conv1.b"], taps=9, conv_hw=hw, n_img=n,
-                 rowvec=ctx.temb[:, off:off + cout], rows_per_img=ctx.temb_rows_per_img_factor * hw[0] * hw[1])
-    g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True, padded_out=True)
+    rpi = ctx.temb_rows_per_img_factor * hw[0] * hw[1]
+    if hw[0] * hw[1] <= _SMALL_CONV_IM2COL:   # experimental: explicit patch matrix, same tap-major weights (see the switch)
+        g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True)
+        h = ops.gemm(ops.im2col_s1(g1, n_img=n, hw=hw), P[p + ".conv1.w"], bias=P[p + ".conv1.b"],
+                     rowvec=ctx.temb[:, off:off + cout], rows_per_img=rpi)
+        g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True)
+        conv2 = lambda sc: ops.gemm(ops.im2col_s1(g2, n_img=n, hw=hw), P[p + ".conv2.w"], bias=P[p + ".conv2.b"], res1=sc)
+    else:
+        g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True,
+                           padded_out=True)
+        h = ops.gemm(g1, P[p + ".conv1.w"], bias=P[p + ".conv1.b"], taps=9, conv_hw=hw, n_img=n,
+                     rowvec=ctx.temb[:, off:off + cout], rows_per_img=rpi)
+        g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True, padded_out=True)
+        conv2 = lambda sc: ops.gemm(g2, P[p + ".conv2.w"], bias=P[p + ".conv2.b"], taps=9, conv_hw=hw, n_img=n, res1=sc)
     if (p + ".conv_shortcut.w") in P:
         sc = ops.gemm(x.rows, P[p + ".conv_shortcut.w"], bias=P[p + ".conv_shortcut.b"], a2=x2)
     else:
         assert x2 is None
         sc = x.rows
-    out = ops.gemm(g2, P[p + ".conv2.w"], bias=P[p + ".conv2.b"], taps=9, conv_hw=hw, n_img=n, res1=sc)
-    return Act(out, n, x.H, x.W)
+    return Act(conv2(sc), n, x.H, x.W)
 
 
 def text_kv(P, p_attn2, enc_rows):

@@ -310,6 +310,19 @@ def im2col_s2(x, *, n_img, hw, out=None):
     return out, (ho, wo)
 
 
+def im2col_s1(x, *, n_img, hw, out=None):
+    """EXPERIMENTAL: 3x3 stride-1 pad-1 patch rows [n_img*H*W, 9*C] of a compact activation (column order of im2col_s2)"""
+    _req(x, torch.bfloat16, "x")
+    H, W = hw
+    c = x.shape[1]
+    assert x.shape[0] == n_img * H * W
+    if out is None:
+        out = torch.empty((n_img * H * W, 9 * c), device=x.device, dtype=torch.bfloat16)
+    with _Rec("layout", 0.0, 2.0 * (n_img * H * W * c + out.numel())):
+        check(_lib.lib().dd_im2col_s1(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s1")
+    return out
+
+
 def upsample_pad(x, *, n_img, hw, hw2, out=None):
     _req(x, torch.bfloat16, "x")
     H, W = hw

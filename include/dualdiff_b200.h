@@ -193,6 +193,9 @@ DD_API int dd_nchw_patches(const dd_to_padded_args* args, void* stream);
 /* 3x3 stride-2 pad-1 patches of a compact activation -> [n_img*Ho*Wo, 9*C] (diffusers Downsample2D.conv and the
  * stride-2 convs of ControlNetConditioningEmbedding) */
 DD_API int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
+/* EXPERIMENTAL (not on the default path): the stride-1 form, [n_img*H*W, 9*C], same column order --
+ * an explicit patch matrix for the smallest feature maps, where the zero-haloed layout wastes 30 % of the UMMA rows */
+DD_API int dd_im2col_s1(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
 /* nearest-neighbour resize to (h2, w2) written in the padded layout (diffusers Upsample2D with explicit size,
  * networks/unet_2d_condition_multiview.py:363-374,500-501): src = floor(dst * in / out) */
 DD_API int dd_upsample_pad(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, int h2, int w2,
