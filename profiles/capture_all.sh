@@ -8,4 +8,11 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 
 GN=2560 GRES=0 ncu --set full --clock-control none -k regex:gemm_tcgen05 -s 2 -c 1 -o gpurun_out/r01_gemm_n2560_k320 python profiles/gemm_one.py > /dev/null 2>&1
 N_IMG=96 ncu --set full --clock-control none --import-source on -k regex:attn_v2 -s 2 -c 1 -o gpurun_out/r01_attn_l0 python profiles/attn_one.py > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:gn_ -s 20 -c 2 -o gpurun_out/r01_gn_c320 python profiles/gn_one.py > /dev/null 2>&1
+python profiles/pipeline_e2e.py 8 25 > gpurun_out/r01_pipeline_e2e.json 2>gpurun_out/pipe.err
+EXTRAS=1 compute-sanitizer --tool memcheck --print-limit 30 --log-file gpurun_out/memcheck_full.log python profiles/memcheck_step.py 2 28 50 2>gpurun_out/memcheck_full.err
+python profiles/gap_table.py gpurun_out/r01_step_shapes.txt > gpurun_out/r01_gap_table.txt
+# experimental variants: parity, then A/B against the default build on the same box
+DD_EXPERIMENTAL=1 python -m pytest tests/test_experimental.py -m gpu -q > gpurun_out/experimental_tests.log 2>&1
+DD_CONV_IN_PATCH=1 python bench.py --steps 10 --warmup 3 > gpurun_out/ab_conv_in_patch.json 2>/dev/null
+DD_SMALL_CONV_IM2COL=28 python bench.py --steps 10 --warmup 3 > gpurun_out/ab_small_conv_im2col.json 2>/dev/null
 ls -la gpurun_out | tail -20
