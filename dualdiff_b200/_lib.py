@@ -7,8 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# DUALDIFF_LIB: A/B measurements against another build of the same C ABI (never a fallback: the file must exist)
-LIB_PATH = os.environ.get("DUALDIFF_LIB") or os.path.join(_HERE, "libdualdiff_sm100.so")
+LIB_PATH = os.path.join(_HERE, "libdualdiff_sm100.so")
 
 
 class DDError(RuntimeError):
@@ -54,7 +53,7 @@ class AttentionArgs(C.Structure):
         ("q_col0", _i), ("k_col0", _i), ("v_col0", _i),
         ("q_head_stride", _i), ("k_head_stride", _i), ("v_head_stride", _i),
         ("n_img", _i), ("n_kv_img", _i), ("heads", _i), ("head_dim", _i), ("lq", _i), ("lk", _i), ("n_src", _i),
-        ("scale", _f),
+        ("scale", _f), ("variant", _i),
     ]
 
 
@@ -120,7 +119,7 @@ EXPORTS = [
     "dd_nchw_to_padded", "dd_im2col_s2", "dd_upsample_pad", "dd_pad_rows", "dd_linear_f32",
     "dd_timestep_embedding", "dd_fourier_embed", "dd_box_features", "dd_silu_to_bf16", "dd_add_bf16",
     "dd_nchw_to_rows", "dd_rows_to_nchw", "dd_cfg_sched_step", "dd_softmax_rows",
-    "dd_clip_embed", "dd_seq_attention", "dd_quick_gelu", "dd_nchw_patches", "dd_im2col_s1",
+    "dd_clip_embed", "dd_seq_attention", "dd_quick_gelu", "dd_nchw_patches",
 ]
 
 

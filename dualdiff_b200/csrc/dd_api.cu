@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "dd_api_internal.h"
 #include "dd_common.cuh"
@@ -20,14 +22,31 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
-  static int sms = 0;
+  static std::atomic<int> sms_of[64];   // per device, 0 = not queried yet (benign race: every thread stores the same value)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int sms = sms_of[dev].load(std::memory_order_relaxed);
   if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
+    sms_of[dev].store(sms, std::memory_order_relaxed);
   }
   return sms;
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  struct Done { const void* func; int dev; int bytes; };
+  static std::mutex mu;
+  static std::vector<Done> done;
+  int dev = 0;
+  DD_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Done& d : done)
+    if (d.func == func && d.dev == dev && d.bytes >= bytes) return 0;
+  DD_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.push_back({func, dev, bytes});
+  return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

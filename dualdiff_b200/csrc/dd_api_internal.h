@@ -16,4 +16,7 @@ int ors_project_run(const float* origins, const float* dirs, const unsigned char
                     cudaStream_t stream);
 int seq_attention_run(const dd_seq_attention_args* a, cudaStream_t stream);
 void count_launch(int n = 1);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device); thread-safe (function attributes are
+// per device context, and the C entry points may be called from several host threads)
+int ensure_dyn_smem(const void* func, int bytes);
 }  // namespace dd

@@ -151,31 +151,6 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ld, bf16*
   }
 }
 
-// 3x3 stride-1 pad-1 im2col of a compact activation (EXPERIMENTAL): same column order as the stride-2 version,
-// so the tap-major conv weights serve unchanged.  For the 4x7-pixel level the zero-haloed implicit-GEMM layout spends 30 % of
-// its UMMA rows on halo pixels; an explicit patch matrix (L2-resident at that size) has none.
-__global__ void im2col_s1_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ out, int n_img, int H, int W,
-                                 int C) {
-  const int vec = C >> 3;
-  const long long total = (long long)n_img * H * W * 9 * vec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    long long t = i / vec;
-    const int tap = (int)(t % 9);
-    t /= 9;
-    const int xo = (int)(t % W);
-    t /= W;
-    const int yo = (int)(t % H);
-    const int img = (int)(t / H);
-    const int y = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H && xx >= 0 && xx < W)
-      val = *reinterpret_cast<const uint4*>(x + (((long long)img * H + y) * W + xx) * ld + v * 8);
-    *reinterpret_cast<uint4*>(out + (((long long)img * H + yo) * W + xo) * (9LL * C) + tap * C + v * 8) = val;
-  }
-}
-
 // nearest resize -> padded layout
 __global__ void upsample_pad_kernel(const bf16* __restrict__ x, long long ld, bf16* __restrict__ out, int n_img,
                                     int H, int W, int C, int H2, int W2) {
@@ -207,17 +182,6 @@ int im2col_s2_run(const void* x, long long ld, void* out, int n_img, int h, int 
   const long long total = (long long)n_img * ho * wo * 9 * (c >> 3);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld,
                                                              reinterpret_cast<bf16*>(out), n_img, h, w, c, ho, wo);
-  DD_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
-int im2col_s1_run(const void* x, long long ld, void* out, int n_img, int h, int w, int c, cudaStream_t stream) {
-  DD_CHECK(x != nullptr && out != nullptr && n_img > 0 && h > 0 && w > 0, -1, "dd_im2col_s1: bad arguments");
-  DD_CHECK(c > 0 && c % 8 == 0 && ld % 8 == 0, -1, "dd_im2col_s1: C and the row pitch must be multiples of 8");
-  const long long total = (long long)n_img * h * w * 9 * (c >> 3);
-  im2col_s1_kernel<<<grid_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ld,
-                                                             reinterpret_cast<bf16*>(out), n_img, h, w, c);
   DD_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -305,7 +269,7 @@ __global__ void box_features_kernel(const float* __restrict__ boxes, const long 
                                     const unsigned char* __restrict__ masks, const float* __restrict__ class_tokens,
                                     const float* __restrict__ null_pos, const float* __restrict__ null_cls,
                                     float* __restrict__ pos_out, long long pos_ld, float* __restrict__ cls_out,
-                                    long long cls_ld, int n_pts, int cls_dim) {
+                                    long long cls_ld, int n_pts, int cls_dim, int n_classes) {
   const long long b = blockIdx.x;
   const float m = masks[b] ? 1.f : 0.f;
   const int nfreq = 4, od = 27;
@@ -323,9 +287,19 @@ __global__ void box_features_kernel(const float* __restrict__ boxes, const long 
       f *= 2.f;
     }
   }
-  const float* ct = class_tokens + classes[b] * cls_dim;
-  for (int i = threadIdx.x; i < cls_dim; i += blockDim.x)
-    cls_out[b * cls_ld + i] = ct[i] * m + null_cls[i] * (1.f - m);
+  // The reference's collate pads `classes` with -1 (dataset/utils.py:243,283) and indexes class_tokens[-1], a valid
+  // Python wrap-around whose value is then multiplied by the mask 0 (bbox_embedder.py:189-190).  A masked-out slot
+  // therefore never reads the token table here; an unmasked id follows the Python rule (negative ids count from the
+  // end) and is clamped into the table -- the host wrapper rejects ids outside [-n_classes, n_classes) beforehand.
+  if (m == 0.f) {
+    for (int i = threadIdx.x; i < cls_dim; i += blockDim.x) cls_out[b * cls_ld + i] = null_cls[i];
+    return;
+  }
+  long long c = classes[b];
+  if (c < 0) c += n_classes;
+  c = c < 0 ? 0 : (c >= n_classes ? n_classes - 1 : c);
+  const float* ct = class_tokens + c * cls_dim;
+  for (int i = threadIdx.x; i < cls_dim; i += blockDim.x) cls_out[b * cls_ld + i] = ct[i];
 }
 
 __global__ void silu_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long n) {
@@ -442,9 +416,6 @@ int dd_nchw_patches(const dd_to_padded_args* args, void* stream) {
 int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream) {
   return im2col_s2_run(x, x_ld, out, n_img, h, w, c, reinterpret_cast<cudaStream_t>(stream));
 }
-int dd_im2col_s1(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream) {
-  return im2col_s1_run(x, x_ld, out, n_img, h, w, c, reinterpret_cast<cudaStream_t>(stream));
-}
 int dd_upsample_pad(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, int h2, int w2,
                     void* stream) {
   return upsample_pad_run(x, x_ld, out, n_img, h, w, c, h2, w2, reinterpret_cast<cudaStream_t>(stream));
@@ -473,10 +444,10 @@ int dd_fourier_embed(const float* x, float* out, long long rows, int nfreq, void
 int dd_box_features(const float* boxes, const long long* classes, const unsigned char* masks,
                     const float* class_tokens, const float* null_pos, const float* null_cls, float* pos_out,
                     long long pos_ld, float* cls_out, long long cls_ld, long long n_box, int n_pts, int cls_dim,
-                    void* stream) {
-  if (n_box <= 0) { set_error("dd_box_features: bad shape"); return -1; }
+                    int n_classes, void* stream) {
+  if (n_box <= 0 || n_classes <= 0) { set_error("dd_box_features: bad shape"); return -1; }
   box_features_kernel<<<(unsigned)n_box, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      boxes, classes, masks, class_tokens, null_pos, null_cls, pos_out, pos_ld, cls_out, cls_ld, n_pts, cls_dim);
+      boxes, classes, masks, class_tokens, null_pos, null_cls, pos_out, pos_ld, cls_out, cls_ld, n_pts, cls_dim, n_classes);
   if (cudaGetLastError() != cudaSuccess) { set_error("dd_box_features launch failed"); return -2; }
   count_launch();
   return 0;

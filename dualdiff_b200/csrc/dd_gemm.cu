@@ -33,8 +33,7 @@ namespace dd {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-static constexpr int GEMM_THREADS = 192;      // 2 + 4 epilogue warps (DD_EPI8=0 A/B switch of the register epilogue)
-static constexpr int GEMM_THREADS_MAX = 320;  // 2 + 8 epilogue warps (default for both epilogues)
+static constexpr int GEMM_THREADS_MAX = 320;  // TMA warp + UMMA warp + 8 epilogue warps
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
 static constexpr int EPI_WARP_BYTES = 32 * 64 * 4;  // per-epilogue-warp transpose buffer (32 rows x 64 fp32)
 // 3x3 conv mode: one staged activation box of 128 + 2 halo rows serves the three kw taps of a kernel row (the UMMA
@@ -844,9 +843,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
                           const CUtensorMap& tmOut, const CUtensorMap& tmR1, GemmDev p, cudaStream_t stream) {
   constexpr int B_BYTES = (BN / CG) * BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_BYTES;
-  // register epilogue: 4 or 8 warps (DD_EPI8=0/1, A/B switch); the TMA epilogue always runs 8
-  static const int epi8 = getenv("DD_EPI8") ? atoi(getenv("DD_EPI8")) : 1;
-  const int epi_warps = (p.tma_epi || epi8) ? 8 : 4;
+  const int epi_warps = 8;   // both epilogues run 8 warps (the 4-warp register epilogue measured slower, round 1)
   const int avail = 227 * 1024 - 3072 - epi_warps * EPI_WARP_BYTES;
   const int kchunks = (p.K + BK - 1) / BK;
   const int iters = CONV ? 3 * kchunks : p.taps * kchunks;
@@ -868,12 +865,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
     p.a_stages = 0;
     smem = (size_t)stages * STAGE_BYTES + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    DD_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, CG, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024 - 2048));
-    attr_done = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BN, CG, CONV>), 227 * 1024 - 2048)) return rc;
   p.m_tiles = (p.M + BM * CG - 1) / (BM * CG);   // tiles of 128 (one CTA) or 256 (CTA pair) rows
   p.n_tiles = (p.N + BN - 1) / BN;
   int workers = p.m_tiles * p.n_tiles;
@@ -882,10 +874,9 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   if (p.sk_chunk > 0) workers = (p.m_tiles * p.n_tiles * iters + p.sk_chunk - 1) / p.sk_chunk;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(workers * CG);
-  cfg.blockDim = dim3(epi_warps == 8 ? GEMM_THREADS_MAX : GEMM_THREADS);
+  cfg.blockDim = dim3(GEMM_THREADS_MAX);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  static const int pdl = getenv("DD_PDL") ? atoi(getenv("DD_PDL")) : 1;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
@@ -894,7 +885,7 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = 2;   // cluster shape + programmatic dependent launch (prologue overlaps the previous kernel's tail)
   DD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, CG, CONV>, tmA, tmA2, tmB, tmOut, tmR1, p));
   return 0;
 }

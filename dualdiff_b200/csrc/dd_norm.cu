@@ -248,11 +248,7 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
     const int rows_per_cta = (HW + n_part - 1) / n_part;
     dim3 grid(n_part, a->n_img);
     const size_t smem = sizeof(float) * 2 * (size_t)C * (rpi + 1);
-    static bool attr = false;
-    if (!attr) {
-      DD_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gn_stats_kernel), 96 * 1024)) return rc;
     DD_CHECK(smem <= 96 * 1024, -1, "dd_groupnorm: reduction buffer too large");
     gn_stats_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const bf16*>(a->x1), a->x1_ld, a->c1,
                                                      reinterpret_cast<const bf16*>(a->x2), a->x2_ld, C, HW,

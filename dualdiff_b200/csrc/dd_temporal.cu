@@ -161,11 +161,7 @@ int temporal_attention_run(const dd_temporal_attention_args* a, cudaStream_t str
   const unsigned grid = (unsigned)((n_seq + tok - 1) / tok);
 #define DD_TMP(D)                                                                                              \
   do {                                                                                                         \
-    static bool attr = false;                                                                                  \
-    if (!attr) {                                                                                               \
-      DD_CUDA(cudaFuncSetAttribute(temporal_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr = true;                                                                                             \
-    }                                                                                                          \
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(temporal_attn_kernel<D>), 200 * 1024)) return rc;  \
     temporal_attn_kernel<D><<<grid, 256, smem, stream>>>(p);                                                   \
   } while (0)
   if (a->head_dim == 40) DD_TMP(40);

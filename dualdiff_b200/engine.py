@@ -29,17 +29,6 @@ NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  
 BF = torch.bfloat16
 
 
-# EXPERIMENTAL A/B switch (default off: op-level parity checked on a B200, not yet measured): conv_in as ONE K = 40 GEMM over an
-# explicit 3x3 patch matrix of the 4-channel latents instead of nine 8-channel taps through the conv path
-_CONV_IN_PATCH = bool(int(__import__("os").environ.get("DD_CONV_IN_PATCH", "0")))
-
-
-# EXPERIMENTAL A/B switch (default 0 = off, not yet run on a GPU): 3x3 convolutions of the ResNet blocks on feature maps of at
-# most this many pixels go through an explicit stride-1 patch matrix + plain GEMM instead of the zero-haloed implicit GEMM
-# (DD_SMALL_CONV_IM2COL=28 covers the 4x7 level, where 30 % of the implicit-GEMM rows are halo)
-_SMALL_CONV_IM2COL = int(__import__("os").environ.get("DD_SMALL_CONV_IM2COL", "0"))
-
-
 def _dp(d):
     """Q/K head stride: head_dim 40 is zero-padded to 48 so the UMMA K extent is a multiple of 16"""
     return 48 if d == 40 else d
@@ -139,9 +128,9 @@ class Packer:
 
     def encoder(self, multiview, temb_list):
         """conv_in, time embedding, 4 down blocks, mid block — shared by the UNet and the ControlNet branches"""
-        self.conv3("conv_in", pad_cin_to=8)
-        if _CONV_IN_PATCH:   # experimental K = 40 form, packed only when the switch is on
-            self.put("conv_in.wp", pack_conv3x3_patch(self.sd["conv_in.weight"].detach().float()))
+        # conv_in on the 4-channel latents: ONE K = 40 GEMM over an explicit 3x3 patch matrix (36 columns + zero tail)
+        self.put("conv_in.wp", pack_conv3x3_patch(self.sd["conv_in.weight"].detach().float()))
+        self.put("conv_in.b", self.f32(self.sd["conv_in.bias"]))
         self.lin32("time_embedding.linear_1"); self.lin32("time_embedding.linear_2")
         for i in range(4):
             for j in range(2):
@@ -266,25 +255,18 @@ def resnet(P, p, x: Act, ctx: StepCtx, x2: Optional[torch.Tensor] = None) -> Act
     n, hw = x.n, x.hw
     off, cout = P["temb_offsets"][p]
     rpi = ctx.temb_rows_per_img_factor * hw[0] * hw[1]
-    if hw[0] * hw[1] <= _SMALL_CONV_IM2COL:   # experimental: explicit patch matrix, same tap-major weights (see the switch)
-        g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True)
-        h = ops.gemm(ops.im2col_s1(g1, n_img=n, hw=hw), P[p + ".conv1.w"], bias=P[p + ".conv1.b"],
-                     rowvec=ctx.temb[:, off:off + cout], rows_per_img=rpi)
-        g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True)
-        conv2 = lambda sc: ops.gemm(ops.im2col_s1(g2, n_img=n, hw=hw), P[p + ".conv2.w"], bias=P[p + ".conv2.b"], res1=sc)
-    else:
-        g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True,
-                           padded_out=True)
-        h = ops.gemm(g1, P[p + ".conv1.w"], bias=P[p + ".conv1.b"], taps=9, conv_hw=hw, n_img=n,
-                     rowvec=ctx.temb[:, off:off + cout], rows_per_img=rpi)
-        g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True, padded_out=True)
-        conv2 = lambda sc: ops.gemm(g2, P[p + ".conv2.w"], bias=P[p + ".conv2.b"], taps=9, conv_hw=hw, n_img=n, res1=sc)
+    g1 = ops.groupnorm(x.rows, P[p + ".norm1.g"], P[p + ".norm1.b"], n_img=n, hw=hw, x2=x2, eps=1e-5, silu=True,
+                       padded_out=True)
+    h = ops.gemm(g1, P[p + ".conv1.w"], bias=P[p + ".conv1.b"], taps=9, conv_hw=hw, n_img=n,
+                 rowvec=ctx.temb[:, off:off + cout], rows_per_img=rpi)
+    g2 = ops.groupnorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"], n_img=n, hw=hw, eps=1e-5, silu=True, padded_out=True)
     if (p + ".conv_shortcut.w") in P:
         sc = ops.gemm(x.rows, P[p + ".conv_shortcut.w"], bias=P[p + ".conv_shortcut.b"], a2=x2)
     else:
         assert x2 is None
         sc = x.rows
-    return Act(conv2(sc), n, x.H, x.W)
+    out = ops.gemm(g2, P[p + ".conv2.w"], bias=P[p + ".conv2.b"], taps=9, conv_hw=hw, n_img=n, res1=sc)
+    return Act(out, n, x.H, x.W)
 
 
 def text_kv(P, p_attn2, enc_rows):
@@ -382,16 +364,10 @@ def upsample(P, p, x: Act, hw2) -> Act:
 def conv_in(P, latents, n_outer, n_view, H, W, res1=None) -> Act:
     """latents: fp32/bf16 NCHW storage of n_view images, logically repeated n_outer times (CFG halves)"""
     assert latents.is_contiguous()
-    if _CONV_IN_PATCH and "conv_in.wp" in P:
-        cols = ops.nchw_patches(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=P["conv_in.wp"].shape[1],
-                                stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
-                                stride_view=4 * H * W, stride_c=H * W, stride_h=W)
-        return Act(ops.gemm(cols, P["conv_in.wp"], bias=P["conv_in.b"], res1=res1), n_outer * n_view, H, W)
-    pad = ops.nchw_to_padded(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=8,
-                             stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
-                             stride_view=4 * H * W, stride_c=H * W, stride_h=W)
-    n = n_outer * n_view
-    return Act(ops.gemm(pad, P["conv_in.w"], bias=P["conv_in.b"], taps=9, conv_hw=(H, W), n_img=n, res1=res1), n, H, W)
+    cols = ops.nchw_patches(latents, n_outer=n_outer, n_view=n_view, c=4, h=H, w=W, cp=P["conv_in.wp"].shape[1],
+                            stride_outer=0 if n_outer > 1 and latents.shape[0] == n_view else n_view * 4 * H * W,
+                            stride_view=4 * H * W, stride_c=H * W, stride_h=W)
+    return Act(ops.gemm(cols, P["conv_in.wp"], bias=P["conv_in.b"], res1=res1), n_outer * n_view, H, W)
 
 
 def down_path(P, x: Act, ctx: StepCtx, multiview: bool):
@@ -496,8 +472,14 @@ def build_tokens(P, camera_param, text, bboxes_3d_data):
     b, n_cam = camera_param.shape[:2]
     cam = camera_tokens(P, camera_param).reshape(b, n_cam, 1, 768)
     txt = text.float()[:, None].expand(b, n_cam, text.shape[1], 768)
+    if bboxes_3d_data is None:
+        # the reference collate returns None when a batch has no visible box / map vector (dataset/utils.py:235-237) and
+        # the branch then runs on [camera | text] tokens only (unet_addon_rawbox.py:892-895,1066-1069): zero box tokens
+        return torch.cat([cam, txt], dim=2).reshape(b * n_cam, 78, 768).to(BF).contiguous()
     bb, cl, mk = bboxes_3d_data["bboxes"], bboxes_3d_data["classes"], bboxes_3d_data["masks"]
     n_box, L = bb.shape[1], bb.shape[2]
+    if L == 0:
+        return torch.cat([cam, txt], dim=2).reshape(b * n_cam, 78, 768).to(BF).contiguous()
     tok = box_tokens(P, bb.reshape(b * n_box, L, 8, 3), cl.reshape(b * n_box, L), mk.reshape(b * n_box, L))
     tok = tok.reshape(b, n_box, L, 768)
     if n_box != n_cam:

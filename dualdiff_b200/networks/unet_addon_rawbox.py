@@ -199,8 +199,6 @@ class BEVControlNetModel(_tree.ModelBase):
             raise NotImplementedError("use_aug_text=True (configs/exp/occ_bg_augtext.yaml) is not on the dual-branch path")
         if guess_mode or attention_mask is not None or class_labels is not None or timestep_cond is not None:
             raise NotImplementedError("guess_mode / attention_mask / class_labels / timestep_cond are unused on the reference path")
-        if bboxes_3d_data is None:
-            raise NotImplementedError("bboxes_3d_data=None: the reference warns this should not happen (:683-686)")
         if not sample.is_cuda:
             raise RuntimeError("dualdiff_b200 has no CPU path: `sample` must be a CUDA tensor")
         if self._packed is None:

@@ -15,9 +15,6 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-_FORCE_ONE_CTA = bool(int(__import__('os').environ.get('DD_ONE_CTA', '0')))   # A/B switch for benchmarking
-
-
 # ---- optional per-launch instrumentation (bench.py roofline pass; never active on the timed path) ----
 _PROF = None
 
@@ -72,7 +69,6 @@ def padded_rows(n_img, H, W):
 
 _WORKSPACE = {}
 _WORKSPACE_BYTES = 64 << 20
-_STREAM_K = int(__import__('os').environ.get('DD_STREAM_K', '0'))   # A/B switch: -1 disables stream-K
 
 
 def gemm_workspace(device):
@@ -127,8 +123,8 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_img=1, res1=None, r
     args.force_bn = force_bn
     args.act = act
     args.no_tma_epilogue = 1 if no_tma_epilogue else 0
-    args.one_cta = 1 if (one_cta or _FORCE_ONE_CTA) else 0
-    args.stream_k = stream_k if stream_k != 0 else _STREAM_K
+    args.one_cta = 1 if one_cta else 0
+    args.stream_k = stream_k
     if args.stream_k >= 0 and not geglu:
         ws = gemm_workspace(a.device)
         args.workspace = _ptr(ws); args.workspace_bytes = ws.numel()
@@ -192,8 +188,9 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_col0=0, v_col0=0,
               q_hs=None, k_hs=None, v_hs=None, kv_map=None, n_src=1, n_kv_img=None, scale=None,
-              q_cols=None, k_cols=None, v_cols=None):
-    """q: [n_img*lq, *], k/v: [n_kv_img*lk, *] bf16 (may be column views of one fused projection output)."""
+              q_cols=None, k_cols=None, v_cols=None, variant=0):
+    """q: [n_img*lq, *], k/v: [n_kv_img*lk, *] bf16 (may be column views of one fused projection output).
+    variant: testing hook of the head_dim-40 kernel (include/dualdiff_b200.h), 0 = auto."""
     _req(q, torch.bfloat16, "q")
     hs_qk = 48 if head_dim == 40 else head_dim
     q_hs = hs_qk if q_hs is None else q_hs
@@ -213,6 +210,7 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
     a.n_img = n_img; a.n_kv_img = n_kv_img; a.heads = heads; a.head_dim = head_dim
     a.lq = lq; a.lk = lk; a.n_src = n_src
     a.scale = float(head_dim) ** -0.5 if scale is None else scale
+    a.variant = variant
     with _Rec("attn_tcgen05", 4.0 * n_img * lq * lk * heads * head_dim * n_src,
               2.0 * heads * head_dim * (2 * n_img * lq + 2 * n_kv_img * lk), f"d{head_dim}_Lq{lq}_Lk{lk}_s{n_src}"):
         check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")
@@ -283,7 +281,8 @@ def nchw_to_padded(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_vi
 
 
 def nchw_patches(src, *, n_outer, n_view, c, h, w, cp, stride_outer, stride_view, stride_c, stride_h, out=None):
-    """EXPERIMENTAL: 3x3 stride-1 pad-1 patch rows [n*h*w, cp] (tap-major, channel-minor, zero tail) of an NCHW image"""
+    """3x3 stride-1 pad-1 patch rows [n*h*w, cp] (tap-major, channel-minor, zero tail) of an NCHW image: conv_in on the
+    4-channel latents as ONE K = 40 GEMM (nine 8-channel taps through the conv path ran at 35 TFLOP/s)"""
     assert src.is_cuda and src.dtype in (torch.float32, torch.bfloat16)
     n = n_outer * n_view
     if out is None:
@@ -308,19 +307,6 @@ def im2col_s2(x, *, n_img, hw, out=None):
     with _Rec("layout", 0.0, 2.0 * (n_img * H * W * c + out.numel())):
         check(_lib.lib().dd_im2col_s2(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s2")
     return out, (ho, wo)
-
-
-def im2col_s1(x, *, n_img, hw, out=None):
-    """EXPERIMENTAL: 3x3 stride-1 pad-1 patch rows [n_img*H*W, 9*C] of a compact activation (column order of im2col_s2)"""
-    _req(x, torch.bfloat16, "x")
-    H, W = hw
-    c = x.shape[1]
-    assert x.shape[0] == n_img * H * W
-    if out is None:
-        out = torch.empty((n_img * H * W, 9 * c), device=x.device, dtype=torch.bfloat16)
-    with _Rec("layout", 0.0, 2.0 * (n_img * H * W * c + out.numel())):
-        check(_lib.lib().dd_im2col_s1(_ptr(x), _L(x.stride(0)), _ptr(out), n_img, H, W, c, _stream()), "dd_im2col_s1")
-    return out
 
 
 def upsample_pad(x, *, n_img, hw, hw2, out=None):
@@ -374,12 +360,22 @@ def fourier_embed(x, nfreq=4):
 
 
 def box_features(boxes, classes, masks, class_tokens, null_pos, null_cls, pos_out, cls_out):
-    """boxes [n, P, 3] fp32, classes [n] int64, masks [n] uint8/bool -> pos_out [n, 27P], cls_out [n, 768]"""
+    """boxes [n, P, 3] fp32, classes [n] int64, masks [n] uint8/bool -> pos_out [n, 27P], cls_out [n, 768].
+    Class ids follow the reference's Python indexing of `class_tokens` (bbox_embedder.py:189): ids in [-n_classes, 0)
+    count from the end (the collate pads with -1, dataset/utils.py:243,283), anything else raises like the reference's
+    IndexError.  Runs once per sample in prepare(), so the range check's host sync is off the step path."""
+    _req(boxes, torch.float32, "boxes")
+    _req(classes, torch.int64, "classes")
+    _req(class_tokens, torch.float32, "class_tokens")
     n, P = boxes.shape[0], boxes.shape[1]
+    n_classes = class_tokens.shape[0]
+    assert classes.numel() == n and masks.numel() == n and classes.is_contiguous() and class_tokens.is_contiguous()
+    if n and bool(((classes < -n_classes) | (classes >= n_classes)).any()):
+        raise IndexError(f"box_features: class id outside [-{n_classes}, {n_classes}) (index out of range for class_tokens)")
     m8 = masks.to(torch.uint8).contiguous()
     check(_lib.lib().dd_box_features(_ptr(boxes), _ptr(classes), _ptr(m8), _ptr(class_tokens), _ptr(null_pos),
                                      _ptr(null_cls), _ptr(pos_out), _L(pos_out.stride(0)), _ptr(cls_out),
-                                     _L(cls_out.stride(0)), _L(n), P, class_tokens.shape[1], _stream()),
+                                     _L(cls_out.stride(0)), _L(n), P, class_tokens.shape[1], _I(n_classes), _stream()),
           "dd_box_features")
 
 

@@ -191,7 +191,7 @@ def slice_views(inputs: dict, views, n_cam: int = 6) -> dict:
     out["latents"] = inputs["latents"][:, idx].contiguous()
     out["camera_param"] = inputs["camera_param"][:, idx].contiguous()
     bb = inputs["boxes_bg"]
-    out["boxes_bg"] = {k: (v[:, idx].contiguous() if v.shape[1] == n_cam else v) for k, v in bb.items()}
+    out["boxes_bg"] = None if bb is None else {k: (v[:, idx].contiguous() if v.shape[1] == n_cam else v) for k, v in bb.items()}
     cb = inputs["cond_bg"]                                   # (B, 3, H, n_cam*W) panorama
     w = cb.shape[-1] // n_cam
     out["cond_bg"] = torch.cat([cb[..., v * w:(v + 1) * w] for v in views], dim=-1).contiguous()

@@ -115,6 +115,8 @@ typedef struct dd_attention_args {
   int q_head_stride, k_head_stride, v_head_stride;
   int n_img, n_kv_img, heads, head_dim, lq, lk, n_src;
   float scale;
+  int variant;                /* testing hook (head_dim 40): 0 = auto (two query tiles per CTA, 25 % of the exponentials on
+                                 the FMA pipe), 1 = one-tile kernel, 2 = two-tile kernel with every exponential on MUFU */
 } dd_attention_args;
 DD_API int dd_attention(const dd_attention_args* args, void* stream);
 
@@ -193,9 +195,6 @@ DD_API int dd_nchw_patches(const dd_to_padded_args* args, void* stream);
 /* 3x3 stride-2 pad-1 patches of a compact activation -> [n_img*Ho*Wo, 9*C] (diffusers Downsample2D.conv and the
  * stride-2 convs of ControlNetConditioningEmbedding) */
 DD_API int dd_im2col_s2(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
-/* EXPERIMENTAL (not on the default path): the stride-1 form, [n_img*H*W, 9*C], same column order --
- * an explicit patch matrix for the smallest feature maps, where the zero-haloed layout wastes 30 % of the UMMA rows */
-DD_API int dd_im2col_s1(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, void* stream);
 /* nearest-neighbour resize to (h2, w2) written in the padded layout (diffusers Upsample2D with explicit size,
  * networks/unet_2d_condition_multiview.py:363-374,500-501): src = floor(dst * in / out) */
 DD_API int dd_upsample_pad(const void* x, long long x_ld, void* out, int n_img, int h, int w, int c, int h2, int w2,
@@ -219,7 +218,7 @@ DD_API int dd_fourier_embed(const float* x, float* out, long long rows, int nfre
 DD_API int dd_box_features(const float* boxes, const long long* classes, const unsigned char* masks,
                            const float* class_tokens, const float* null_pos, const float* null_cls,
                            float* pos_out, long long pos_ld, float* cls_out, long long cls_ld,
-                           long long n_box, int n_pts, int cls_dim, void* stream);
+                           long long n_box, int n_pts, int cls_dim, int n_classes, void* stream);
 /* out = silu(x) (fp32 -> bf16), n elements */
 DD_API int dd_silu_to_bf16(const float* x, void* out, long long n, void* stream);
 /* out = a + b (+ c) elementwise over bf16, n elements (multiple of 8) */

@@ -68,8 +68,12 @@ def mha(q, k, v, heads):
     qh = q.reshape(b, lq, heads, d).transpose(1, 2)
     kh = k.reshape(b, k.shape[1], heads, d).transpose(1, 2)
     vh = v.reshape(b, v.shape[1], heads, d).transpose(1, 2)
-    s = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
-    o = torch.matmul(s.softmax(-1), vh)
+    step = max(1, (1 << 28) // max(1, heads * lq * k.shape[1]))   # batch-chunked: dense scores stay below ~1 GiB
+    outs = []
+    for i in range(0, b, step):
+        s = torch.matmul(qh[i:i + step], kh[i:i + step].transpose(-1, -2)) * (d ** -0.5)
+        outs.append(torch.matmul(s.softmax(-1), vh[i:i + step]))
+    o = outs[0] if len(outs) == 1 else torch.cat(outs)
     return o.transpose(1, 2).reshape(b, lq, c)
 
 
@@ -272,13 +276,16 @@ def controlnet_forward(sd: SD, sample, timestep, camera_param, bboxes_3d_data, e
     cam = camera_tokens(sd, camera_param)                                       # :832-837
     txt = enc_text[:, None].expand(b, n_cam, *enc_text.shape[1:])               # use_aug_text False: repeat (:354)
     enc_cam = torch.cat([cam[:, :, None], txt], dim=2)                          # (b, n, 78, 768)  :355-360
-    bb, cl, mk = bboxes_3d_data["bboxes"], bboxes_3d_data["classes"], bboxes_3d_data["masks"]
-    n_box = bb.shape[1]
-    tok = box_tokens(sd, bb.reshape(-1, *bb.shape[2:]), cl.reshape(-1, cl.shape[-1]), mk.reshape(-1, mk.shape[-1]))
-    if n_box != n_cam:                                                          # view-shared boxes: repeat (:879-883)
-        tok = tok.reshape(b, 1, *tok.shape[1:]).expand(b, n_cam, *tok.shape[1:])
+    if bboxes_3d_data is None:                                                  # bbox_emb = None: no box tokens (:892-895)
+        tok = enc_cam.new_zeros((b, n_cam, 0, enc_cam.shape[-1]))
     else:
-        tok = tok.reshape(b, n_cam, *tok.shape[1:])
+        bb, cl, mk = bboxes_3d_data["bboxes"], bboxes_3d_data["classes"], bboxes_3d_data["masks"]
+        n_box = bb.shape[1]
+        tok = box_tokens(sd, bb.reshape(-1, *bb.shape[2:]), cl.reshape(-1, cl.shape[-1]), mk.reshape(-1, mk.shape[-1]))
+        if n_box != n_cam:                                                      # view-shared boxes: repeat (:879-883)
+            tok = tok.reshape(b, 1, *tok.shape[1:]).expand(b, n_cam, *tok.shape[1:])
+        else:
+            tok = tok.reshape(b, n_cam, *tok.shape[1:])
     emb = time_embedding(sd, torch.as_tensor(timestep).reshape(-1))             # :903-929
     x = sample.reshape(b * n_cam, *sample.shape[2:])                            # :944
     enc_cam = enc_cam.reshape(b * n_cam, *enc_cam.shape[2:])
@@ -304,7 +311,8 @@ def add_uncond(sd: SD, camera_param, bboxes_3d_data):
     b, n = camera_param.shape[:2]
     unc = sd["uncond_cam.weight"][0].reshape(1, 1, 3, 7).expand(b, n, 3, 7)
     cam = torch.cat([unc, camera_param], dim=0)
-    boxes = {k: torch.cat([torch.zeros_like(v), v], dim=0) for k, v in bboxes_3d_data.items()}
+    boxes = None if bboxes_3d_data is None else \
+        {k: torch.cat([torch.zeros_like(v), v], dim=0) for k, v in bboxes_3d_data.items()}   # None stays None (:683-700)
     return cam, boxes
 
 

@@ -106,8 +106,15 @@ class AttnProcessor:
         query = attn.head_to_batch_dim(query)
         key = attn.head_to_batch_dim(key)
         value = attn.head_to_batch_dim(value)
-        probs = attn.get_attention_scores(query, key, attention_mask)
-        hidden_states = torch.bmm(probs, value)
+        # batch-chunked so the dense score tensor stays below ~1 GiB at HD latents (each batch item is independent:
+        # the result is identical to the one-shot evaluation)
+        step = max(1, (1 << 28) // max(1, query.shape[1] * key.shape[1]))
+        outs = []
+        for i in range(0, query.shape[0], step):
+            m = None if attention_mask is None else attention_mask[i:i + step]
+            probs = attn.get_attention_scores(query[i:i + step], key[i:i + step], m)
+            outs.append(torch.bmm(probs, value[i:i + step]))
+        hidden_states = outs[0] if len(outs) == 1 else torch.cat(outs)
         hidden_states = attn.batch_to_head_dim(hidden_states)
         hidden_states = attn.to_out[0](hidden_states)
         hidden_states = attn.to_out[1](hidden_states)

@@ -12,11 +12,16 @@ def memory_efficient_attention(query, key, value, attn_bias=None, op=None, scale
     v = value.transpose(1, 2)
     if scale is None:
         scale = q.shape[-1] ** -0.5
-    s = torch.matmul(q, k.transpose(-1, -2)) * scale
-    if attn_bias is not None:
-        b = attn_bias
-        if b.dim() == 3:  # [B*H or B, Lq, Lk]
-            b = b.reshape(q.shape[0], -1, b.shape[-2], b.shape[-1])
-        s = s + b
-    o = torch.matmul(s.softmax(dim=-1), v).transpose(1, 2)
+    b = attn_bias
+    if b is not None and b.dim() == 3:  # [B*H or B, Lq, Lk]
+        b = b.reshape(q.shape[0], -1, b.shape[-2], b.shape[-1])
+    # batch-chunked (dense scores below ~1 GiB at HD latents); identical to the one-shot evaluation per batch item
+    step = max(1, (1 << 28) // max(1, q.shape[1] * q.shape[2] * k.shape[2]))
+    outs = []
+    for i in range(0, q.shape[0], step):
+        s = torch.matmul(q[i:i + step], k[i:i + step].transpose(-1, -2)) * scale
+        if b is not None:
+            s = s + b[i:i + step]
+        outs.append(torch.matmul(s.softmax(dim=-1), v[i:i + step]))
+    o = (outs[0] if len(outs) == 1 else torch.cat(outs)).transpose(1, 2)
     return o[:, :, 0] if three_d else o

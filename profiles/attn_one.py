@@ -1,20 +1,51 @@
-"""one L0 self-attention launch (d=40, T=1400) for ncu"""
+"""level-0 attention launches (d = 40) timed per kernel variant: self (T x T), cross-view (two sources) and text (Lk = 106).
+    python profiles/attn_one.py            # table over variants 1 (one-tile), 2 (two-tile, all MUFU), 0 (two-tile + FMA-pipe share)
+    VARIANT=0 ONLY=self python profiles/attn_one.py   # one configuration (for ncu)"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dualdiff_b200 import ops
-n = int(os.environ.get("N_IMG", "24"))
-L, d, dp = 1400, 40, 48
+n = int(os.environ.get("N_IMG", "96"))
+L = int(os.environ.get("TOKENS", "1400"))
+d, dp = 40, 48
 qkv = (torch.randn(n * L, 16 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
-for _ in range(3):
-    ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp)
-torch.cuda.synchronize()
-ts = []
-for i in range(8):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp)
-    e1.record()
+txt = (torch.randn(n * 106, 8 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
+kv_map = torch.tensor([[(i // 6) * 6 + (i + 5) % 6, (i // 6) * 6 + (i + 1) % 6] for i in range(n)], dtype=torch.int32, device="cuda")
+
+
+def run(kind, variant):
+    if kind == "self":
+        return ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp,
+                             variant=variant)
+    if kind == "xview":
+        return ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp,
+                             kv_map=kv_map, n_src=2, variant=variant)
+    return ops.attention(qkv, txt, txt, n_img=n, lq=L, lk=106, heads=8, head_dim=d, q_col0=0, k_col0=0, v_col0=8 * dp,
+                         q_cols=8 * dp, variant=variant)
+
+
+def timed(kind, variant, reps=8):
+    for _ in range(3):
+        run(kind, variant)
     torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
-t = sorted(ts)[len(ts) // 2]
-print(f"attention d={d} L={L} n_img={n} poly={os.environ.get('DD_ATTN_POLY', '0')}: {t * 1e3:8.1f} us  {4.0 * n * L * L * 8 * d / t / 1e9:7.1f} TFLOP/s")
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(kind, variant); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+kinds = [os.environ["ONLY"]] if os.environ.get("ONLY") else ["self", "xview", "text"]
+variants = [int(os.environ["VARIANT"])] if os.environ.get("VARIANT") else [1, 2, 0]
+ref = {}
+for kind in kinds:
+    lk, ns = (106, 1) if kind == "text" else (L, 2 if kind == "xview" else 1)
+    for v in variants:
+        t = timed(kind, v)
+        out = run(kind, v).float()
+        if kind not in ref:
+            ref[kind] = out
+        err = ((out - ref[kind]).abs().max() / ref[kind].abs().max()).item()
+        print(f"attention d={d} {kind:5s} Lq={L} Lk={lk} n_img={n} variant={v}: {t * 1e3:8.1f} us  "
+              f"{4.0 * n * L * lk * ns * 8 * d / t / 1e9:7.1f} TFLOP/s  max-rel diff vs first variant {err:.2e}", flush=True)

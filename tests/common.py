@@ -75,3 +75,38 @@ def metrics(out, ref):
     rel_l2 = ((out - ref).norm() / ref.norm()).item()
     max_rel = ((out - ref).abs().max() / ref.abs().max()).item()
     return dict(cos=cos, rel_l2=rel_l2, max_rel=max_rel)
+
+
+def strided_sample(t, n):
+    """every k-th element of the flattened tensor, k chosen so that about n elements are kept (k is odd, so the sample
+    walks through all channels / rows / columns of an NCHW tensor).  Used by oracle/make_golden.py to keep large
+    reference tensors as small fixtures and by the tests to sample the CUDA result the same way."""
+    f = t.reshape(-1)
+    k = max(1, f.numel() // n) | 1
+    return f[::k].clone()
+
+
+def make_scene_batch(seeds, h, w, L_bg=28, L_fg=32):
+    """step inputs of len(seeds) scenes where scene i is exactly synthetic.make_inputs(1, h, w, seed=seeds[i]) -- so that a
+    scene computed inside a batch can be compared with the same scene computed alone (make_inputs(B, ...) draws all scenes
+    from one generator stream).  prompt_embeds keeps the pipeline's layout: all uncond rows first, then all cond rows."""
+    from dualdiff_b200 import synthetic as S
+    per = [S.make_inputs(1, h, w, seed=s, L_bg=L_bg, L_fg=L_fg) for s in seeds]
+    out = {}
+    for k in ("latents", "camera_param", "cond_bg", "cond_fg"):
+        out[k] = torch.cat([p[k] for p in per])
+    out["prompt_embeds"] = torch.cat([p["prompt_embeds"][:1] for p in per] + [p["prompt_embeds"][1:] for p in per])
+    for k in ("boxes_bg", "boxes_fg"):
+        out[k] = {kk: torch.cat([p[k][kk] for p in per]) for kk in per[0][k]}
+    return out
+
+
+def scene_of(inputs, i, n_cam=6):
+    """scene i of a make_scene_batch() dict, in the layout of synthetic.make_inputs(1, ...)"""
+    B = inputs["latents"].shape[0]
+    out = {k: inputs[k][i:i + 1] for k in ("latents", "camera_param", "cond_bg")}
+    out["cond_fg"] = inputs["cond_fg"][i * n_cam:(i + 1) * n_cam]
+    out["prompt_embeds"] = torch.stack([inputs["prompt_embeds"][i], inputs["prompt_embeds"][B + i]])
+    for k in ("boxes_bg", "boxes_fg"):
+        out[k] = {kk: v[i:i + 1] for kk, v in inputs[k].items()}
+    return out

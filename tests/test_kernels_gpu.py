@@ -107,6 +107,31 @@ def test_cross_view_attention_two_neighbours(d, L):
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("lq,lk,n_src", [(128, 48, 1), (129, 49, 1), (256, 47, 2), (257, 96, 1), (1400, 1400, 2), (640, 1, 1),
+                                         (5600, 200, 1), (100, 145, 2)])
+def test_head_dim_40_kernel_variants(lq, lk, n_src, variant):
+    """the level-0 kernel (two query tiles per CTA, 48-key tiles; variant 0 = with 25 % of the exponentials on the FMA pipe,
+    2 = all on MUFU) and the one-tile kernel (1) on ragged shapes: odd / even query-tile counts, key counts around the
+    48-key tile, a single key, one and two K/V sources"""
+    from dualdiff_b200 import ops
+    d, heads, n = 40, 8, 3
+    C = heads * d
+    q = _mk((n * lq, C), 11); k = _mk((n * lk, C), 12, 2.0); v = _mk((n * lk, C), 13)
+    kv = torch.cat([_heads_pad(k, heads, d, 48), v], dim=1).contiguous()
+    kv_map = torch.tensor([[(i + 1) % n, (i + 2) % n] for i in range(n)], dtype=torch.int32).cuda() if n_src == 2 else None
+    out = ops.attention(_heads_pad(q, heads, d, 48), kv, kv, n_img=n, lq=lq, lk=lk, heads=heads, head_dim=d,
+                        k_col0=0, v_col0=heads * 48, kv_map=kv_map, n_src=n_src, variant=variant)
+    qh, kh, vh = _ref_attn(q, k, v, n, lq, lk, heads, d)
+    if n_src == 1:
+        ref = F.scaled_dot_product_attention(qh, kh, vh)
+    else:
+        ref = sum(F.scaled_dot_product_attention(qh, kh[kv_map[:, s].long()], vh[kv_map[:, s].long()]) for s in range(2))
+    ref = ref.transpose(1, 2).reshape(n * lq, C)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
 @pytest.mark.parametrize("n,H,W,c1,c2,padded,silu,eps", [
     (3, 28, 50, 320, 0, True, True, 1e-5), (2, 14, 25, 640, 0, False, False, 1e-6), (2, 7, 13, 1280, 1280, True, True, 1e-5),
     (2, 14, 25, 1280, 640, True, True, 1e-5), (2, 28, 50, 640, 320, True, True, 1e-5), (2, 4, 7, 1280, 0, True, True, 1e-5)])
@@ -168,18 +193,42 @@ def test_upsample_nearest_to_size(hw, hw2):
     assert torch.equal(out.float(), packing.to_padded(ref))
 
 
-def test_latent_conv_in():
-    """conv_in 4->320 on fp32 NCHW latents with CFG duplication (stride_outer = 0)"""
-    from dualdiff_b200 import ops, packing
-    n, H, W = 6, 28, 50
-    lat = torch.randn(n, 4, H, W, generator=torch.Generator().manual_seed(1)).cuda()
-    w = _mk((320, 4, 3, 3), 2, 1 / 6.0)
-    wp = torch.zeros(320, 8, 3, 3, dtype=torch.bfloat16, device="cuda"); wp[:, :4] = w
-    pad = ops.nchw_to_padded(lat, n_outer=2, n_view=n, c=4, h=H, w=W, cp=8, stride_outer=0,
-                             stride_view=4 * H * W, stride_c=H * W, stride_h=W)
-    out = ops.gemm(pad, packing.pack_conv3x3(wp), taps=9, conv_hw=(H, W), n_img=2 * n)
-    ref = F.conv2d(torch.cat([lat, lat]).to(torch.bfloat16).float(), w.float(), None, padding=1)
-    assert _rel(out, ref.permute(0, 2, 3, 1).reshape(-1, 320)) < 1e-2
+def _patch_rows(x, cp):
+    """torch restatement of dd_nchw_patches: [n, C, H, W] -> [n*H*W, cp], columns tap-major / channel-minor, zero tail"""
+    n, c, h, w = x.shape
+    cols = F.unfold(x, 3, padding=1)                                         # [n, C*9, H*W], channel-major / tap-minor
+    cols = cols.reshape(n, c, 9, h * w).permute(0, 3, 2, 1).reshape(n * h * w, 9 * c)
+    out = x.new_zeros((n * h * w, cp))
+    out[:, :9 * c] = cols
+    return out
+
+
+@pytest.mark.parametrize("n_outer,n_view,h,w,shared", [(2, 6, 28, 50, True), (1, 3, 5, 7, False), (2, 2, 8, 12, False)])
+def test_latent_conv_in(n_outer, n_view, h, w, shared):
+    """conv_in 4->320 on fp32 NCHW latents (CFG duplication = stride_outer 0) as ONE K = 40 GEMM over the 3x3 patch matrix:
+    the patch kernel is bit-equal to the torch restatement, the GEMM equals F.conv2d (+ the ControlNet's fused condition
+    residual, unet_addon_rawbox.py:965,990) and the nine-tap implicit-GEMM convolution on the same weights"""
+    from dualdiff_b200 import ops
+    from dualdiff_b200.packing import pack_conv3x3, pack_conv3x3_patch
+    g = torch.Generator().manual_seed(1)
+    n_src = n_view if shared else n_outer * n_view
+    lat = torch.randn(n_src, 4, h, w, generator=g)
+    wt, b = torch.randn(320, 4, 3, 3, generator=g) * 0.2, torch.randn(320, generator=g)
+    res = torch.randn(n_outer * n_view * h * w, 320, generator=g).to(torch.bfloat16)
+    kw = dict(n_outer=n_outer, n_view=n_view, c=4, h=h, w=w, stride_outer=0 if shared else n_view * 4 * h * w,
+              stride_view=4 * h * w, stride_c=h * w, stride_h=w)
+    cols = ops.nchw_patches(lat.cuda(), cp=40, **kw)
+    full = torch.cat([lat] * n_outer) if shared else lat
+    assert torch.equal(cols.float().cpu(), _patch_rows(full, 40).to(torch.bfloat16).float())
+    out = ops.gemm(cols, pack_conv3x3_patch(wt).cuda(), bias=b.cuda(), res1=res.cuda()).float().cpu()
+    w8 = torch.zeros(320, 8, 3, 3); w8[:, :4] = wt
+    pad = ops.nchw_to_padded(lat.cuda(), cp=8, **kw)
+    taps = ops.gemm(pad, pack_conv3x3(w8).cuda(), bias=b.cuda(), taps=9, conv_hw=(h, w), n_img=n_outer * n_view,
+                    res1=res.cuda()).float().cpu()
+    ref = F.conv2d(full.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), b, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, 320) + res.float()
+    assert (out - ref).abs().max() <= 2e-2 * ref.abs().max()
+    assert (out - taps).abs().max() <= 2e-2 * ref.abs().max()
 
 
 def test_small_fp32_pieces():
@@ -217,6 +266,46 @@ def test_box_features():
     emb = torch.cat([boxes] + [fn(boxes * 2.0 ** k) for k in range(4) for fn in (torch.sin, torch.cos)], -1).reshape(n, -1)
     assert (pos - (emb * m + null_pos * (1 - m))).abs().max() < 1e-4
     assert (cls - (tokens[classes] * m + null_cls * (1 - m))).abs().max() < 1e-6
+
+
+def test_box_features_padded_class_ids_follow_the_reference():
+    """the reference's collate pads `classes` with -1 where masks == 0 (dataset/utils.py:243,283) and indexes
+    class_tokens[-1] (a Python wrap-around) before multiplying by the mask: the kernel must neither read before the
+    token table nor let whatever lies there leak in, an unmasked -k counts from the end, and ids outside
+    [-n_classes, n_classes) raise like the reference's IndexError.  Checked against the oracle (torch indexing)."""
+    from dualdiff_b200 import ops
+    from oracle import dualdiff_oracle as O
+    g = torch.Generator().manual_seed(5)
+    R, L, P, n_cls = 3, 9, 8, 10
+    boxes = torch.rand(R, L, P, 3, generator=g) * 100 - 50
+    masks = torch.rand(R, L, generator=g) < 0.5
+    classes = torch.randint(0, n_cls, (R, L), generator=g)
+    classes[~masks] = -1                      # collate padding
+    boxes[~masks] = 0
+    classes[0, 0], masks[0, 0] = -3, True     # unmasked negative id: Python semantics = n_cls - 3
+    sd = {"bbox_embedder._class_tokens": torch.randn(n_cls, 768, generator=g),
+          "bbox_embedder.null_pos_feature": torch.randn(27 * P, generator=g),
+          "bbox_embedder.null_class_feature": torch.randn(768, generator=g)}
+    m = masks.reshape(-1, 1).float()
+    ref_cls = sd["bbox_embedder._class_tokens"][classes.reshape(-1)] * m + sd["bbox_embedder.null_class_feature"][None] * (1 - m)
+    ref_pos = O.fourier_embed(boxes.reshape(R * L, P, 3)).reshape(R * L, -1) * m + sd["bbox_embedder.null_pos_feature"][None] * (1 - m)
+    # poison the memory in front of the token table: a stray read of class_tokens[-1] would pick up NaNs
+    arena = torch.full((n_cls + 4, 768), float("nan"), device="cuda")
+    arena[4:] = sd["bbox_embedder._class_tokens"].cuda()
+    tokens = arena[4:]
+    pos = torch.empty(R * L, 27 * P, device="cuda"); cls = torch.empty(R * L, 768, device="cuda")
+    ops.box_features(boxes.reshape(R * L, P, 3).cuda(), classes.reshape(-1).cuda(), masks.reshape(-1).cuda(), tokens,
+                     sd["bbox_embedder.null_pos_feature"].cuda(), sd["bbox_embedder.null_class_feature"].cuda(), pos, cls)
+    assert torch.isfinite(cls).all() and torch.isfinite(pos).all()
+    assert (cls.cpu() - ref_cls).abs().max() < 1e-6
+    assert (pos.cpu() - ref_pos).abs().max() < 1e-4
+    bad = classes.reshape(-1).clone(); bad[1] = n_cls
+    with pytest.raises(IndexError):
+        ops.box_features(boxes.reshape(R * L, P, 3).cuda(), bad.cuda(), masks.reshape(-1).cuda(), tokens,
+                         sd["bbox_embedder.null_pos_feature"].cuda(), sd["bbox_embedder.null_class_feature"].cuda(), pos, cls)
+    with pytest.raises(TypeError):
+        ops.box_features(boxes.reshape(R * L, P, 3).cuda(), classes.reshape(-1).int().cuda(), masks.reshape(-1).cuda(), tokens,
+                         sd["bbox_embedder.null_pos_feature"].cuda(), sd["bbox_embedder.null_class_feature"].cuda(), pos, cls)
 
 
 def test_layout_roundtrip_and_cfg_sched():

@@ -198,3 +198,20 @@ def test_samplers_converge_to_the_analytic_ode_solution():
         assert all(b < 0.62 * a for a, b in zip(err[k], err[k][1:])), (k, err[k])     # halving the step at least ~halves the error
     assert all(u < d for u, d in zip(err["unipc"], err["ddim"])), err
     assert err["unipc"][-1] < 5e-3 and err["ddim"][-1] < 2e-2, err
+
+
+def test_patch_weight_packing_reproduces_the_convolution():
+    """host half of the conv_in path (engine.conv_in): [patch matrix] x [pack_conv3x3_patch weights]^T == F.conv2d"""
+    from dualdiff_b200.packing import pack_conv3x3_patch
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn(16, 4, 3, 3, generator=g), torch.randn(16, generator=g)
+    x = torch.randn(3, 4, 5, 7, generator=g)
+    wp = pack_conv3x3_patch(w)
+    assert wp.shape == (16, 40) and wp.dtype == torch.bfloat16 and (wp[:, 36:] == 0).all()
+    n, c, h, wd = x.shape
+    cols = torch.nn.functional.unfold(x, 3, padding=1).reshape(n, c, 9, h * wd).permute(0, 3, 2, 1).reshape(n * h * wd, 9 * c)
+    rows = x.new_zeros((n * h * wd, 40))
+    rows[:, :36] = cols
+    out = rows @ wp.float().T + b
+    ref = torch.nn.functional.conv2d(x, w.to(torch.bfloat16).float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, 16)
+    assert (out - ref).abs().max() < 1e-4
