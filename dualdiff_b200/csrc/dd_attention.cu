@@ -32,7 +32,7 @@ __device__ __forceinline__ float fast_exp2(float x) {  // inputs are <= 0 after 
 }
 static constexpr int ATT_BM = 128;
 static constexpr int ATT_THREADS = 160;     // attn_v2: 4 softmax warps + 1 TMA/UMMA warp
-static constexpr int PP_THREADS = 288;      // attn_pp: 2 softmax warpgroups (one query tile each) + 1 TMA/UMMA warp
+static constexpr int PP_THREADS = 320;      // attn_pp: 2 softmax warpgroups (one query tile each) + 2 UMMA-issuing warps
 
 struct AttnDev {
   int Lq, Lk, n_src, n_kv_tiles;
@@ -41,6 +41,7 @@ struct AttnDev {
   bf16* out;
   long long out_ld;
   int q_col0, k_col0, v_col0, q_hs, k_hs, v_hs, o_hs;
+  int heads, n_img;   // persistent kernel: item -> (image, head, query-tile pair)
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -100,65 +101,79 @@ __device__ __forceinline__ void store_o_row(uint32_t tmem_o_row, float inv, bf16
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// attn_pp_kernel: two query tiles per CTA.
+// attn_pp_kernel: persistent CTAs, two query tiles per CTA.
 //
 // ncu on the one-tile kernel at head_dim 40 (profiles/r01_ncu_attn_L0_self.txt + source page): a 128 x 128 tile needs 16 384
 // ex2 = 1024 cycles of the 16-lane MUFU pipe against 384 tensor cycles, so the kernel is MUFU-bound -- but the pipe was only
-// 65 % busy.  The softmax warps almost never wait for S (4 % of their samples); they spend 45 % of their time in the
-// non-exponential part of the loop (TMEM load, row maximum, P store, barrier round trips), and with one softmax warp per
-// CTA and scheduler only two warps share a MUFU pipe, often in the same phase.  Here:
-//   * a CTA owns TWO 128-row query tiles of one (image, head): softmax warpgroup 0 / 1 (warps 0-3 / 4-7) each run the
-//     online softmax of their own tile, the issuing warp interleaves the UMMAs of both; with two CTAs per SM FOUR softmax
-//     warps share every scheduler, so the MUFU pipe always finds a warp in its exponential phase;
+// 65 % busy.  The softmax warps spend 45 % of their time in the non-exponential part of the loop (TMEM load, row maximum,
+// P store, barrier round trips), and with one softmax warp per CTA and scheduler only two warps share a MUFU pipe, often in
+// the same phase.  Here:
+//   * a work item = TWO 128-row query tiles of one (image, head): softmax warpgroup 0 / 1 (warps 0-3 / 4-7) each run the
+//     online softmax of their own tile; with two CTAs per SM FOUR softmax warps share every scheduler, so the MUFU pipe
+//     nearly always finds a warp in its exponential phase;
+//   * every tile has its own UMMA-issuing warp (8 / 9; warp 8 also runs the TMA loads).  With one warp issuing for both tiles
+//     (349 instructions per key tile, integer divisions and descriptor rebuilds included) the softmax warps spent 47 % of
+//     their samples waiting for S (profiles/r02_attn_notes.md); now the (item, source, key tile) cursor is carried in
+//     counters and the operand descriptors are formed once and advanced by adding to their low word;
 //   * both tiles consume the same K/V stage: the K/V bytes crossing the L2 -> SM fabric halve (3.4 GB per level-0 launch
 //     before, 5.7 TB/s -- the next limit once the MUFU pipe is busy);
 //   * key tiles are 48 wide: S (48 columns) + P (24) + O (48) = 120 TMEM columns per query tile, 256 per CTA, and the
-//     48 scores + 24 packed probabilities of a row fit the 112 registers two 288-thread CTAs leave per thread;
+//     48 scores + 24 packed probabilities of a row fit the 96 registers two 320-thread CTAs leave per thread;
+//   * the CTAs are PERSISTENT (grid = 2 x SMs): a CTA walks the items  blockIdx.x, blockIdx.x + gridDim.x, ...  as ONE stream
+//     of K/V tiles through the TMA ring, with the query tiles double-buffered, so barrier set-up, TMEM allocation and the
+//     first Q / K / V round trip (13 % of a CTA's life when every item was its own CTA) are paid once per CTA and the
+//     epilogue of an item overlaps the first key tiles of the next;
 //   * POLY: one pair of every four is exponentiated on the FMA pipe (exp2_poly_pair) instead of the MUFU pipe, which then
 //     has 25 % fewer operations; with four warps per scheduler the polynomial of one warp overlaps the MUFU stream of the
 //     others (the all-or-nothing and same-warp forms measured slower in round 1).
 // TMEM columns of query tile t (base t * 128): S [0, BN) | P [BN, BN + BN/2) | O [BN + BN/2, BN + BN/2 + DVP).
 // ---------------------------------------------------------------------------------------------------------------
+struct PPCursor {       // position of one role in the CTA's stream of key tiles: (item, source, key tile) + running tile index
+  int item, src, jt, G;
+};
+
 template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
 __global__ void __launch_bounds__(PP_THREADS, 2)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
   static_assert(DQK <= 64 && DVP <= 64 && DQK % 16 == 0 && DVP % 16 == 0, "one 64-column swizzle chunk per operand");
-  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 64 && STAGES >= 2 && STAGES <= 4, "key tile / ring geometry");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 64 && (STAGES == 4 || STAGES == 8), "key tile / ring geometry");
   constexpr int Q_TILE = ATT_BM * 128;                  // bytes: 128 query rows x 64 bf16
   constexpr int K_TILE = BN * 128;                      // bytes: BN key rows x 64 bf16 (a multiple of the 1024-byte swizzle atom)
   constexpr int KV_STAGE_BYTES = 2 * K_TILE;
   constexpr int T_STRIDE = 128;                         // TMEM columns per query tile
   constexpr int P_COL = BN, O_COL = BN + BN / 2;
   static_assert(O_COL + DVP <= T_STRIDE && K_TILE % 1024 == 0, "TMEM / swizzle geometry");
-  constexpr int ISSUER = 8;                             // warp index of the TMA / UMMA warp
+  constexpr int ISSUER = 8;                             // warps 8, 9: UMMA issuers of tile 0, 1 (warp 8 also runs the TMA loads)
+  constexpr int SMASK = STAGES - 1, SSHIFT = (STAGES == 4) ? 2 : 3;
   constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, BN, 0, 0);
   constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, DVP, 0, 1);  // B (=V) is MN-major
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t sQ = smem_base;                        // [2] query tiles
-  const uint32_t sKV = sQ + 2 * Q_TILE;                 // [STAGES] {K tile, V tile}
+  const uint32_t sQ = smem_base;                        // [2 buffers][2 tiles] query tiles
+  const uint32_t sKV = sQ + 4 * Q_TILE;                 // [STAGES] {K tile, V tile}
   const uint32_t bar0 = sKV + STAGES * KV_STAGE_BYTES;
-  const uint32_t q_full = bar0;                         // [2]  (per query tile)
-  const uint32_t s_full = bar0 + 16;                    // [2]
-  const uint32_t s_free = bar0 + 32;                    // [2]
-  const uint32_t p_full = bar0 + 48;                    // [2]
-  const uint32_t o_full = bar0 + 64;                    // [2]
-  const uint32_t kv_full = bar0 + 80;                   // [STAGES <= 4]
-  const uint32_t kv_empty = bar0 + 112;                 // [STAGES <= 4]
-  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - smem_base) + 144);
+  const uint32_t q_full = bar0;                         // [2 buffers][2 tiles]
+  const uint32_t s_full = bar0 + 32;                    // [2]  (per query tile)
+  const uint32_t s_free = bar0 + 48;                    // [2]
+  const uint32_t p_full = bar0 + 64;                    // [2]
+  const uint32_t o_full = bar0 + 80;                    // [2]
+  const uint32_t kv_full = bar0 + 96;                   // [STAGES <= 8]
+  const uint32_t kv_empty = bar0 + 160;                 // [STAGES <= 8]
+  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - smem_base) + 224);
   if ((smem_base & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5;
-  const int head = blockIdx.y, img = blockIdx.z;
   const int n_q_tiles = (p.Lq + ATT_BM - 1) / ATT_BM;
-  const int qt0 = blockIdx.x * 2;
-  const int nt = (qt0 + 1 < n_q_tiles) ? 2 : 1;         // query tiles this CTA owns (the last CTA of an odd count: one)
+  const int n_pairs = (n_q_tiles + 1) >> 1;
+  const int n_items = n_pairs * p.heads * p.n_img;      // item = (image, head, pair of query tiles), pair fastest
+  const int total = p.n_src * p.n_kv_tiles;             // key tiles per item
+  const int stride = gridDim.x;
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(q_full + 8 * i, 1);
     for (int t = 0; t < 2; ++t) {
-      mbar_init(q_full + 8 * t, 1);
       mbar_init(s_full + 8 * t, 1);
       mbar_init(s_free + 8 * t, 128);
       mbar_init(p_full + 8 * t, 128);
@@ -166,107 +181,180 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(kv_full + 8 * s, 1);
-      mbar_init(kv_empty + 8 * s, 1);
+      mbar_init(kv_empty + 8 * s, 2);       // two tcgen05.commit arrivals per key tile (one per query tile of the item)
     }
     fence_mbar_init();
   }
   if (warp == ISSUER) {
-    tmem_alloc(bar0 + 144, 2 * T_STRIDE);
+    tmem_alloc(bar0 + 224, 2 * T_STRIDE);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr_gen);
-  const int total = p.n_src * p.n_kv_tiles;
 
-  if (warp == ISSUER) {
-    // ---------------- TMA producer + UMMA issuer (warp-uniform control flow, one elected lane issues) ----------------
+  // tile t of an item exists unless the item is the last pair of an odd tile count and t == 1
+  auto tile_active = [&](int item, int t) { return ((item % n_pairs) * 2 + t) < n_q_tiles; };
+  // move a cursor of role-tile t to the next key tile it takes part in (items whose tile t does not exist are skipped whole)
+  auto advance = [&](PPCursor& c, int t) {
+    ++c.G;
+    if (++c.jt == p.n_kv_tiles) {
+      c.jt = 0;
+      if (++c.src == p.n_src) {
+        c.src = 0;
+        c.item += stride;
+        while (c.item < n_items && !tile_active(c.item, t)) { c.item += stride; c.G += total; }
+      }
+    }
+  };
+
+  if (warp >= ISSUER) {
+    // ---------------- UMMA issuer of query tile t = warp - ISSUER (warp-uniform control flow, one elected lane issues) ----------------
+    const int t = warp - ISSUER;
+    const bool producer = (t == 0);
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      for (int t = 0; t < nt; ++t) {
-        mbar_arrive_expect_tx(q_full + 8 * t, Q_TILE);
-        tma_load_3d(sQ + t * Q_TILE, &tmQ, q_full + 8 * t, p.q_col0 + head * p.q_hs, (qt0 + t) * ATT_BM, img);
-      }
     }
     __syncwarp();
-    auto produce = [&](int g) {
-      const int s = g % STAGES;
-      mbar_wait(kv_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
-      const int src = g / p.n_kv_tiles, jt = g - src * p.n_kv_tiles;
-      const int kv_img = p.kv_map ? p.kv_map[img * p.n_src + src] : img;
+    // ---- TMA producer state (issuer 0): the K/V tiles of ALL items of this CTA, in stream order
+    PPCursor pc{(int)blockIdx.x, 0, 0, 0};
+    int p_img = 0, p_head = 0, p_kvimg = 0;
+    auto p_decode = [&]() {
+      const int r = pc.item / n_pairs;
+      p_head = r % p.heads;
+      p_img = r / p.heads;
+      p_kvimg = p.kv_map ? p.kv_map[p_img * p.n_src + pc.src] : p_img;
+    };
+    if (producer) p_decode();
+    auto produce = [&]() {
+      if (pc.item >= n_items) return;
+      const int s = pc.G & SMASK;
+      mbar_wait(kv_empty + 8 * s, ((pc.G >> SSHIFT) & 1) ^ 1);
       const uint32_t sK = sKV + s * KV_STAGE_BYTES;
       if (elect_one()) {
         mbar_arrive_expect_tx(kv_full + 8 * s, KV_STAGE_BYTES);
-        tma_load_3d(sK, &tmK, kv_full + 8 * s, p.k_col0 + head * p.k_hs, jt * BN, kv_img);
-        tma_load_3d(sK + K_TILE, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs, jt * BN, kv_img);
+        tma_load_3d(sK, &tmK, kv_full + 8 * s, p.k_col0 + p_head * p.k_hs, pc.jt * BN, p_kvimg);
+        tma_load_3d(sK + K_TILE, &tmV, kv_full + 8 * s, p.v_col0 + p_head * p.v_hs, pc.jt * BN, p_kvimg);
+      }
+      __syncwarp();
+      const int item0 = pc.item, src0 = pc.src;
+      advance(pc, 0);
+      if (pc.item < n_items && (pc.item != item0 || pc.src != src0)) p_decode();
+    };
+    // ---- query tile loads: issuer t loads tile t of its li-th item into buffer li & 1
+    auto load_q = [&](int item, int li) {
+      if (item >= n_items) return;
+      const int r = item / n_pairs;
+      const int buf = li & 1;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full + 8 * (buf * 2 + t), Q_TILE);
+        tma_load_3d(sQ + (buf * 2 + t) * Q_TILE, &tmQ, q_full + 8 * (buf * 2 + t), p.q_col0 + (r % p.heads) * p.q_hs,
+                    ((item % n_pairs) * 2 + t) * ATT_BM, r / p.heads);
       }
       __syncwarp();
     };
-    // S_t(g) = Q_t K(g)^T  (both operands K-major inside one 64-column swizzle chunk)
-    auto issue_qk = [&](int t, int g) {
-      const uint32_t sK = sKV + (g % STAGES) * KV_STAGE_BYTES;
+    auto next_active_item = [&](int item) {
+      item += stride;
+      while (item < n_items && !tile_active(item, t)) item += stride;
+      return item;
+    };
+    // Every issuer walks EVERY key tile of the CTA's stream, so that it consumes the phases of the kv_full / kv_empty ring
+    // in order (an mbarrier parity wait is only meaningful within one phase of the barrier): for the items whose query tile
+    // t does not exist (last pair of an odd tile count, t == 1) it merely waits for the tile and releases it again.
+    auto advance_all = [&](PPCursor& c) {
+      ++c.G;
+      if (++c.jt == p.n_kv_tiles) {
+        c.jt = 0;
+        if (++c.src == p.n_src) { c.src = 0; c.item += stride; }
+      }
+    };
+    PPCursor cur{(int)blockIdx.x, 0, 0, 0};
+    bool act = tile_active(cur.item, t);                   // gridDim.x <= n_items: every CTA has a first item
+    load_q(act ? cur.item : next_active_item(cur.item), 0);
+    if (producer) {
+#pragma unroll 1
+      for (int i = 0; i < STAGES; ++i) produce();
+    }
+    const uint32_t tS = tmem_base + t * T_STRIDE, tP = tS + P_COL, tO = tS + O_COL;
+    const uint64_t dQ0 = umma_smem_desc(sQ + t * Q_TILE, 16, 1024, 2);      // + 2 per 16-column K step, + 2 Q tiles per buffer
+    const uint64_t dK0 = umma_smem_desc(sKV, 16, 1024, 2);                  // + 2 per K step, + STAGE16 per stage
+    const uint64_t dV0 = umma_smem_desc(sKV + K_TILE, K_TILE, 1024, 2);     // + 128 per 16 keys, + STAGE16 per stage
+    constexpr uint32_t STAGE16 = KV_STAGE_BYTES >> 4, QBUF16 = (2 * Q_TILE) >> 4;
+    const uint32_t b_sfull = s_full + 8 * t, b_sfree = s_free + 8 * t, b_pfull = p_full + 8 * t, b_ofull = o_full + 8 * t;
+    auto issue_qk = [&](const PPCursor& c, int li) {      // S_t = Q_t(item li) K(tile c)^T
+      const int s = c.G & SMASK;
+      mbar_wait(kv_full + 8 * s, (c.G >> SSHIFT) & 1);
+      tc_fence_after();
       if (elect_one()) {
+        const uint64_t dQ = dQ0 + (uint64_t)((li & 1) * QBUF16);
+        const uint64_t dK = dK0 + (uint64_t)(s * STAGE16);
 #pragma unroll
-        for (int kk = 0; kk < DQK / 16; ++kk)
-          umma_bf16(tmem_base + t * T_STRIDE, umma_smem_desc(sQ + t * Q_TILE + kk * 32, 16, 1024, 2),
-                    umma_smem_desc(sK + kk * 32, 16, 1024, 2), IDESC_S, kk != 0 ? 1u : 0u);
-        umma_commit(s_full + 8 * t);
+        for (int kk = 0; kk < DQK / 16; ++kk) umma_bf16(tS, dQ + 2 * kk, dK + 2 * kk, IDESC_S, kk != 0 ? 1u : 0u);
+        umma_commit(b_sfull);
       }
       __syncwarp();
     };
-    // O_t += P_t(g) V(g): A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major: rows = keys)
-    auto issue_pv = [&](int t, int g) {
-      const uint32_t sV = sKV + (g % STAGES) * KV_STAGE_BYTES + K_TILE;
-      const uint32_t acc0 = (g % p.n_kv_tiles) != 0 ? 1u : 0u;     // O accumulates in TMEM over one source
-      if (elect_one()) {
+    int li = 0;                 // index of the current (or next) active item among the items this issuer takes part in
+    uint32_t k = 0;             // key tiles issued for this query-tile slot so far (parity of the per-tile barriers)
+    bool qk_issued = false;     // has S_t of the tile under `cur` been issued already (look-ahead of the previous iteration)?
+#pragma unroll 1
+    while (cur.item < n_items) {
+      if (!act) {               // tile t of this item does not exist: consume the K/V tile's phase and release the stage
+        const int s = cur.G & SMASK;
+        mbar_wait(kv_full + 8 * s, (cur.G >> SSHIFT) & 1);
+        if (elect_one()) mbar_arrive(kv_empty + 8 * s);
+        __syncwarp();
+        const int item0 = cur.item;
+        advance_all(cur);
+        if (cur.item != item0 && cur.item < n_items) act = tile_active(cur.item, t);
+        continue;
+      }
+      const bool first = (cur.src == 0 && cur.jt == 0);
+      if (first) load_q(next_active_item(cur.item), li + 1);   // into the other buffer: the item that used it has retired
+      if (!qk_issued) {         // no look-ahead reached this tile (start of the stream, or the previous item was skipped)
+        if (first) mbar_wait(q_full + 8 * ((li & 1) * 2 + t), (li >> 1) & 1);
+        if (k > 0) mbar_wait(b_sfree, (k - 1) & 1);
+        tc_fence_after();
+        issue_qk(cur, li);
+      }
+      PPCursor nxt = cur;
+      advance_all(nxt);
+      const bool new_item = nxt.item != cur.item;
+      const bool nxt_act = nxt.item < n_items && (!new_item || tile_active(nxt.item, t));
+      // S_t(next tile) is issued as soon as the softmax warpgroup holds S_t(this tile) in registers
+      if (nxt_act) {
+        if (new_item) mbar_wait(q_full + 8 * (((li + 1) & 1) * 2 + t), ((li + 1) >> 1) & 1);
+        mbar_wait(b_sfree, k & 1);
+        tc_fence_after();
+        issue_qk(nxt, new_item ? li + 1 : li);
+      }
+      qk_issued = nxt_act;
+      mbar_wait(b_pfull, k & 1);
+      tc_fence_after();
+      const int s_cur = cur.G & SMASK;
+      if (elect_one()) {              // O_t += P_t V: A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major)
+        const uint64_t dV = dV0 + (uint64_t)(s_cur * STAGE16);
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk)
-          umma_bf16_ts(tmem_base + t * T_STRIDE + O_COL, tmem_base + t * T_STRIDE + P_COL + kk * 8,
-                       umma_smem_desc(sV + kk * 16 * 128, K_TILE, 1024, 2), IDESC_O, (kk != 0) ? 1u : acc0);
-        umma_commit(o_full + 8 * t);
+          umma_bf16_ts(tO, tP + kk * 8, dV + 128 * kk, IDESC_O, (kk != 0 || cur.jt != 0) ? 1u : 0u);   // O accumulates over one source
+        umma_commit(b_ofull);
+        umma_commit(kv_empty + 8 * s_cur);                 // the stage is free once the UMMAs of both issuers retired
       }
       __syncwarp();
-    };
-#pragma unroll 1
-    for (int g = 0; g < STAGES && g < total; ++g) produce(g);
-    mbar_wait(kv_full, 0);
-    tc_fence_after();
-    for (int t = 0; t < nt; ++t) {
-      mbar_wait(q_full + 8 * t, 0);
-      tc_fence_after();
-      issue_qk(t, 0);
+      // refill the stage released one key tile ago: its P V have retired (on both tiles), so the issuer does not sit on
+      // kv_empty while its softmax warpgroup waits for the next Q K^T / P V
+      if (producer && cur.G >= 1) produce();
+      if (new_item) { ++li; act = nxt_act; }               // li counts the active items started; an inactive item keeps it
+      cur = nxt;
+      ++k;
     }
-#pragma unroll 1
-    for (int g = 0; g < total; ++g) {
-      // S_t(g+1) is issued as soon as the softmax threads of tile t hold S_t(g) in registers
-      if (g + 1 < total) {
-        mbar_wait(kv_full + 8 * ((g + 1) % STAGES), ((g + 1) / STAGES) & 1);
-        tc_fence_after();
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(s_free + 8 * t, g & 1);
-          tc_fence_after();
-          issue_qk(t, g + 1);
-        }
-      }
-      for (int t = 0; t < nt; ++t) {
-        mbar_wait(p_full + 8 * t, g & 1);
-        tc_fence_after();
-        issue_pv(t, g);
-      }
-      if (elect_one()) umma_commit(kv_empty + 8 * (g % STAGES));   // stage free once QK/PV of both tiles retire
-      __syncwarp();
-      // refill the stage released ONE iteration ago: its P V have long retired, so the issuer never sits on kv_empty
-      // while the softmax warpgroups are waiting for their next Q K^T / P V to be issued
-      if (g >= 1 && g - 1 + STAGES < total) produce(g - 1 + STAGES);
-    }
-  } else if ((warp >> 2) < nt) {
+  } else {
     // ------------------------------- softmax / correction / epilogue of query tile t -------------------------------
     const int t = warp >> 2;
     const int row = threadIdx.x & 127;            // == TMEM lane
-    const int q_row = (qt0 + t) * ATT_BM + row;
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tmem_S = tmem_base + t * T_STRIDE + lane_sel;
     const uint32_t tmem_P = tmem_S + P_COL;
@@ -274,110 +362,120 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t bs_full = s_full + 8 * t, bs_free = s_free + 8 * t, bp_full = p_full + 8 * t, bo_full = o_full + 8 * t;
     const float sl2 = p.scale_log2e;
     const uint64_t SL2 = pack_f32x2(sl2, sl2);
-    bf16* orow = p.out + ((long long)img * p.Lq + q_row) * p.out_ld + head * p.o_hs;
-    int g = 0;
-    for (int src = 0; src < p.n_src; ++src) {
-      float m = -INFINITY, l = 0.f;
+    uint32_t k = 0;                               // key tiles processed by this warpgroup (parity of the per-tile barriers)
+    int item = blockIdx.x;
+    while (item < n_items && !tile_active(item, t)) item += stride;
 #pragma unroll 1
-      for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
-        mbar_wait(bs_full, g & 1);
-        tc_fence_after();
-        uint32_t sv[BN];
-        if constexpr (BN == 48) {
-          tmem_ld_32x32(tmem_S, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-          tmem_ld_32x16(tmem_S + 32, *reinterpret_cast<uint32_t(*)[16]>(&sv[32]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < BN; c += 32) tmem_ld_32x32(tmem_S + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bs_free);                      // S_t(g) now lives in registers -> the issuer starts S_t(g+1)
-        const int nvalid = p.Lk - jt * BN;         // keys >= nvalid in this tile are padding (warp-uniform)
-        if (nvalid < BN) {
-#pragma unroll
-          for (int j = 0; j < BN; ++j) sv[j] = (j < nvalid) ? sv[j] : 0xff800000u;   // -inf
-        }
-        // row maximum on four independent FMNMX3 chains
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < BN; j += 8) {
-          mx0 = fmax3(mx0, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(sv[j + 2]), __uint_as_float(sv[j + 3]));
-          mx2 = fmax3(mx2, __uint_as_float(sv[j + 4]), __uint_as_float(sv[j + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(sv[j + 6]), __uint_as_float(sv[j + 7]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        // lazy running max: only advanced (and O rescaled) when it grows by more than 2^8, so p <= 256
-        const float m_cand = fmaxf(m, mx * sl2);
-        const bool grow = __any_sync(0xffffffffu, m_cand > m + 8.f);   // warp-uniform (first tile: m = -inf)
-        float alpha = 1.f;
-        if (grow) {
-          alpha = fast_exp2(m - m_cand);
-          m = m_cand;
-          l *= alpha;
-        }
-        // p = exp2(s * scale * log2e - m) packed to bf16; row sum on four packed accumulators
-        const uint64_t NEGM = pack_f32x2(-m, -m);
-        uint64_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
-        uint32_t pk[BN / 2];
-#pragma unroll
-        for (int jp = 0; jp < BN / 2; ++jp) {
-          const uint64_t X = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * jp]), __uint_as_float(sv[2 * jp + 1])), SL2, NEGM);
-          float x0, x1, p0, p1;
-          unpack_f32x2(X, x0, x1);
-          if (POLY != 0 && (jp & 3) == 3) {
-            exp2_poly_pair(x0, x1, p0, p1);
-          } else {
-            p0 = fast_exp2(x0);
-            p1 = fast_exp2(x1);
-          }
-          const uint64_t PP = pack_f32x2(p0, p1);
-          const int u = jp & 3;
-          if (u == 0) acc0 = add_f32x2(acc0, PP);
-          if (u == 1) acc1 = add_f32x2(acc1, PP);
-          if (u == 2) acc2 = add_f32x2(acc2, PP);
-          if (u == 3) acc3 = add_f32x2(acc3, PP);
-          pk[jp] = pack_bf16(p0, p1);
-        }
-        {
-          float s0, s1;
-          unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
-          l += s0 + s1;
-        }
-        // the previous tile's P V must have retired before P is overwritten / O is rescaled
-        if (g > 0) {
-          mbar_wait(bo_full, (g - 1) & 1);
+    for (; item < n_items;) {
+      const int r = item / n_pairs;
+      const int q_row = ((item % n_pairs) * 2 + t) * ATT_BM + row;
+      bf16* orow = p.out + ((long long)(r / p.heads) * p.Lq + q_row) * p.out_ld + (r % p.heads) * p.o_hs;
+      for (int src = 0; src < p.n_src; ++src) {
+        float m = -INFINITY, l = 0.f;
+#pragma unroll 1
+        for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++k) {
+          mbar_wait(bs_full, k & 1);
           tc_fence_after();
-        }
-        if (grow && jt > 0) {
+          uint32_t sv[BN];
+          if constexpr (BN == 48) {
+            tmem_ld_32x32(tmem_S, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+            tmem_ld_32x16(tmem_S + 32, *reinterpret_cast<uint32_t(*)[16]>(&sv[32]));
+          } else {
 #pragma unroll
-          for (int c = 0; c < DVP; c += 16) {
-            uint32_t ov[16];
-            tmem_ld_32x16(tmem_O + c, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
-            tmem_st_32x16(tmem_O + c, ov);
+            for (int c = 0; c < BN; c += 32) tmem_ld_32x32(tmem_S + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
           }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bs_free);                      // S_t now lives in registers -> the issuer starts the next Q K^T
+          const int nvalid = p.Lk - jt * BN;         // keys >= nvalid in this tile are padding (warp-uniform)
+          if (nvalid < BN) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) sv[j] = (j < nvalid) ? sv[j] : 0xff800000u;   // -inf
+          }
+          // row maximum on four independent FMNMX3 chains
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < BN; j += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(sv[j + 2]), __uint_as_float(sv[j + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(sv[j + 4]), __uint_as_float(sv[j + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(sv[j + 6]), __uint_as_float(sv[j + 7]));
+          }
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+          // lazy running max: only advanced (and O rescaled) when it grows by more than 2^8, so p <= 256
+          const float m_cand = fmaxf(m, mx * sl2);
+          const bool grow = __any_sync(0xffffffffu, m_cand > m + 8.f);   // warp-uniform (first tile: m = -inf)
+          float alpha = 1.f;
+          if (grow) {
+            alpha = fast_exp2(m - m_cand);
+            m = m_cand;
+            l *= alpha;
+          }
+          // p = exp2(s * scale * log2e - m) packed to bf16; row sum on four packed accumulators
+          const uint64_t NEGM = pack_f32x2(-m, -m);
+          uint64_t acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+          uint32_t pk[BN / 2];
+#pragma unroll
+          for (int jp = 0; jp < BN / 2; ++jp) {
+            const uint64_t X = fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * jp]), __uint_as_float(sv[2 * jp + 1])), SL2, NEGM);
+            float x0, x1, p0, p1;
+            unpack_f32x2(X, x0, x1);
+            if (POLY != 0 && (jp & 3) == 3) {
+              exp2_poly_pair(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            const uint64_t PP = pack_f32x2(p0, p1);
+            const int u = jp & 3;
+            if (u == 0) acc0 = add_f32x2(acc0, PP);
+            if (u == 1) acc1 = add_f32x2(acc1, PP);
+            if (u == 2) acc2 = add_f32x2(acc2, PP);
+            if (u == 3) acc3 = add_f32x2(acc3, PP);
+            pk[jp] = pack_bf16(p0, p1);
+          }
+          {
+            float s0, s1;
+            unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
+            l += s0 + s1;
+          }
+          // the previous tile's P V must have retired before P is overwritten / O is rescaled
+          if (k > 0) {
+            mbar_wait(bo_full, (k - 1) & 1);
+            tc_fence_after();
+          }
+          if (grow && jt > 0) {
+#pragma unroll
+            for (int c = 0; c < DVP; c += 16) {
+              uint32_t ov[16];
+              tmem_ld_32x16(tmem_O + c, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * alpha);
+              tmem_st_32x16(tmem_O + c, ov);
+            }
+          }
+          if constexpr (BN == 48) {
+            tmem_st_32x16(tmem_P, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
+            tmem_st_32x8(tmem_P + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[16]));
+          } else if constexpr (BN == 64) {
+            tmem_st_32x32(tmem_P, pk);
+          } else {
+            tmem_st_32x16(tmem_P, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bp_full);
         }
-        if constexpr (BN == 48) {
-          tmem_st_32x16(tmem_P, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
-          tmem_st_32x8(tmem_P + 16, *reinterpret_cast<const uint32_t(*)[8]>(&pk[16]));
-        } else if constexpr (BN == 64) {
-          tmem_st_32x32(tmem_P, pk);
-        } else {
-          tmem_st_32x16(tmem_P, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
-        }
-        tmem_st_wait();
+        // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first).  The issuer is
+        // already feeding the next source / item: its first P V cannot start before this warpgroup's next p_full arrival.
+        mbar_wait(bo_full, (k - 1) & 1);
+        tc_fence_after();
+        store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0);
         tc_fence_before();
-        mbar_arrive(bp_full);
       }
-      // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first)
-      mbar_wait(bo_full, (g - 1) & 1);
-      tc_fence_after();
-      store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0);
-      tc_fence_before();
+      item += stride;
+      while (item < n_items && !tile_active(item, t)) item += stride;
     }
   }
   tc_fence_before();
@@ -680,7 +778,7 @@ static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t st
 
 template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
 static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)2 * ATT_BM * 128 + (size_t)STAGES * 2 * BN * 128 + 160;
+  constexpr size_t smem = (size_t)4 * ATT_BM * 128 + (size_t)STAGES * 2 * BN * 128 + 256;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   rc = make_tmap_3d_bf16(&tmQ, a->q, (uint64_t)a->q_cols, (uint64_t)a->lq, (uint64_t)a->n_img, (uint64_t)a->q_ld,
@@ -695,9 +793,12 @@ static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t st
   p.n_kv_tiles = (a->lk + BN - 1) / BN;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY>), (int)smem)) return e;
   const int n_q_tiles = (a->lq + ATT_BM - 1) / ATT_BM;
-  dim3 grid((n_q_tiles + 1) / 2, a->heads, a->n_img);
+  const long long n_items = (long long)((n_q_tiles + 1) / 2) * a->heads * a->n_img;
+  DD_CHECK(n_items < (1ll << 30), -1, "dd_attention: too many work items");
+  const int slots = 2 * num_sms();                        // persistent: two CTAs per SM
+  dim3 grid((unsigned)(n_items < slots ? n_items : slots));
   attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY><<<grid, PP_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
-  DD_CUDA(cudaGetLastError());
+  DD_CHECK(cudaGetLastError() == cudaSuccess, -2, "dd_attention: launch failed");
   return 0;
 }
 
@@ -719,6 +820,7 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   p.out = reinterpret_cast<bf16*>(a->out); p.out_ld = a->out_ld;
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.q_hs = a->q_head_stride; p.k_hs = a->k_head_stride; p.v_hs = a->v_head_stride; p.o_hs = a->head_dim;
+  p.heads = a->heads; p.n_img = a->n_img;
   switch (a->head_dim) {
     case 40:
       DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
