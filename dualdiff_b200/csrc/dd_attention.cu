@@ -46,6 +46,26 @@ struct AttnDev {
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// Timeline instrumentation of attn_pp_kernel for profiles/attn_trace.py: only in a -DDD_ATTN_TRACE build (never in the shipped
+// library).  Lane 0 of the first warp of each role of ONE CTA records (event, warp, tile, SM clock) pairs.
+#ifdef DD_ATTN_TRACE
+// per-warp regions (no atomics: an event is one clock read and two fire-and-forget stores)
+__device__ unsigned long long g_attn_trace[10 * 2 * 4096];
+#define DD_TR_DECL unsigned int tr_n_ = 0;
+#define DD_TR(ev, tile)                                                                                     \
+  do {                                                                                                      \
+    if (blockIdx.x == 7 && (threadIdx.x & 31) == 0 && tr_n_ < 4096u) {                                      \
+      unsigned long long* e_ = g_attn_trace + ((threadIdx.x >> 5) * 4096u + tr_n_) * 2u;                    \
+      e_[0] = ((unsigned long long)(ev) << 48) | ((unsigned long long)(threadIdx.x >> 5) << 32) | (unsigned)(tile); \
+      e_[1] = clock64();                                                                                    \
+      ++tr_n_;                                                                                              \
+    }                                                                                                       \
+  } while (0)
+#else
+#define DD_TR_DECL
+#define DD_TR(ev, tile) do { } while (0)
+#endif
+
 // 2^x for a pair of fp32 values on the FMA pipe (Cody-Waite split + degree-3 polynomial, max rel. error 7.5e-5 -- below the
 // bf16 rounding of P).  x <= ~8 (lazy running max), clamped below at -126.
 __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, float& r1) {
@@ -120,24 +140,20 @@ __device__ __forceinline__ void store_o_row(uint32_t tmem_o_row, float inv, bf16
 //   * key tiles are 48 wide: S (48 columns) + P (24) + O (48) = 120 TMEM columns per query tile, 256 per CTA, and the
 //     48 scores + 24 packed probabilities of a row fit the 96 registers two 320-thread CTAs leave per thread;
 //   * the CTAs are PERSISTENT (grid = 2 x SMs): a CTA walks the items  blockIdx.x, blockIdx.x + gridDim.x, ...  as ONE stream
-//     of K/V tiles through the TMA ring, with the query tiles double-buffered, so barrier set-up, TMEM allocation and the
-//     first Q / K / V round trip (13 % of a CTA's life when every item was its own CTA) are paid once per CTA and the
-//     epilogue of an item overlaps the first key tiles of the next;
+//     of K/V tiles through a six-stage TMA ring, so barrier set-up, TMEM allocation and the first K / V round trip are paid
+//     once per CTA and the epilogue of an item overlaps the first key tiles of the next; the query tile of the next item is
+//     reloaded while the softmax warpgroup works on the last key tile of the current one;
 //   * POLY: one pair of every four is exponentiated on the FMA pipe (exp2_poly_pair) instead of the MUFU pipe, which then
 //     has 25 % fewer operations; with four warps per scheduler the polynomial of one warp overlaps the MUFU stream of the
 //     others (the all-or-nothing and same-warp forms measured slower in round 1).
 // TMEM columns of query tile t (base t * 128): S [0, BN) | P [BN, BN + BN/2) | O [BN + BN/2, BN + BN/2 + DVP).
 // ---------------------------------------------------------------------------------------------------------------
-struct PPCursor {       // position of one role in the CTA's stream of key tiles: (item, source, key tile) + running tile index
-  int item, src, jt, G;
-};
-
 template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
 __global__ void __launch_bounds__(PP_THREADS, 2)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
   static_assert(DQK <= 64 && DVP <= 64 && DQK % 16 == 0 && DVP % 16 == 0, "one 64-column swizzle chunk per operand");
-  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 64 && (STAGES == 4 || STAGES == 8), "key tile / ring geometry");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 64 && STAGES >= 3 && STAGES <= 8, "key tile / ring geometry");
   constexpr int Q_TILE = ATT_BM * 128;                  // bytes: 128 query rows x 64 bf16
   constexpr int K_TILE = BN * 128;                      // bytes: BN key rows x 64 bf16 (a multiple of the 1024-byte swizzle atom)
   constexpr int KV_STAGE_BYTES = 2 * K_TILE;
@@ -145,26 +161,26 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   constexpr int P_COL = BN, O_COL = BN + BN / 2;
   static_assert(O_COL + DVP <= T_STRIDE && K_TILE % 1024 == 0, "TMEM / swizzle geometry");
   constexpr int ISSUER = 8;                             // warps 8, 9: UMMA issuers of tile 0, 1 (warp 8 also runs the TMA loads)
-  constexpr int SMASK = STAGES - 1, SSHIFT = (STAGES == 4) ? 2 : 3;
   constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, BN, 0, 0);
   constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, DVP, 0, 1);  // B (=V) is MN-major
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t sQ = smem_base;                        // [2 buffers][2 tiles] query tiles
-  const uint32_t sKV = sQ + 4 * Q_TILE;                 // [STAGES] {K tile, V tile}
+  const uint32_t sQ = smem_base;                        // [2] query tiles
+  const uint32_t sKV = sQ + 2 * Q_TILE;                 // [STAGES] {K tile, V tile}
   const uint32_t bar0 = sKV + STAGES * KV_STAGE_BYTES;
-  const uint32_t q_full = bar0;                         // [2 buffers][2 tiles]
-  const uint32_t s_full = bar0 + 32;                    // [2]  (per query tile)
-  const uint32_t s_free = bar0 + 48;                    // [2]
-  const uint32_t p_full = bar0 + 64;                    // [2]
-  const uint32_t o_full = bar0 + 80;                    // [2]
-  const uint32_t kv_full = bar0 + 96;                   // [STAGES <= 8]
-  const uint32_t kv_empty = bar0 + 160;                 // [STAGES <= 8]
-  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - smem_base) + 224);
+  const uint32_t q_full = bar0;                         // [2]  (per query tile)
+  const uint32_t s_full = bar0 + 16;                    // [2]
+  const uint32_t s_free = bar0 + 32;                    // [2]
+  const uint32_t p_full = bar0 + 48;                    // [2]
+  const uint32_t o_full = bar0 + 64;                    // [2]
+  const uint32_t kv_full = bar0 + 80;                   // [STAGES <= 8]
+  const uint32_t kv_empty = bar0 + 144;                 // [STAGES <= 8]
+  uint32_t* tmem_ptr_gen = reinterpret_cast<uint32_t*>(smem_raw + (bar0 - smem_base) + 208);
   if ((smem_base & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5;
+  DD_TR_DECL
   const int n_q_tiles = (p.Lq + ATT_BM - 1) / ATT_BM;
   const int n_pairs = (n_q_tiles + 1) >> 1;
   const int n_items = n_pairs * p.heads * p.n_img;      // item = (image, head, pair of query tiles), pair fastest
@@ -172,8 +188,8 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int stride = gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(q_full + 8 * i, 1);
     for (int t = 0; t < 2; ++t) {
+      mbar_init(q_full + 8 * t, 1);
       mbar_init(s_full + 8 * t, 1);
       mbar_init(s_free + 8 * t, 128);
       mbar_init(p_full + 8 * t, 128);
@@ -181,12 +197,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(kv_full + 8 * s, 1);
-      mbar_init(kv_empty + 8 * s, 2);       // two tcgen05.commit arrivals per key tile (one per query tile of the item)
+      mbar_init(kv_empty + 8 * s, 2);       // two arrivals per key tile: one per issuing warp
     }
     fence_mbar_init();
   }
   if (warp == ISSUER) {
-    tmem_alloc(bar0 + 224, 2 * T_STRIDE);
+    tmem_alloc(bar0 + 208, 2 * T_STRIDE);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -196,21 +212,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   // tile t of an item exists unless the item is the last pair of an odd tile count and t == 1
   auto tile_active = [&](int item, int t) { return ((item % n_pairs) * 2 + t) < n_q_tiles; };
-  // move a cursor of role-tile t to the next key tile it takes part in (items whose tile t does not exist are skipped whole)
-  auto advance = [&](PPCursor& c, int t) {
-    ++c.G;
-    if (++c.jt == p.n_kv_tiles) {
-      c.jt = 0;
-      if (++c.src == p.n_src) {
-        c.src = 0;
-        c.item += stride;
-        while (c.item < n_items && !tile_active(c.item, t)) { c.item += stride; c.G += total; }
-      }
-    }
-  };
 
   if (warp >= ISSUER) {
     // ---------------- UMMA issuer of query tile t = warp - ISSUER (warp-uniform control flow, one elected lane issues) ----------------
+    // The timeline of a CTA (profiles/attn_trace.py) showed the issuing warp, not the softmax warpgroups, setting the pace when
+    // its loop carried a generic (item, source, tile) cursor: 207 instructions and ~2700 cycles per key tile (a ready
+    // mbarrier.try_wait alone costs ~90 cycles, every tcgen05 / TMA instruction ~50) against ~1400 cycles of softmax work.
+    // Hence the shape below: all item-level decisions (integer divisions, query-tile loads, single-tile items) sit in the outer
+    // loop; the inner loop over the key tiles of one item only waits, issues and counts.
     const int t = warp - ISSUER;
     const bool producer = (t == 0);
     if (elect_one()) {
@@ -219,39 +228,42 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tma_prefetch_desc(&tmV);
     }
     __syncwarp();
-    // ---- TMA producer state (issuer 0): the K/V tiles of ALL items of this CTA, in stream order
-    PPCursor pc{(int)blockIdx.x, 0, 0, 0};
-    int p_img = 0, p_head = 0, p_kvimg = 0;
+    // ---- TMA producer (issuer 0): the K/V tiles of ALL items of this CTA in stream order, STAGES - 1 tiles ahead of the UMMAs
+    int p_item = blockIdx.x, p_src = 0, p_jt = 0, p_row = 0, p_kcol = 0, p_vcol = 0, p_kvimg = 0;
+    uint32_t p_s = 0, p_ph = 1;
     auto p_decode = [&]() {
-      const int r = pc.item / n_pairs;
-      p_head = r % p.heads;
-      p_img = r / p.heads;
-      p_kvimg = p.kv_map ? p.kv_map[p_img * p.n_src + pc.src] : p_img;
+      const int r = p_item / n_pairs;
+      const int hd = r % p.heads, im = r / p.heads;
+      p_kcol = p.k_col0 + hd * p.k_hs;
+      p_vcol = p.v_col0 + hd * p.v_hs;
+      p_kvimg = p.kv_map ? p.kv_map[im * p.n_src + p_src] : im;
     };
     if (producer) p_decode();
     auto produce = [&]() {
-      if (pc.item >= n_items) return;
-      const int s = pc.G & SMASK;
-      mbar_wait(kv_empty + 8 * s, ((pc.G >> SSHIFT) & 1) ^ 1);
-      const uint32_t sK = sKV + s * KV_STAGE_BYTES;
+      if (p_item >= n_items) return;
+      mbar_wait(kv_empty + 8 * p_s, p_ph);
       if (elect_one()) {
-        mbar_arrive_expect_tx(kv_full + 8 * s, KV_STAGE_BYTES);
-        tma_load_3d(sK, &tmK, kv_full + 8 * s, p.k_col0 + p_head * p.k_hs, pc.jt * BN, p_kvimg);
-        tma_load_3d(sK + K_TILE, &tmV, kv_full + 8 * s, p.v_col0 + p_head * p.v_hs, pc.jt * BN, p_kvimg);
+        const uint32_t sK = sKV + p_s * KV_STAGE_BYTES;
+        mbar_arrive_expect_tx(kv_full + 8 * p_s, KV_STAGE_BYTES);
+        tma_load_3d(sK, &tmK, kv_full + 8 * p_s, p_kcol, p_row, p_kvimg);
+        tma_load_3d(sK + K_TILE, &tmV, kv_full + 8 * p_s, p_vcol, p_row, p_kvimg);
       }
       __syncwarp();
-      const int item0 = pc.item, src0 = pc.src;
-      advance(pc, 0);
-      if (pc.item < n_items && (pc.item != item0 || pc.src != src0)) p_decode();
+      if (++p_s == STAGES) { p_s = 0; p_ph ^= 1; }
+      p_row += BN;
+      if (++p_jt == p.n_kv_tiles) {          // next source / next item: rare
+        p_jt = 0;
+        p_row = 0;
+        if (++p_src == p.n_src) { p_src = 0; p_item += stride; }
+        if (p_item < n_items) p_decode();
+      }
     };
-    // ---- query tile loads: issuer t loads tile t of its li-th item into buffer li & 1
-    auto load_q = [&](int item, int li) {
-      if (item >= n_items) return;
+    // ---- query tile t of an item (one buffer per tile: reloaded when the last Q K^T of the previous item has retired)
+    auto load_q = [&](int item) {
       const int r = item / n_pairs;
-      const int buf = li & 1;
       if (elect_one()) {
-        mbar_arrive_expect_tx(q_full + 8 * (buf * 2 + t), Q_TILE);
-        tma_load_3d(sQ + (buf * 2 + t) * Q_TILE, &tmQ, q_full + 8 * (buf * 2 + t), p.q_col0 + (r % p.heads) * p.q_hs,
+        mbar_arrive_expect_tx(q_full + 8 * t, Q_TILE);
+        tma_load_3d(sQ + t * Q_TILE, &tmQ, q_full + 8 * t, p.q_col0 + (r % p.heads) * p.q_hs,
                     ((item % n_pairs) * 2 + t) * ATT_BM, r / p.heads);
       }
       __syncwarp();
@@ -261,35 +273,29 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       while (item < n_items && !tile_active(item, t)) item += stride;
       return item;
     };
-    // Every issuer walks EVERY key tile of the CTA's stream, so that it consumes the phases of the kv_full / kv_empty ring
-    // in order (an mbarrier parity wait is only meaningful within one phase of the barrier): for the items whose query tile
-    // t does not exist (last pair of an odd tile count, t == 1) it merely waits for the tile and releases it again.
-    auto advance_all = [&](PPCursor& c) {
-      ++c.G;
-      if (++c.jt == p.n_kv_tiles) {
-        c.jt = 0;
-        if (++c.src == p.n_src) { c.src = 0; c.item += stride; }
-      }
-    };
-    PPCursor cur{(int)blockIdx.x, 0, 0, 0};
-    bool act = tile_active(cur.item, t);                   // gridDim.x <= n_items: every CTA has a first item
-    load_q(act ? cur.item : next_active_item(cur.item), 0);
+    int item = blockIdx.x;                                   // gridDim.x <= n_items: every CTA has a first item
+    {
+      const int first = tile_active(item, t) ? item : next_active_item(item);
+      if (first < n_items) load_q(first);
+    }
     if (producer) {
 #pragma unroll 1
-      for (int i = 0; i < STAGES; ++i) produce();
+      for (int i = 0; i < STAGES - 1; ++i) produce();
     }
     const uint32_t tS = tmem_base + t * T_STRIDE, tP = tS + P_COL, tO = tS + O_COL;
-    const uint64_t dQ0 = umma_smem_desc(sQ + t * Q_TILE, 16, 1024, 2);      // + 2 per 16-column K step, + 2 Q tiles per buffer
+    const uint64_t dQ = umma_smem_desc(sQ + t * Q_TILE, 16, 1024, 2);       // + 2 per 16-column K step
     const uint64_t dK0 = umma_smem_desc(sKV, 16, 1024, 2);                  // + 2 per K step, + STAGE16 per stage
     const uint64_t dV0 = umma_smem_desc(sKV + K_TILE, K_TILE, 1024, 2);     // + 128 per 16 keys, + STAGE16 per stage
-    constexpr uint32_t STAGE16 = KV_STAGE_BYTES >> 4, QBUF16 = (2 * Q_TILE) >> 4;
+    constexpr uint32_t STAGE16 = KV_STAGE_BYTES >> 4;
     const uint32_t b_sfull = s_full + 8 * t, b_sfree = s_free + 8 * t, b_pfull = p_full + 8 * t, b_ofull = o_full + 8 * t;
-    auto issue_qk = [&](const PPCursor& c, int li) {      // S_t = Q_t(item li) K(tile c)^T
-      const int s = c.G & SMASK;
-      mbar_wait(kv_full + 8 * s, (c.G >> SSHIFT) & 1);
+    uint32_t s_cur = 0, ph_cur = 0;   // ring stage / phase of the key tile whose P V comes next
+    uint32_t k = 0;                   // key tiles issued for this query-tile slot (parity of the per-tile barriers)
+    uint32_t n_q = 0;                 // query tiles loaded so far by this issuer (parity of q_full)
+    // S_t = Q_t K(stage s)^T
+    auto issue_qk = [&](uint32_t s, uint32_t ph) {
+      mbar_wait(kv_full + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t dQ = dQ0 + (uint64_t)((li & 1) * QBUF16);
         const uint64_t dK = dK0 + (uint64_t)(s * STAGE16);
 #pragma unroll
         for (int kk = 0; kk < DQK / 16; ++kk) umma_bf16(tS, dQ + 2 * kk, dK + 2 * kk, IDESC_S, kk != 0 ? 1u : 0u);
@@ -297,59 +303,70 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       __syncwarp();
     };
-    int li = 0;                 // index of the current (or next) active item among the items this issuer takes part in
-    uint32_t k = 0;             // key tiles issued for this query-tile slot so far (parity of the per-tile barriers)
-    bool qk_issued = false;     // has S_t of the tile under `cur` been issued already (look-ahead of the previous iteration)?
-#pragma unroll 1
-    while (cur.item < n_items) {
-      if (!act) {               // tile t of this item does not exist: consume the K/V tile's phase and release the stage
-        const int s = cur.G & SMASK;
-        mbar_wait(kv_full + 8 * s, (cur.G >> SSHIFT) & 1);
-        if (elect_one()) mbar_arrive(kv_empty + 8 * s);
-        __syncwarp();
-        const int item0 = cur.item;
-        advance_all(cur);
-        if (cur.item != item0 && cur.item < n_items) act = tile_active(cur.item, t);
-        continue;
-      }
-      const bool first = (cur.src == 0 && cur.jt == 0);
-      if (first) load_q(next_active_item(cur.item), li + 1);   // into the other buffer: the item that used it has retired
-      if (!qk_issued) {         // no look-ahead reached this tile (start of the stream, or the previous item was skipped)
-        if (first) mbar_wait(q_full + 8 * ((li & 1) * 2 + t), (li >> 1) & 1);
-        if (k > 0) mbar_wait(b_sfree, (k - 1) & 1);
-        tc_fence_after();
-        issue_qk(cur, li);
-      }
-      PPCursor nxt = cur;
-      advance_all(nxt);
-      const bool new_item = nxt.item != cur.item;
-      const bool nxt_act = nxt.item < n_items && (!new_item || tile_active(nxt.item, t));
-      // S_t(next tile) is issued as soon as the softmax warpgroup holds S_t(this tile) in registers
-      if (nxt_act) {
-        if (new_item) mbar_wait(q_full + 8 * (((li + 1) & 1) * 2 + t), ((li + 1) >> 1) & 1);
-        mbar_wait(b_sfree, k & 1);
-        tc_fence_after();
-        issue_qk(nxt, new_item ? li + 1 : li);
-      }
-      qk_issued = nxt_act;
+    // O_t (+)= P_t V(stage s): A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major)
+    auto issue_pv = [&](uint32_t s, bool accumulate) {
       mbar_wait(b_pfull, k & 1);
       tc_fence_after();
-      const int s_cur = cur.G & SMASK;
-      if (elect_one()) {              // O_t += P_t V: A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major)
-        const uint64_t dV = dV0 + (uint64_t)(s_cur * STAGE16);
+      if (elect_one()) {
+        const uint64_t dV = dV0 + (uint64_t)(s * STAGE16);
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          umma_bf16_ts(tO, tP + kk * 8, dV + 128 * kk, IDESC_O, (kk != 0 || cur.jt != 0) ? 1u : 0u);   // O accumulates over one source
+        for (int kk = 0; kk < BN / 16; ++kk) umma_bf16_ts(tO, tP + kk * 8, dV + 128 * kk, IDESC_O, (kk != 0 || accumulate) ? 1u : 0u);
         umma_commit(b_ofull);
-        umma_commit(kv_empty + 8 * s_cur);                 // the stage is free once the UMMAs of both issuers retired
+        umma_commit(kv_empty + 8 * s);                     // the stage is free once the UMMAs of both issuers retired
       }
       __syncwarp();
-      // refill the stage released one key tile ago: its P V have retired (on both tiles), so the issuer does not sit on
-      // kv_empty while its softmax warpgroup waits for the next Q K^T / P V
-      if (producer && cur.G >= 1) produce();
-      if (new_item) { ++li; act = nxt_act; }               // li counts the active items started; an inactive item keeps it
-      cur = nxt;
-      ++k;
+    };
+#pragma unroll 1
+    for (; item < n_items; item += stride) {
+      if (!tile_active(item, t)) {
+        // tile t of this item does not exist (last pair of an odd tile count): walk its K/V tiles anyway so that this issuer
+        // consumes the phases of the kv ring in order (a parity wait is only meaningful within one phase), releasing each
+#pragma unroll 1
+        for (int i = 0; i < total; ++i) {
+          mbar_wait(kv_full + 8 * s_cur, ph_cur);
+          if (elect_one()) mbar_arrive(kv_empty + 8 * s_cur);
+          __syncwarp();
+          if (++s_cur == STAGES) { s_cur = 0; ph_cur ^= 1; }
+        }
+        continue;
+      }
+      // first key tile of the item: its Q K^T waits for the query tile (loaded while the previous item was finishing)
+      mbar_wait(q_full + 8 * t, n_q & 1);
+      ++n_q;
+      if (k > 0) mbar_wait(b_sfree, (k - 1) & 1);          // S_t of the previous item's last tile is in registers
+      tc_fence_after();
+      issue_qk(s_cur, ph_cur);
+      int jt = 0;
+#pragma unroll 1
+      for (int i = 0; i < total; ++i) {
+        DD_TR(10, k);
+        uint32_t s_nxt = s_cur + 1, ph_nxt = ph_cur;
+        if (s_nxt == STAGES) { s_nxt = 0; ph_nxt ^= 1; }
+        if (i + 1 < total) {
+          // S_t(next tile) is issued as soon as the softmax warpgroup holds S_t(this tile) in registers
+          mbar_wait(b_sfree, k & 1);
+          tc_fence_after();
+          DD_TR(11, k);
+          issue_qk(s_nxt, ph_nxt);
+          DD_TR(12, k);
+        } else {
+          // last key tile of the item: once its S is in registers every Q K^T of the item has retired -> reload the query tile
+          const int nxt = next_active_item(item);
+          if (nxt < n_items) {
+            mbar_wait(b_sfree, k & 1);
+            load_q(nxt);
+          }
+        }
+        // refill the ring while the softmax warpgroup is still exponentiating this tile
+        if (producer) produce();
+        DD_TR(15, k);
+        issue_pv(s_cur, jt != 0);
+        DD_TR(16, k);
+        if (++jt == p.n_kv_tiles) jt = 0;
+        s_cur = s_nxt;
+        ph_cur = ph_nxt;
+        ++k;
+      }
     }
   } else {
     // ------------------------------- softmax / correction / epilogue of query tile t -------------------------------
@@ -374,8 +391,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float m = -INFINITY, l = 0.f;
 #pragma unroll 1
         for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++k) {
+          DD_TR(0, k);
           mbar_wait(bs_full, k & 1);
           tc_fence_after();
+          DD_TR(1, k);
           uint32_t sv[BN];
           if constexpr (BN == 48) {
             tmem_ld_32x32(tmem_S, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
@@ -387,6 +406,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(bs_free);                      // S_t now lives in registers -> the issuer starts the next Q K^T
+          DD_TR(2, k);
           const int nvalid = p.Lk - jt * BN;         // keys >= nvalid in this tile are padding (warp-uniform)
           if (nvalid < BN) {
 #pragma unroll
@@ -439,11 +459,13 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
             l += s0 + s1;
           }
+          DD_TR(3, k);
           // the previous tile's P V must have retired before P is overwritten / O is rescaled
           if (k > 0) {
             mbar_wait(bo_full, (k - 1) & 1);
             tc_fence_after();
           }
+          DD_TR(4, k);
           if (grow && jt > 0) {
 #pragma unroll
             for (int c = 0; c < DVP; c += 16) {
@@ -466,6 +488,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bp_full);
+          DD_TR(5, k);
         }
         // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first).  The issuer is
         // already feeding the next source / item: its first P V cannot start before this warpgroup's next p_full arrival.
@@ -473,6 +496,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0);
         tc_fence_before();
+        DD_TR(6, k);
       }
       item += stride;
       while (item < n_items && !tile_active(item, t)) item += stride;
@@ -778,7 +802,7 @@ static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t st
 
 template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
 static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t stream) {
-  constexpr size_t smem = (size_t)4 * ATT_BM * 128 + (size_t)STAGES * 2 * BN * 128 + 256;
+  constexpr size_t smem = (size_t)2 * ATT_BM * 128 + (size_t)STAGES * 2 * BN * 128 + 256;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   rc = make_tmap_3d_bf16(&tmQ, a->q, (uint64_t)a->q_cols, (uint64_t)a->lq, (uint64_t)a->n_img, (uint64_t)a->q_ld,
@@ -795,8 +819,13 @@ static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t st
   const int n_q_tiles = (a->lq + ATT_BM - 1) / ATT_BM;
   const long long n_items = (long long)((n_q_tiles + 1) / 2) * a->heads * a->n_img;
   DD_CHECK(n_items < (1ll << 30), -1, "dd_attention: too many work items");
-  const int slots = 2 * num_sms();                        // persistent: two CTAs per SM
-  dim3 grid((unsigned)(n_items < slots ? n_items : slots));
+  // Short K/V streams (text / SFA cross-attention: 2-3 key tiles per item) run PERSISTENT, two CTAs per SM, so that barrier
+  // set-up, TMEM allocation and the first Q / K / V round trip are paid once per CTA (170 -> 124 us per level-0 text launch).
+  // Long streams (self / cross-view: 30-120 key tiles per item) launch one CTA per item: the hardware's dynamic CTA scheduling
+  // balances the SMs better than a static round-robin (measured 539 vs 565 us per level-0 self-attention launch).
+  const int slots = 2 * num_sms();
+  const bool persistent = a->n_src * p.n_kv_tiles <= 8;
+  dim3 grid((unsigned)((n_items < slots || !persistent) ? n_items : slots));
   attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY><<<grid, PP_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
   DD_CHECK(cudaGetLastError() == cudaSuccess, -2, "dd_attention: launch failed");
   return 0;
@@ -812,7 +841,7 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   DD_CHECK(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->out_ld % 8 == 0, -1,
            "dd_attention: leading dims must be multiples of 8");
   DD_CHECK(a->n_kv_img > 0, -1, "dd_attention: n_kv_img missing");
-  DD_CHECK(a->variant >= 0 && a->variant <= 3, -1, "dd_attention: variant must be 0 (auto), 1, 2 or 3");
+  DD_CHECK(a->variant >= 0 && a->variant <= 2, -1, "dd_attention: variant must be 0 (auto), 1 or 2");
   AttnDev p;
   p.Lq = a->lq; p.Lk = a->lk; p.n_src = a->n_src; p.n_kv_tiles = 0;
   p.kv_map = a->kv_map;
@@ -826,8 +855,8 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
       DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
                "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
       if (a->variant == 1) return launch_attn_v2<48, 40, 48, 128, 3, 2>(a, p, stream);   // testing hook: one-tile kernel
-      if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 4, 0>(a, p, stream);     // testing hook: all ex2 on MUFU
-      return launch_attn_pp<48, 40, 48, 48, 4, 1>(a, p, stream);
+      if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 6, 0>(a, p, stream);     // testing hook: all ex2 on MUFU
+      return launch_attn_pp<48, 40, 48, 48, 6, 1>(a, p, stream);
     case 80: return launch_attn_v2<80, 80, 80, 64, 2, 2>(a, p, stream);
     case 160: return launch_attn_v2<160, 160, 160, 64, 1, 2>(a, p, stream);
   }
@@ -835,3 +864,14 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dd
+
+#ifdef DD_ATTN_TRACE
+// trace builds only (profiles/attn_trace.py): copy out and clear the per-warp timelines of attn_pp_kernel (10 x 4096 events)
+extern "C" __attribute__((visibility("default"))) int dd_attn_trace_read(unsigned long long* dst) {
+  if (cudaMemcpyFromSymbol(dst, dd::g_attn_trace, sizeof(dd::g_attn_trace)) != cudaSuccess) return -1;
+  void* sym = nullptr;
+  if (cudaGetSymbolAddress(&sym, dd::g_attn_trace) != cudaSuccess) return -1;
+  cudaMemset(sym, 0, sizeof(dd::g_attn_trace));
+  return 10 * 4096;
+}
+#endif

@@ -37,7 +37,7 @@ def timed(kind, variant, reps=8):
 
 
 kinds = [os.environ["ONLY"]] if os.environ.get("ONLY") else ["self", "xview", "text"]
-variants = [int(os.environ["VARIANT"])] if os.environ.get("VARIANT") else [1, 2, 0]
+variants = [int(v) for v in os.environ["VARIANT"].split(",")] if os.environ.get("VARIANT") else [1, 2, 0]
 ref = {}
 for kind in kinds:
     lk, ns = (106, 1) if kind == "text" else (L, 2 if kind == "xview" else 1)
