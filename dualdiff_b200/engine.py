@@ -25,7 +25,23 @@ from . import ops
 from .packing import pack_conv1x1, pack_conv3x3, pack_conv3x3_patch, pack_geglu, pack_linear
 
 HEADS = 8
-NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  # configs/dataset/Nuscenes.yaml:27-33
+NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  # configs/dataset/Nuscenes.yaml:27-33 (default)
+
+
+def check_view_pairs(pairs):
+    """the cross-view topology the kernels can run: every view lists the same number (1 or 2) of neighbour views, all inside
+    the view range.  Returns (pairs with int keys, neighbours per view).  Anything else raises instead of silently computing
+    the default ring (networks/blocks.py:106-121 builds the (view, neighbour) pairs from this table)."""
+    if pairs is None:
+        pairs = NEIGHBORS
+    pairs = {int(k): [int(x) for x in v] for k, v in pairs.items()}
+    n_cam = len(pairs)
+    counts = {len(v) for v in pairs.values()}
+    if sorted(pairs) != list(range(n_cam)) or len(counts) != 1 or next(iter(counts)) not in (1, 2) or \
+            any(not 0 <= x < n_cam for v in pairs.values() for x in v):
+        raise NotImplementedError(f"neighboring_view_pair {pairs}: the cross-view attention kernel needs views 0..n-1 with the "
+                                  "same number (1 or 2) of neighbours each")
+    return pairs, next(iter(counts))
 BF = torch.bfloat16
 
 
@@ -48,8 +64,9 @@ def pad_heads(w, d, dp):
 # packing
 # ---------------------------------------------------------------------------------------------------
 class Packer:
-    def __init__(self, sd: Dict[str, torch.Tensor], device):
+    def __init__(self, sd: Dict[str, torch.Tensor], device, n_nbr: int = 2):
         self.sd, self.dev, self.out = sd, device, {}
+        self.n_nbr = n_nbr            # neighbour views summed by the cross-view attention (to_out's bias counts once per neighbour)
 
     def f32(self, t):
         return t.detach().float().contiguous().to(self.dev)
@@ -113,7 +130,7 @@ class Packer:
             wo, bo = f("attn4.to_out.0.weight").double(), f("attn4.to_out.0.bias").double()
             wc, bc = f("connector.weight").double(), f("connector.bias").double()
             self.put(p + ".attn4.oc.w", (wc @ wo).float().to(BF))          # connector o to_out, fused
-            self.put(p + ".attn4.oc.b", self.f32(2.0 * (wc @ bo) + bc))    # bias counted twice (blocks.py:203-217)
+            self.put(p + ".attn4.oc.b", self.f32(float(self.n_nbr) * (wc @ bo) + bc))   # bias once per neighbour (blocks.py:203-217)
         if (p + ".attn_temp.to_q.weight") in self.sd:   # temporal block of the video configuration (BASELINE config 5)
             self.norm(p + ".norm_temp")
             self.attn_self(p + ".attn_temp", d)
@@ -156,8 +173,9 @@ class Packer:
         self.out["temb_total"] = off
 
 
-def pack_unet(sd, device):
-    pk = Packer(sd, device)
+def pack_unet(sd, device, neighboring_view_pair=None):
+    pairs, n_nbr = check_view_pairs(neighboring_view_pair)
+    pk = Packer(sd, device, n_nbr)
     tl: List[str] = []
     pk.encoder(True, tl)
     for i in range(4):
@@ -170,7 +188,25 @@ def pack_unet(sd, device):
     pk.norm("conv_norm_out")
     pk.conv3("conv_out")
     pk.temb(tl)
+    pk.out["view_pairs"] = pairs
+    pk.out["n_nbr"] = n_nbr
     return pk.out
+
+
+def pack_sfa(pk: "Packer", p="txt_con_fusion"):
+    """Semantic Fusion Attention (txt_con_fusion.py:27-33): 8 heads x 40, Q/K heads zero-padded to 48 columns"""
+    f = lambda n: pk.sd[f"{p}.{n}.weight"].detach().float()
+    pk.put(p + ".q.w", pad_heads(f("to_q"), 40, 48).to(BF))
+    pk.put(p + ".kv.w", torch.cat([pad_heads(f("to_k"), 40, 48), f("to_v")], 0).to(BF))
+    pk.lin(p + ".to_out.0")
+
+
+def pack_cond_embedding(pk: "Packer", e="controlnet_cond_embedding"):
+    """ControlNetConditioningEmbedding (map_embedder.py:81-112): conv_in (3 -> 16, channels padded to 8), 6 blocks, conv_out"""
+    pk.conv3(e + ".conv_in", pad_cin_to=8)
+    for i in range(6):
+        pk.conv3(f"{e}.blocks.{i}")
+    pk.conv3(e + ".conv_out")
 
 
 def pack_controlnet(sd, device, use_occ_3d: bool):
@@ -188,18 +224,9 @@ def pack_controlnet(sd, device, use_occ_3d: bool):
         pk.lin32("bbox_embedder." + n)
     for n in ("_class_tokens", "null_class_feature", "null_pos_feature"):
         pk.put("bbox_embedder." + n, pk.f32(sd["bbox_embedder." + n]))
-    # Semantic Fusion Attention (txt_con_fusion.py:27-33): 8 heads x 40
-    p = "txt_con_fusion"
-    f = lambda n: sd[f"{p}.{n}.weight"].detach().float()
-    pk.put(p + ".q.w", pad_heads(f("to_q"), 40, 48).to(BF))
-    pk.put(p + ".kv.w", torch.cat([pad_heads(f("to_k"), 40, 48), f("to_v")], 0).to(BF))
-    pk.lin(p + ".to_out.0")
+    pack_sfa(pk)
     if not use_occ_3d:
-        e = "controlnet_cond_embedding"
-        pk.conv3(e + ".conv_in", pad_cin_to=8)
-        for i in range(6):
-            pk.conv3(f"{e}.blocks.{i}")
-        pk.conv3(e + ".conv_out")
+        pack_cond_embedding(pk)
     pk.out["use_occ_3d"] = use_occ_3d
     return pk.out
 
@@ -232,6 +259,7 @@ class StepCtx:
     text_kv: Dict[str, torch.Tensor] = field(default_factory=dict)   # attn2 prefix -> [n*Lk, 8*dp + C]
     lk: int = 0
     kv_map: Optional[torch.Tensor] = None
+    n_nbr: int = 2                        # neighbour views per view (columns of kv_map)
     view_shard: Optional[object] = None   # sharding.ViewShard when camera views are split across ranks
     n_outer: int = 0                      # scenes x CFG halves (sharded mode)
     n_frames: int = 1                     # video clips: local frames per clip; images are ordered [clip][frame][view]
@@ -296,7 +324,7 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
         if ctx.view_shard is None:
             qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
             a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
-                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
         else:
             # camera views sharded across ranks: project locally, then fetch the two halo views' rows from the ring
             # neighbours straight into the tail of the projection buffer (the only exchange step of the path)
@@ -306,7 +334,7 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
             ops.gemm(ln, P[p + ".attn4.qkv.w"], out=buf[: n * T])
             vs.exchange(buf, ctx.n_outer, T)
             a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=vs.kv_rows(ctx.n_outer), lq=T, lk=T, heads=HEADS,
-                              head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=2)
+                              head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
     # 3b. temporal attention over the frames of the clip (no reference code: defined in csrc/dd_temporal.cu and
     #     oracle/dualdiff_oracle.py:temporal_attention); only packed for the video configuration
@@ -396,10 +424,15 @@ ATTN2_LAYERS_UNET = ATTN2_LAYERS_ENC + [f"up_blocks.{i}.attentions.{j}.transform
                                         for i in range(1, 4) for j in range(3)]
 
 
-def make_kv_map(n, n_cam, device):
-    """kv image of (query image, neighbour slot); view index = image index mod n_cam (blocks.py:196-197)"""
-    assert n % n_cam == 0 and n_cam == len(NEIGHBORS)
-    rows = [[(i // n_cam) * n_cam + nb for nb in NEIGHBORS[i % n_cam]] for i in range(n)]
+def make_kv_map(n, pairs, device):
+    """kv image of (query image, neighbour slot); view index = image index mod n_cam (blocks.py:196-197).
+    `pairs`: the model's neighboring_view_pair table (an int = that many views of the default ring, for callers without a model)"""
+    if isinstance(pairs, int):
+        assert pairs == len(NEIGHBORS), "an integer view count selects the default 6-view ring"
+        pairs = NEIGHBORS
+    n_cam = len(pairs)
+    assert n % n_cam == 0
+    rows = [[(i // n_cam) * n_cam + nb for nb in pairs[i % n_cam]] for i in range(n)]
     return torch.tensor(rows, dtype=torch.int32, device=device)
 
 
@@ -451,13 +484,16 @@ def camera_tokens(P, camera_param):
 
 
 def box_tokens(P, bboxes, classes, masks):
-    """bboxes (R, L, 8, 3), classes (R, L), masks (R, L) -> (R*L, 768) fp32   (bbox_embedder.py:155-203)"""
+    """bboxes (R, L, n_pts, 3), classes (R, L), masks (R, L) -> (R*L, 768) fp32   (bbox_embedder.py:155-203)"""
     R, L = classes.shape
     nb = R * L
     dev = bboxes.device
-    pos = torch.empty((nb, 216), device=dev, dtype=torch.float32)
+    n_pts = bboxes.shape[-2]                  # 8 box corners / map-vector points (40 after `reinitialize()`, bbox_embedder.py:122-130)
+    if P["bbox_embedder.bbox_proj.w32"].shape[1] != 27 * n_pts:
+        raise ValueError(f"bbox_embedder expects {P['bbox_embedder.bbox_proj.w32'].shape[1] // 27} points per box, got {n_pts}")
+    pos = torch.empty((nb, 27 * n_pts), device=dev, dtype=torch.float32)
     cat = torch.empty((nb, 768 + 768), device=dev, dtype=torch.float32)
-    ops.box_features(bboxes.reshape(nb, 8, 3).float().contiguous(), classes.reshape(-1).contiguous(),
+    ops.box_features(bboxes.reshape(nb, n_pts, 3).float().contiguous(), classes.reshape(-1).contiguous(),
                      masks.reshape(-1), P["bbox_embedder._class_tokens"], P["bbox_embedder.null_pos_feature"],
                      P["bbox_embedder.null_class_feature"], pos, cat[:, 768:])
     ops.linear_f32(pos, P["bbox_embedder.bbox_proj.w32"], P["bbox_embedder.bbox_proj.b32"], act=1, out=cat[:, :768])
@@ -480,7 +516,7 @@ def build_tokens(P, camera_param, text, bboxes_3d_data):
     n_box, L = bb.shape[1], bb.shape[2]
     if L == 0:
         return torch.cat([cam, txt], dim=2).reshape(b * n_cam, 78, 768).to(BF).contiguous()
-    tok = box_tokens(P, bb.reshape(b * n_box, L, 8, 3), cl.reshape(b * n_box, L), mk.reshape(b * n_box, L))
+    tok = box_tokens(P, bb.reshape(b * n_box, L, bb.shape[-2], 3), cl.reshape(b * n_box, L), mk.reshape(b * n_box, L))
     tok = tok.reshape(b, n_box, L, 768)
     if n_box != n_cam:
         tok = tok.expand(b, n_cam, L, 768)
@@ -511,18 +547,21 @@ def cond_embedding(P, cond, n_cam=6) -> Act:
     return Act(ops.gemm(pad, P[e + ".conv_out.w"], bias=P[e + ".conv_out.b"], taps=9, conv_hw=x.hw, n_img=n), n, x.H, x.W)
 
 
+def sfa_rows(P, cond_rows, txt_rows, n, T, L, p="txt_con_fusion") -> torch.Tensor:
+    """cond + W_o MHA(W_q cond, W_k txt, W_v txt) + b_o on rows: cond_rows [n*T, 320], txt_rows [n*L, 768] (the L text tokens
+    of every image, camera token already dropped) -> [n*T, 320]   (txt_con_fusion.py:110-177)"""
+    q = ops.gemm(cond_rows, P[p + ".q.w"])
+    kv = ops.gemm(txt_rows, P[p + ".kv.w"])
+    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48)
+    return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond_rows)
+
+
 def sfa(P, cond: Act, enc_rows, lk_total, n) -> torch.Tensor:
-    """Semantic Fusion Attention (txt_con_fusion.py:74-181): cond + W_o MHA(W_q cond, W_k txt, W_v txt) + b_o.
-    enc_rows: [n*(78+L), 768]; the 77 text tokens are rows 1..77 of each image (camera token dropped, :977)."""
-    p = "txt_con_fusion"
-    q = ops.gemm(cond.rows, P[p + ".q.w"])
-    kv = ops.gemm(enc_rows, P[p + ".kv.w"])   # projects all tokens; the attention reads rows 1..77 only
-    T = cond.H * cond.W
-    kv3 = kv.reshape(n, lk_total, kv.shape[1])[:, 1:78]
-    # a strided view cannot be addressed as [n*77, ld]; copy the 77-token window (plumbing, timestep-invariant)
-    kv77 = kv3.contiguous().reshape(n * 77, kv.shape[1])
-    a = ops.attention(q, kv77, kv77, n_img=n, lq=T, lk=77, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48)
-    return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond.rows)
+    """Semantic Fusion Attention inside a branch.  enc_rows: [n*(78+L), 768]; the 77 text tokens are rows 1..77 of each image
+    (camera token dropped, unet_addon_rawbox.py:977).  A strided window cannot be addressed as [n*77, ld]: the 77-token window
+    is copied once (plumbing, timestep-invariant)."""
+    txt = enc_rows.reshape(n, lk_total, enc_rows.shape[1])[:, 1:78].contiguous().reshape(n * 77, enc_rows.shape[1])
+    return sfa_rows(P, cond.rows, txt, n, cond.H * cond.W, 77)
 
 
 @dataclass

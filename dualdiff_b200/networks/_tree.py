@@ -13,6 +13,30 @@ class _NoForward(nn.Module):
         raise RuntimeError(f"{type(self).__name__} is a parameter container; the CUDA engine runs the math")
 
 
+class FusedAttnProcessor:
+    """The one attention implementation of this package: softmax(Q K^T * scale) V in the fused tcgen05 kernel
+    (csrc/dd_attention.cu).  It stands where the reference installs diffusers' `XFormersAttnProcessor`
+    (`enable_xformers_memory_efficient_attention`, misc/test_utils.py:164-165; protocol: box_adapter.py:33-40)."""
+
+    def __repr__(self):
+        return "FusedAttnProcessor(tcgen05)"
+
+
+# stock processors whose arithmetic is exactly what the fused kernel computes: installing one changes nothing
+_EQUIVALENT_PROCESSORS = ("AttnProcessor", "AttnProcessor2_0", "XFormersAttnProcessor", "FusedAttnProcessor")
+
+
+def check_attn_processor(processor):
+    """`set_attn_processor` / `set_processor` contract: None (default) or a processor with the stock arithmetic is accepted;
+    anything else would be silently ignored by the fused kernel, so it raises (no silent dispatch)."""
+    if processor is None or type(processor).__name__ in _EQUIVALENT_PROCESSORS:
+        return
+    raise NotImplementedError(
+        f"attention processor {type(processor).__name__!r} is not supported: dualdiff_b200 runs every attention in its fused "
+        "tcgen05 kernel and cannot call back into Python processors (e.g. box_adapter's Adapter_XFormersAttnProcessor, "
+        "which the reference itself asserts incompatible with the dual branch, runner/multiview_runner.py:240)")
+
+
 class Attention(_NoForward):
     """diffusers Attention parameter layout: to_q/to_k/to_v (no bias), to_out = [Linear(bias), Dropout]."""
 
@@ -25,10 +49,11 @@ class Attention(_NoForward):
         self.to_k = nn.Linear(kv_dim, inner, bias=bias)
         self.to_v = nn.Linear(kv_dim, inner, bias=bias)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
-        self.processor = None
+        self.processor = FusedAttnProcessor()
 
     def set_processor(self, processor):
-        self.processor = processor
+        check_attn_processor(processor)
+        self.processor = FusedAttnProcessor()
 
 
 class GEGLU(_NoForward):
@@ -194,13 +219,17 @@ class ModelBase(nn.Module):
     weights_names = ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")
 
     @classmethod
-    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, subfolder=None, **kwargs):
+    def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, subfolder=None,
+                        ignore_mismatched_sizes=False, **kwargs):
         """load a diffusers-format checkpoint directory (config.json + diffusion_pytorch_model.{safetensors,bin}) the
-        way misc/test_utils.py:111-113,146-147 does.  Unknown kwargs of the diffusers loader (low_cpu_mem_usage,
-        device_map, ignore_mismatched_sizes, ...) are accepted and ignored; mismatched / missing keys are skipped
-        like `ignore_mismatched_sizes=True`."""
+        way misc/test_utils.py:111-113,146-147 does.  Like diffusers' loader: keys missing from the checkpoint and
+        unexpected keys are reported with a warning; a shape mismatch RAISES unless `ignore_mismatched_sizes=True` (the
+        reference passes it for the ControlNet branches only, misc/test_utils.py:111-113), in which case the mismatched
+        tensors keep their fresh initialisation and are listed in the warning.  Other kwargs of the diffusers loader
+        (low_cpu_mem_usage, device_map, ...) are accepted and ignored."""
         import inspect
         import json
+        import logging
         import os
         root = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
         with open(os.path.join(root, cls.config_name)) as fh:
@@ -220,8 +249,26 @@ class ModelBase(nn.Module):
         if sd is None:
             raise FileNotFoundError(f"no {' / '.join(cls.weights_names)} under {root}")
         own = model.state_dict()
-        sd = {k: v for k, v in sd.items() if k in own and tuple(own[k].shape) == tuple(v.shape)}
-        model.load_state_dict(sd, strict=False)
+        mismatched = [(k, tuple(v.shape), tuple(own[k].shape)) for k, v in sd.items()
+                      if k in own and tuple(own[k].shape) != tuple(v.shape)]
+        if mismatched and not ignore_mismatched_sizes:
+            lines = "\n".join(f"  {k}: checkpoint {a} vs model {b}" for k, a, b in mismatched[:20])
+            raise RuntimeError(f"{cls.__name__}.from_pretrained({root}): size mismatch for {len(mismatched)} tensor(s); pass "
+                               f"ignore_mismatched_sizes=True to keep the model's initialisation for them\n{lines}")
+        bad = {k for k, _, _ in mismatched}
+        res = model.load_state_dict({k: v for k, v in sd.items() if k not in bad}, strict=False)
+        missing = [k for k in res.missing_keys if k not in bad]
+        log = logging.getLogger(__name__)
+        if missing:
+            log.warning("%s.from_pretrained(%s): %d key(s) missing from the checkpoint keep their fresh initialisation: %s%s",
+                        cls.__name__, root, len(missing), ", ".join(missing[:8]), " ..." if len(missing) > 8 else "")
+        if res.unexpected_keys:
+            log.warning("%s.from_pretrained(%s): %d unexpected key(s) in the checkpoint were ignored: %s%s", cls.__name__, root,
+                        len(res.unexpected_keys), ", ".join(res.unexpected_keys[:8]), " ..." if len(res.unexpected_keys) > 8 else "")
+        if mismatched:
+            log.warning("%s.from_pretrained(%s): %d mismatched tensor(s) were NOT loaded (ignore_mismatched_sizes=True): %s",
+                        cls.__name__, root, len(mismatched), ", ".join(k for k, _, _ in mismatched[:8]))
+        model._load_report = dict(missing=missing, unexpected=list(res.unexpected_keys), mismatched=[k for k, _, _ in mismatched])
         if torch_dtype is not None:
             model = model.to(torch_dtype)
         return model.eval()
@@ -240,6 +287,39 @@ class ModelBase(nn.Module):
             save_file(sd, os.path.join(save_directory, self.weights_names[0]))
         else:
             torch.save(sd, os.path.join(save_directory, self.weights_names[1]))
+
+    # ---- the kernel-layout (bf16, packed) copy of the weights follows the parameters: whatever changes them drops it, the
+    # next forward / prepare() re-packs, and DualDiffDenoiser re-captures its CUDA graph when the pack object changed ----
+    def invalidate_pack(self):
+        for m in self.modules():
+            if getattr(m, "_packed", None) is not None:
+                m._packed = None
+            if hasattr(m, "_prep_cache"):
+                m._prep_cache = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_pack()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .half() ...
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_pack()
+        return out
+
+    def ensure_packed(self, device=None):
+        """pack on first use; re-pack when load_state_dict / .to() dropped the copy or a parameter was modified in place"""
+        if getattr(self, "_packed", None) is None or self.pack_is_stale():
+            self.pack(device)
+        return self._packed
+
+    def pack_is_stale(self):
+        """True when a parameter was modified in place after pack() (optimizer step, set_category_token, copy_)"""
+        ver = getattr(self, "_packed_versions", None)
+        return ver is not None and ver != self._param_versions()
+
+    def _param_versions(self):
+        return tuple((id(t), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     @property
     def dtype(self):
@@ -264,6 +344,8 @@ class ModelBase(nn.Module):
         return out
 
     def set_attn_processor(self, processor):
+        """diffusers signature (unet_addon_rawbox.py:523-593).  Only the default / stock-arithmetic processors are accepted:
+        the fused kernel cannot call a Python processor, and silently ignoring one would change the model's output."""
         mods = {f"{n}.processor": m for n, m in self.named_modules() if hasattr(m, "set_processor")}
         if isinstance(processor, dict):
             if len(processor) != len(mods):

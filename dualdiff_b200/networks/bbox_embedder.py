@@ -33,6 +33,14 @@ class ContinuousBBoxWithTextEmbedding(nn.Module):
     def class_tokens(self):
         return self._class_tokens
 
+    def reinitialize(self, output_num: int = 40):
+        """re-create `bbox_proj` / `null_pos_feature` for map vectors of 40 points (reference bbox_embedder.py:122-130; called by
+        misc/test_utils.py:116-121 before the branch's bbox_embedder weights are loaded a second time)"""
+        proj_dim = self.bbox_proj.out_features
+        dev, dt = self.bbox_proj.weight.device, self.bbox_proj.weight.dtype
+        self.bbox_proj = nn.Linear(self.fourier_embedder.out_dim * output_num, proj_dim).to(device=dev, dtype=dt)
+        self.null_pos_feature = nn.Parameter(torch.zeros([self.fourier_embedder.out_dim * output_num], device=dev, dtype=dt))
+
     def prepare(self, cfg, **kwargs):
         if self.use_text_encoder_init:
             self.set_category_token(kwargs["tokenizer"], kwargs["text_encoder"], cfg.dataset.object_classes)

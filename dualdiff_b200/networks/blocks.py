@@ -61,11 +61,17 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
 
     def pack(self):
         from .. import engine
-        pk = engine.Packer({k: v for k, v in self.state_dict().items()}, next(self.parameters()).device)
+        pairs, n_nbr = engine.check_view_pairs(self.neighboring_view_pair)
+        pk = engine.Packer({k: v for k, v in self.state_dict().items()}, next(self.parameters()).device, n_nbr)
         pk.sd = {"b." + k: v for k, v in pk.sd.items()}
         pk.tblock("b", True)
+        pk.out["n_nbr"] = n_nbr
         self._packed = pk.out
         return self
+
+    def _apply(self, fn, *args, **kwargs):      # .to() / .cuda(): the packed copy follows the parameters
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, hidden_states, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None,
                 timestep=None, cross_attention_kwargs=None, class_labels=None, frame_shard=None):
@@ -83,7 +89,7 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         enc = encoder_hidden_states.to(torch.bfloat16)
         lk = enc.shape[1]
         ctx = engine.StepCtx(n=n, temb=None, temb_rows_per_img_factor=1, lk=lk,
-                             kv_map=engine.make_kv_map(n, self.n_cam, h.device))
+                             kv_map=engine.make_kv_map(n, self.neighboring_view_pair, h.device), n_nbr=P["n_nbr"])
         if self.temporal_frames > 1:
             ctx.n_view = self.n_cam
             ctx.frame_shard = frame_shard

@@ -174,6 +174,7 @@ class BEVControlNetModel(_tree.ModelBase):
         if getattr(self, "use_box_adapter", False):
             raise NotImplementedError("use_box_adapter is incompatible with the dual branch (multiview_runner.py:240)")
         self._packed = engine.pack_controlnet(self.state_dict(), device, bool(self.use_occ_3d))
+        self._packed_versions = self._param_versions()
         self._prep_cache = None
         return self
 
@@ -181,8 +182,7 @@ class BEVControlNetModel(_tree.ModelBase):
         """timestep-invariant half of forward (tokens, K/V of every text cross-attention, condition embedding, SFA);
         the sampler calls it once per sample, `forward` calls it on demand."""
         from .. import engine
-        if self._packed is None:
-            self.pack(camera_param.device)
+        self.ensure_packed(camera_param.device)
         return engine.controlnet_prepare(self._packed, camera_param.float(), encoder_hidden_states, bboxes_3d_data,
                                          controlnet_cond, H, W)
 
@@ -201,9 +201,7 @@ class BEVControlNetModel(_tree.ModelBase):
             raise NotImplementedError("guess_mode / attention_mask / class_labels / timestep_cond are unused on the reference path")
         if not sample.is_cuda:
             raise RuntimeError("dualdiff_b200 has no CPU path: `sample` must be a CUDA tensor")
-        if self._packed is None:
-            self.pack(sample.device)
-        P = self._packed
+        P = self.ensure_packed(sample.device)
         b, n_cam, c, H, W = sample.shape
         prep = self.prepare_condition(camera_param, encoder_hidden_states, bboxes_3d_data, controlnet_cond, H, W)
         t = timestep

@@ -64,8 +64,7 @@ class DualDiffDenoiser:
         n = G * B * n_cam
         self.n = n
         for m in [self.unet] + self.nets:
-            if m._packed is None:
-                m.pack(dev)
+            m.ensure_packed(dev)          # packs on first use and re-packs when the weights changed since
         if self.cfg:  # uncond in the front, cond in the tail (pipeline:349-375; camera from nets[0])
             kw = self.nets[0].add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, image=None)
             cam, boxes = kw["camera_param"], kw["bboxes_3d_data"]
@@ -80,7 +79,7 @@ class DualDiffDenoiser:
         Pu = self.unet._packed
         unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, preps[0].enc_rows)  # tokens of branch 0
         if self.view_shard is None:
-            kv_map = engine.make_kv_map(n, n_cam, dev)
+            kv_map = engine.make_kv_map(n, Pu["view_pairs"], dev)
         else:
             assert self.view_shard.v_loc == n_cam
             kv_map = self.view_shard.kv_map(G * B, dev)
@@ -131,7 +130,7 @@ class DualDiffDenoiser:
                 acc = down + [mid]
             temb = engine.time_embedding(Pu, self.t_cur)
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                                 lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
             self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
             eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
@@ -149,7 +148,7 @@ class DualDiffDenoiser:
                 res.append((down, mid))
             temb = engine.time_embedding(Pu, self.t_cur)
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                                 lk=self.preps[0].lk, kv_map=self.kv_map, view_shard=self.view_shard,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
             self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
 

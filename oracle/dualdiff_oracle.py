@@ -117,7 +117,7 @@ def temporal_attention(sd: SD, p: str, x, n_frames: int, n_cam=6):
     return o.reshape(n_clip, n_cam, T, n_frames, C).permute(0, 3, 1, 2, 4).reshape(n, T, C)
 
 
-def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames: int = 1):
+def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames: int = 1, neighbors=None):
     x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x))             # blocks.py:163-172
     x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), enc)        # blocks.py:175-188
     if multiview:
@@ -131,11 +131,13 @@ def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames
         k = _lin(sd, p + ".attn4.to_k", hv, False)
         v = _lin(sd, p + ".attn4.to_v", hv, False)
         acc = torch.zeros_like(hv)
-        for cam, nbrs in NEIGHBORS.items():
+        nbr_table = NEIGHBORS if neighbors is None else neighbors       # neighboring_view_pair (blocks.py:112-121)
+        n_nbr = len(next(iter(nbr_table.values())))
+        for cam, nbrs in nbr_table.items():
             for nb in nbrs:
                 acc[:, cam] += mha(q[:, cam], k[:, nb], v[:, nb], HEADS)
         w_o, b_o = sd[p + ".attn4.to_out.0.weight"], sd[p + ".attn4.to_out.0.bias"]
-        out = F.linear(acc, w_o) + 2.0 * b_o
+        out = F.linear(acc, w_o) + float(n_nbr) * b_o                  # to_out runs once per (view, neighbour) pair
         out = _lin(sd, p + ".connector", out).reshape(bn, T, C)                # zero_linear connector, blocks.py:83,220
         x = x + out
     if n_frames > 1 and (p + ".attn_temp.to_q.weight") in sd:
@@ -237,7 +239,7 @@ def box_tokens(sd: SD, bboxes, classes, masks):
     """bboxes (B, L, 8, 3), classes (B, L) int64, masks (B, L) bool -> (B, L, 768).  minmax_normalize False."""
     B, L = classes.shape
     m = masks.reshape(-1, 1).float()
-    pos = fourier_embed(bboxes.reshape(B * L, 8, 3)).reshape(B * L, -1)
+    pos = fourier_embed(bboxes.reshape(B * L, bboxes.shape[-2], 3)).reshape(B * L, -1)   # 8 corners (40 points after reinitialize())
     pos = pos * m + sd["bbox_embedder.null_pos_feature"][None] * (1 - m)
     cls = sd["bbox_embedder._class_tokens"][classes.reshape(-1)]
     cls = cls * m + sd["bbox_embedder.null_class_feature"][None] * (1 - m)
