@@ -36,7 +36,7 @@ class GroupNormArgs(C.Structure):
         ("x1", _vp), ("x2", _vp), ("out", _vp), ("stats", _vp), ("gamma", _vp), ("beta", _vp),
         ("x1_ld", _ll), ("x2_ld", _ll), ("out_ld", _ll),
         ("n_img", _i), ("h", _i), ("w", _i), ("c1", _i), ("c2", _i), ("groups", _i),
-        ("eps", _f), ("silu", _i), ("padded_out", _i),
+        ("eps", _f), ("silu", _i), ("padded_out", _i), ("two_pass", _i),
     ]
 
 

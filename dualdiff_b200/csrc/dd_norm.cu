@@ -195,6 +195,235 @@ gn_apply_kernel(const bf16* __restrict__ x1, long long ld1, int C1, const bf16* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm in ONE pass over HBM: a CTA owns ALL rows of a few whole groups of one image.
+//
+// The two-kernel form above reads every activation twice (statistics, then apply): 6 bytes per element against the 4 the
+// operator needs, and ncu showed the apply pass half MUFU-bound on top (SiLU = ex2 + rcp per element, XU 54 %).  Groups are
+// independent of each other, so the image is cut along the CHANNELS: a CTA pulls the [rows x (a few groups)] slab into
+// shared memory with 16-byte cp.async copies (row segments of 80-240 bytes; the CTAs owning the neighbouring channel
+// ranges of the same rows run next to it, so DRAM still streams whole lines), and everything else happens on chip with
+// CTA-level barriers only: group means, then the sum of squared deviations from the mean (a true two-pass variance -- no
+// E[x^2] - mean^2 cancellation), then normalise + affine (+ SiLU as x/2 (1 + tanh(x/2)): one MUFU op per element) straight
+// into the compact or zero-haloed output.  One read + one write of HBM, no scratch buffer, no atomics, fixed reduction
+// orders (bit-reproducible).  A first version that cut the image along the ROWS over a thread-block cluster (partials
+// exchanged through distributed shared memory) was 2-4x SLOWER than the two-kernel form at cluster sizes 8 / 16
+// (profiles/r02_gn_notes.md): co-scheduling 16 CTAs and three cluster barriers cost more than the second read.
+// The channel range of a CTA starts and ends on a multiple of 8 channels (16-byte vectors); inside it an octet of channels
+// may straddle two groups (10 / 20 / 30 / 60 channels per group), which the (lo, hi) bookkeeping below resolves.
+// ---------------------------------------------------------------------------------------------------
+struct GnSlabDev {
+  const bf16* x1; const bf16* x2; bf16* out; const float* gamma; const float* beta;
+  long long ld1, ld2, out_ld;
+  int C1, C, H, W, groups, cpg, g_per_cta, silu, padded, rows_out_img;
+  float eps;
+};
+constexpr int GN_SLAB_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(GN_SLAB_THREADS, 3)
+gn_slab_kernel(const GnSlabDev p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  // layout: [group mean: 64 floats][group rstd: 64 floats][scratch: 256 x float2][slab: rows x width bf16]
+  float* gmean = reinterpret_cast<float*>(gsm);
+  float* grstd = gmean + 64;
+  float2* scratch = reinterpret_cast<float2*>(gsm + 512);
+  uint8_t* slab = gsm + 512 + GN_SLAB_THREADS * 8;
+  const int img = blockIdx.y;
+  const int g0 = blockIdx.x * p.g_per_cta;
+  const int ng = min(p.g_per_cta, p.groups - g0);       // groups of this CTA
+  const int ca = g0 * p.cpg;                             // first channel (a multiple of 8 by construction)
+  const int width = ng * p.cpg;                          // channels of this CTA (a multiple of 8)
+  const int wv = width >> 3;                             // 16-byte vectors per row
+  const int HW = p.H * p.W;
+  const int rpi = GN_SLAB_THREADS / wv;                  // rows per iteration
+  const int j = threadIdx.x % wv, sub = threadIdx.x / wv;
+  const bool on = sub < rpi;
+  const int c0 = ca + 8 * j;                             // my octet of channels
+  const uint32_t pitch = (uint32_t)width * 2;
+  // ---- slab in: my column of 16-byte vectors, every rpi-th row
+  if (on) {
+    const bool from1 = c0 < p.C1;
+    const bf16* src = (from1 ? p.x1 + c0 : p.x2 + (c0 - p.C1)) + (long long)img * HW * (from1 ? p.ld1 : p.ld2);
+    const long long ld = from1 ? p.ld1 : p.ld2;
+    const uint32_t dst = smem_u32(slab) + 16u * (uint32_t)j;
+    for (int r = sub; r < HW; r += rpi) cp_async16(dst + (uint32_t)r * pitch, src + (long long)r * ld);
+  }
+  // the octet's group split: it lies in at most two groups (cpg >= 8), "lo" and "hi"
+  const int glo = on ? c0 / p.cpg : g0;
+  const int n_lo = on ? min(8, (glo + 1) * p.cpg - c0) : 8;      // channels of the octet that belong to the lo group
+  cp_async_wait_all();
+  __syncthreads();
+  const uint8_t* my = slab + 16 * j;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // CTA-level reduction of per-thread (lo, hi) values to per-group totals (one warp per group, fixed order)
+  auto group_totals = [&](const float (&v)[8], float* dst, bool finish_rstd) {
+    float lo = 0.f, hi = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e < n_lo) lo += v[e]; else hi += v[e];
+    }
+    if (on) scratch[sub * wv + j] = make_float2(lo, hi);
+    __syncthreads();
+    for (int gi = warp; gi < ng; gi += GN_SLAB_THREADS / 32) {
+      const int g = g0 + gi;
+      const int ja = (g * p.cpg - ca) >> 3, jb = ((g + 1) * p.cpg - 1 - ca) >> 3;     // octets overlapping the group
+      const int n_oct = jb - ja + 1;
+      float acc = 0.f;
+      for (int i = lane; i < n_oct * rpi; i += 32) {
+        const int sb = i / n_oct, jj = ja + (i - sb * n_oct);
+        const float2 f = scratch[sb * wv + jj];
+        acc += ((ca + 8 * jj) / p.cpg == g) ? f.x : f.y;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float inv_n = 1.f / (float)(p.cpg * HW);
+        dst[gi] = finish_rstd ? rsqrtf(acc * inv_n + p.eps) : acc * inv_n;
+      }
+    }
+    __syncthreads();
+  };
+  // ---- pass A: per-channel sums (one FADD per element; folded into the two groups once, above) -> group means
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (on) {
+    for (int r = sub; r < HW; r += rpi) {
+      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)r * pitch);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  }
+  group_totals(acc, gmean, false);
+  float mu[8];                               // mean of each channel's group
+  {
+    const float mean_lo = gmean[glo - g0], mean_hi = gmean[min(glo - g0 + 1, ng - 1)];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mu[e] = e < n_lo ? mean_lo : mean_hi;
+      acc[e] = 0.f;
+    }
+  }
+  // ---- pass B: squared deviations from the group mean
+  if (on) {
+    for (int r = sub; r < HW; r += rpi) {
+      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)r * pitch);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const float d0 = f.x - mu[2 * e], d1 = f.y - mu[2 * e + 1];
+        acc[2 * e] = fmaf(d0, d0, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(d1, d1, acc[2 * e + 1]);
+      }
+    }
+  }
+  group_totals(acc, grstd, true);
+  if (!on) return;
+  // y = x * sc + sh; with SiLU the halves are kept: h = y / 2, silu(y) = h * tanh(h) + h (one MUFU op per element)
+  uint64_t SC[4], SH[4];
+  {
+    const float rstd_lo = grstd[glo - g0], rstd_hi = grstd[min(glo - g0 + 1, ng - 1)];
+    const float4 a0 = *reinterpret_cast<const float4*>(p.gamma + c0), a1 = *reinterpret_cast<const float4*>(p.gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p.beta + c0), b1 = *reinterpret_cast<const float4*>(p.beta + c0 + 4);
+    const float ga[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float half = p.silu ? 0.5f : 1.f;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = half * ga[e] * (e < n_lo ? rstd_lo : rstd_hi);
+      sh[e] = half * be[e] - mu[e] * sc[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      SC[e] = pack_f32x2(sc[2 * e], sc[2 * e + 1]);
+      SH[e] = pack_f32x2(sh[2 * e], sh[2 * e + 1]);
+    }
+  }
+  // ---- normalise the image's output rows from shared memory (the padded layout interleaves zero halo rows / columns)
+  bf16* obase = p.out + (size_t)img * p.rows_out_img * p.out_ld + c0;
+  const int Wp = p.W + 1;
+  int hp = 0, wp = sub;                      // padded (row, column) of output row rr, carried without divisions
+  if (p.padded) { hp = sub / Wp; wp = sub - hp * Wp; }
+  const int dh = rpi / Wp, dw = rpi - dh * Wp;
+  for (int rr = sub; rr < p.rows_out_img; rr += rpi) {
+    int src = rr;
+    bool live = true;
+    if (p.padded) {
+      live = (hp < p.H) && (wp < p.W);
+      src = hp * p.W + wp;
+    }
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);   // halo rows / columns of the padded layout are zeros
+    if (live) {
+      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)src * pitch);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const uint64_t Y = fma_f32x2(pack_f32x2(f.x, f.y), SC[e], SH[e]);
+        float a, b;
+        unpack_f32x2(Y, a, b);
+        if (p.silu) {
+          const uint64_t T = pack_f32x2(tanh_approx(a), tanh_approx(b));
+          unpack_f32x2(fma_f32x2(Y, T, Y), a, b);
+        }
+        pk[e] = pack_bf16(a, b);
+      }
+      o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    *reinterpret_cast<uint4*>(obase + (size_t)rr * p.out_ld) = o;
+    if (p.padded) {
+      hp += dh;
+      wp += dw;
+      if (wp >= Wp) { wp -= Wp; ++hp; }
+    }
+  }
+}
+
+// groups per CTA of the single-pass kernel (0 = the two-kernel form must be used): the channel range must start on a
+// multiple of 8 channels, an octet may straddle at most two groups, and the [rows x channels] slab must leave room for two
+// CTAs per SM; among the admissible sizes the largest one of at most 64 KB is taken as long as it still yields two waves
+// of CTAs, else the smallest.
+static int gn_slab_plan(int C, int groups, int HW, int n_img, size_t* smem_bytes) {
+  const int cpg = C / groups;
+  if (cpg < 8 || groups > 64 * 64) return 0;
+  int unit = 1;
+  while ((unit * cpg) % 8 != 0) ++unit;                 // 1, 2 or 4 groups
+  if (unit > groups) return 0;
+  const size_t hdr = 512 + GN_SLAB_THREADS * 8;
+  const size_t limit = 112 * 1024;
+  int best = 0;
+  for (int g = unit; g <= groups && g <= 64; g += unit) {
+    const int width = g * cpg;
+    if (width / 8 > GN_SLAB_THREADS) break;
+    const size_t need = hdr + (size_t)HW * width * 2;
+    if (need > limit) break;
+    const long long ctas = (long long)n_img * ((groups + g - 1) / g);
+    if (best == 0 || (need <= 64 * 1024 + hdr && ctas >= 2LL * 2 * num_sms())) best = g;
+  }
+  if (best == 0) return 0;
+  *smem_bytes = hdr + (size_t)HW * best * cpg * 2;
+  return best;
+}
+
 // number of stats CTAs (= partial rows) per image: one wave of two 512-thread CTAs per SM, every CTA non-empty
 static int groupnorm_partials(int n_img, int HW, int rpi) {
   const int sms = num_sms();
@@ -239,6 +468,27 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
   int rpi = 0;
   const int threads = groupnorm_threads(C, &rpi);
   DD_CHECK(rpi >= 1, -1, "dd_groupnorm: C=%d too large", C);
+  // ---- single-pass kernel when a [rows x few groups] slab of the image fits shared memory (see gn_slab_kernel) ----
+  if (!a->two_pass && a->x1_ld % 8 == 0 && (a->c2 == 0 || a->x2_ld % 8 == 0) && a->out_ld % 8 == 0) {
+    size_t smem = 0;
+    const int gpc = gn_slab_plan(C, a->groups, HW, a->n_img, &smem);
+    if (gpc > 0) {
+      GnSlabDev p;
+      p.x1 = reinterpret_cast<const bf16*>(a->x1); p.x2 = reinterpret_cast<const bf16*>(a->x2);
+      p.out = reinterpret_cast<bf16*>(a->out); p.gamma = a->gamma; p.beta = a->beta;
+      p.ld1 = a->x1_ld; p.ld2 = a->x2_ld; p.out_ld = a->out_ld;
+      p.C1 = a->c1; p.C = C; p.H = a->h; p.W = a->w; p.groups = a->groups; p.cpg = C / a->groups; p.g_per_cta = gpc;
+      p.silu = a->silu; p.padded = a->padded_out; p.rows_out_img = a->padded_out ? (a->h + 1) * (a->w + 1) : HW;
+      p.eps = a->eps;
+      if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gn_slab_kernel), 113 * 1024)) return rc;
+      dim3 grid((a->groups + gpc - 1) / gpc, a->n_img);
+      gn_slab_kernel<<<grid, GN_SLAB_THREADS, smem, stream>>>(p);
+      DD_CUDA(cudaGetLastError());
+      count_launch(1);
+      return 0;
+    }
+  }
+  // ---- two passes (statistics, then apply) for images whose slabs do not fit shared memory ----
   // stats scratch layout: [n_img][n_part][groups][2] per-CTA partial group sums
   const int sms = num_sms();
   const int n_part = groupnorm_partials(a->n_img, HW, rpi);

@@ -148,7 +148,7 @@ _I = C.c_int
 
 
 def groupnorm(x1, gamma, beta, *, n_img, hw, x2=None, eps=1e-5, silu=True, padded_out=False, groups=32,
-              out=None, stats=None):
+              out=None, stats=None, two_pass=False):
     """GroupNorm(32) [+SiLU] over compact channels-last rows; x2 = second channel source (skip concat)."""
     _req(x1, torch.bfloat16, "x1")
     H, W = hw
@@ -167,7 +167,7 @@ def groupnorm(x1, gamma, beta, *, n_img, hw, x2=None, eps=1e-5, silu=True, padde
     a.gamma = _ptr(gamma); a.beta = _ptr(beta)
     a.x1_ld = x1.stride(0); a.x2_ld = x2.stride(0) if x2 is not None else 0; a.out_ld = out.stride(0)
     a.n_img = n_img; a.h = H; a.w = W; a.c1 = c1; a.c2 = c2; a.groups = groups
-    a.eps = eps; a.silu = 1 if silu else 0; a.padded_out = 1 if padded_out else 0
+    a.eps = eps; a.silu = 1 if silu else 0; a.padded_out = 1 if padded_out else 0; a.two_pass = 1 if two_pass else 0
     with _Rec("groupnorm_silu", 0.0, 2.0 * (2 * n_img * H * W * C_ + rows * C_), f"C{C_}_HW{H * W}"):
         check(_lib.lib().dd_groupnorm(C.byref(a), _stream()), "dd_groupnorm")
     return out

@@ -86,6 +86,7 @@ typedef struct dd_groupnorm_args {
   int n_img, h, w, c1, c2, groups;
   float eps;
   int silu, padded_out;
+  int two_pass;   /* testing hook: 1 forces the two-kernel (statistics, apply) form; 0 = single-pass cluster kernel when it fits */
 } dd_groupnorm_args;
 DD_API int dd_groupnorm(const dd_groupnorm_args* args, void* stream);
 DD_API long long dd_groupnorm_scratch_floats(int n_img, int c, int hw);

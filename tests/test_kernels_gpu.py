@@ -132,17 +132,23 @@ def test_head_dim_40_kernel_variants(lq, lk, n_src, variant):
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("n,H,W,c1,c2,padded,silu,eps", [
     (3, 28, 50, 320, 0, True, True, 1e-5), (2, 14, 25, 640, 0, False, False, 1e-6), (2, 7, 13, 1280, 1280, True, True, 1e-5),
-    (2, 14, 25, 1280, 640, True, True, 1e-5), (2, 28, 50, 640, 320, True, True, 1e-5), (2, 4, 7, 1280, 0, True, True, 1e-5)])
-def test_groupnorm_silu(n, H, W, c1, c2, padded, silu, eps):
+    (2, 14, 25, 1280, 640, True, True, 1e-5), (2, 28, 50, 640, 320, True, True, 1e-5), (2, 4, 7, 1280, 0, True, True, 1e-5),
+    (5, 28, 50, 320, 0, False, False, 1e-6), (1, 56, 100, 320, 0, True, True, 1e-5), (3, 1, 1, 1280, 1280, True, True, 1e-5),
+    (2, 5, 7, 256, 0, True, True, 1e-6), (2, 9, 11, 128, 0, True, True, 1e-6)])
+def test_groupnorm_silu(n, H, W, c1, c2, padded, silu, eps, two_pass):
+    """both forms of the operator: the single-pass cluster kernel (the image lives in the shared memory of a cluster) and the
+    two-kernel fallback (forced here; taken on its own for images too large for a cluster, e.g. 640 channels at 28x50, or
+    fewer than 8 channels per group, e.g. the VAE's 128-channel layers)"""
     from dualdiff_b200 import ops, packing
     x1 = _mk((n * H * W, c1), 1) * 2 + 0.5
     x2 = _mk((n * H * W, c2), 2) if c2 else None
     C = c1 + c2
     gamma = (1 + 0.1 * torch.randn(C, generator=torch.Generator().manual_seed(3))).cuda()
     beta = (0.1 * torch.randn(C, generator=torch.Generator().manual_seed(4))).cuda()
-    out = ops.groupnorm(x1, gamma, beta, n_img=n, hw=(H, W), x2=x2, eps=eps, silu=silu, padded_out=padded)
+    out = ops.groupnorm(x1, gamma, beta, n_img=n, hw=(H, W), x2=x2, eps=eps, silu=silu, padded_out=padded, two_pass=two_pass)
     x = torch.cat([x1, x2], 1) if c2 else x1
     ref = F.group_norm(x.float().reshape(n, H, W, C).permute(0, 3, 1, 2), 32, gamma, beta, eps)
     if silu:
@@ -153,6 +159,21 @@ def test_groupnorm_silu(n, H, W, c1, c2, padded, silu, eps):
     if padded:  # halo must be exactly zero
         o = out.reshape(n, H + 1, W + 1, C)
         assert o[:, H].abs().max() == 0 and o[:, :, W].abs().max() == 0
+    again = ops.groupnorm(x1, gamma, beta, n_img=n, hw=(H, W), x2=x2, eps=eps, silu=silu, padded_out=padded, two_pass=two_pass)
+    assert torch.equal(out, again)        # fixed reduction orders: bit-reproducible
+
+
+def test_groupnorm_large_offset_activations():
+    """activations with a mean far above their spread (mean 200, std 0.5: E[x^2] - mean^2 would lose every significant bit
+    in fp32): the single-pass kernel forms the variance from squared deviations around the group mean"""
+    from dualdiff_b200 import ops
+    n, H, W, C = 2, 14, 25, 640
+    g = torch.Generator().manual_seed(11)
+    x = (200.0 + 0.5 * torch.randn(n * H * W, C, generator=g)).to(torch.bfloat16).cuda()
+    gamma = torch.ones(C).cuda(); beta = torch.zeros(C).cuda()
+    out = ops.groupnorm(x, gamma, beta, n_img=n, hw=(H, W), eps=1e-5, silu=False)
+    ref = F.group_norm(x.double().reshape(n, H, W, C).permute(0, 3, 1, 2), 32, None, None, 1e-5).permute(0, 2, 3, 1).reshape(n * H * W, C)
+    assert _rel(out, ref.float()) < 2e-2, _rel(out, ref.float())
 
 
 @pytest.mark.parametrize("rows,C", [(1400, 320), (701, 640), (91, 1280), (5, 1280)])
