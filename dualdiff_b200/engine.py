@@ -320,20 +320,27 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
     h = ops.gemm(a, P[p + ".attn2.to_out.0.w"], bias=P[p + ".attn2.to_out.0.b"], res1=h)
     # 3. cross-view attention over the two ring neighbours (blocks.py:190-222)
     if multiview:
-        ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
         if ctx.view_shard is None:
+            ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
             qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
             a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
                               k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
         else:
-            # camera views sharded across ranks: project locally, then fetch the two halo views' rows from the ring
-            # neighbours straight into the tail of the projection buffer (the only exchange step of the path)
+            # camera views sharded across ranks (the only exchange step of the path): the norm4 rows of the first / last local
+            # view travel to the ring neighbours on a side stream WHILE the local views are projected; the K/V projection of
+            # the two halo views (rows behind the local ones) follows when they have arrived
             vs = ctx.view_shard
-            wq = P[p + ".attn4.qkv.w"].shape[0]
-            buf = torch.empty((vs.kv_rows(ctx.n_outer) * T, wq), device=h.device, dtype=BF)
-            ops.gemm(ln, P[p + ".attn4.qkv.w"], out=buf[: n * T])
-            vs.exchange(buf, ctx.n_outer, T)
-            a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=vs.kv_rows(ctx.n_outer), lq=T, lk=T, heads=HEADS,
+            w_qkv = P[p + ".attn4.qkv.w"]
+            wq, q_cols = w_qkv.shape[0], HEADS * dp
+            n_kv = vs.kv_rows(ctx.n_outer)
+            ln_ext = torch.empty((n_kv * T, C), device=h.device, dtype=BF)
+            ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"], out=ln_ext[: n * T])
+            vs.exchange_async(ln_ext, ctx.n_outer, T)
+            buf = torch.empty((n_kv * T, wq), device=h.device, dtype=BF)
+            ops.gemm(ln_ext[: n * T], w_qkv, out=buf[: n * T])
+            vs.exchange_wait(h.device)
+            ops.gemm(ln_ext[n * T:], w_qkv[q_cols:], out=buf[n * T:, q_cols:])      # halo views: K and V columns only
+            a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=n_kv, lq=T, lk=T, heads=HEADS,
                               head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
     # 3b. temporal attention over the frames of the clip (no reference code: defined in csrc/dd_temporal.cu and

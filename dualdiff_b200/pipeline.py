@@ -29,8 +29,10 @@ class DualDiffDenoiser:
         self.scheduler = scheduler if scheduler is not None else UniPCMultistepScheduler()
         self.scheduler.guidance_scale = guidance_scale
         self.view_shard = view_shard               # sharding.ViewShard: camera views split across ranks (config 4)
-        # the K/V exchanges of the view- / frame-sharded configurations run eagerly on NCCL
-        self.use_cuda_graph = use_cuda_graph and view_shard is None and getattr(unet, "frame_shard", None) is None
+        # The view-sharded step is captured like the unsharded one (NCCL send/recv and the side-stream fork/join are
+        # capturable); the frame-sharded video configuration still launches eagerly (its all-gather sizes follow the clip).
+        self.use_cuda_graph = use_cuda_graph and getattr(unet, "frame_shard", None) is None
+        self.graph_note = None                     # why a requested CUDA graph was not used (capture failed), if so
         self._graph = None
         self.device = None
         # The two condition branches and the UNet encoder are mutually independent until the skip/mid residual adds
@@ -45,13 +47,19 @@ class DualDiffDenoiser:
         """latents (B, 6, 4, h, w) fp32; prompt_embeds (2B, 77, 768) uncond first (or (B, ...) without CFG);
         camera_param (B, 6, 3, 7); bboxes_3d_data = [bg boxes, fg map vectors]; images = [bg panorama
         (B, 3, 8h, 48w), fg ORS (B*6, 320, h, w)]."""
-        if self.view_shard is not None:   # every rank passes the full scene inputs and keeps its own camera views
-            from .sharding import slice_views
+        if self.view_shard is not None:
+            # every rank passes the FULL inputs of the call and keeps the scenes of its group and its own camera views
+            from .sharding import slice_scenes, slice_views
+            vs = self.view_shard
+            B_all = latents.shape[0]
+            mine = vs.scenes(B_all)
             full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
-                        cond_fg=images[1])
-            loc = slice_views(full, self.view_shard.views, latents.shape[1])
-            latents, camera_param = loc["latents"], loc["camera_param"]
-            bboxes_3d_data = [loc["boxes_bg"], bboxes_3d_data[1]]
+                        cond_fg=images[1], prompt_embeds=prompt_embeds)
+            loc = slice_views(full, vs.views, latents.shape[1], scenes=mine)
+            latents, camera_param, prompt_embeds = loc["latents"], loc["camera_param"], loc["prompt_embeds"]
+            fg_boxes = bboxes_3d_data[1]            # map vectors are view-shared: only the scene selection applies
+            fg_boxes = None if fg_boxes is None else slice_scenes(fg_boxes, mine, B_all, vs.n_cam)
+            bboxes_3d_data = [loc["boxes_bg"], fg_boxes]
             images = [loc["cond_bg"], loc["cond_fg"]]
         dev = latents.device
         if dev.type != "cuda":
@@ -181,13 +189,27 @@ class DualDiffDenoiser:
                 torch.cuda.current_stream().wait_stream(s)
                 for t, sv in zip((self.latents, self.last, self.m0, self.m1), saved):
                     t.copy_(sv)
-                self._graph = torch.cuda.CUDAGraph()
+                graph = torch.cuda.CUDAGraph()
                 n0 = _launches()
-                with torch.cuda.graph(self._graph):
-                    self._step_kernels()
+                try:
+                    with torch.cuda.graph(graph):
+                        self._step_kernels()
+                    self._graph = graph
+                except Exception as e:      # a capture the driver / NCCL build refuses: launch eagerly, and say so
+                    if self.view_shard is None:
+                        raise
+                    import logging
+                    self.graph_note = f"CUDA graph capture of the view-sharded step failed ({type(e).__name__}: {e}); eager launches"
+                    logging.getLogger(__name__).warning(self.graph_note)
+                    self.use_cuda_graph = False
+                    torch.cuda.synchronize()
                 self.launches_per_step = _launches() - n0
                 for t, sv in zip((self.latents, self.last, self.m0, self.m1), saved):
                     t.copy_(sv)
+                if self._graph is None:
+                    self._step_kernels()
+                    self.step_index = i + 1
+                    return self.latents
             self._graph.replay()
         self.step_index = i + 1
         return self.latents

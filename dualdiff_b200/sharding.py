@@ -82,29 +82,58 @@ def run_scene_sharded(pipe, *, prompt, image, camera_param, bev_controlnet_kwarg
     return [scene for part in parts for scene in part]  # PIL: [scene][view]
 
 
-class ViewShard:
-    """Camera-view sharding inside a scene (BASELINE config 4).
+def default_ranks_per_scene(world: int, n_cam: int = 6) -> int:
+    """largest divisor of the camera count that also divides the world size: 1 -> 1, 2 / 4 / 8 -> 2, 3 -> 3, 6 / 12 -> 6"""
+    for r in range(min(world, n_cam), 0, -1):
+        if n_cam % r == 0 and world % r == 0:
+            return r
+    return 1
 
-    Rank r owns the V_loc = n_cam / world consecutive views [r*V_loc, (r+1)*V_loc) of every scene (and CFG half).
+
+class ViewShard:
+    """Camera-view sharding inside a scene (BASELINE config 4), for ANY world size.
+
+    The unit of work is (scene, camera view), both CFG halves of a view staying together (so the CFG combine and the
+    scheduler update need no communication).  The `world` ranks form world / R GROUPS of R ranks (R = `ranks_per_scene`, a
+    divisor of the camera count: 2 on 2 / 4 / 8 GPUs by default); the scenes of a call are dealt out to the groups
+    (`shard_scenes`, no communication between groups -- scenes are independent, networks/blocks.py:196-197), and inside a
+    group rank g owns the V_loc = n_cam / R consecutive views [g V_loc, (g+1) V_loc) of each of the group's scenes.
+    8 GPUs therefore run 4 (or 8, 12 ...) scenes with 3 views x 2 CFG halves per scene on every GPU.
+
     Convolutions, norms, self- and text-attention and the ControlNet branches are per image -> unit-local.  The one
-    exchange step of the path is the cross-view attention (networks/blocks.py:190-222): view v attends to views
-    v-1 and v+1 (ring, configs/dataset/Nuscenes.yaml:27-33), so per transformer block each rank sends the projected
-    rows of its FIRST view to the left rank and of its LAST view to the right rank (grouped NCCL send/recv over
-    NVLink) and receives the two halo views into the tail of its own projection buffer; the attention kernel then
-    addresses local and halo images uniformly through `kv_map`.
+    exchange step of the path is the cross-view attention (networks/blocks.py:190-222): view v attends to views v-1 and v+1
+    (ring, configs/dataset/Nuscenes.yaml:27-33), so per transformer block each rank sends the norm4 output rows of its FIRST
+    view to the left rank of its group and of its LAST view to the right rank (grouped NCCL send/recv over NVLink) and
+    receives the two halo views behind its own rows.  The rows exchanged are the LayerNorm output (C columns), not the
+    projections (K + V = 2C columns): half the bytes, and the K/V projection of the two halo views is recomputed locally.
+    `exchange_async` runs the transfer on a side stream so that it overlaps the Q/K/V projection of the local views.
     """
 
-    def __init__(self, rank: int, world: int, n_cam: int = 6, group=None):
-        if n_cam % world != 0:
-            raise ValueError(f"world size {world} must divide the number of camera views {n_cam}")
+    def __init__(self, rank: int, world: int, n_cam: int = 6, ranks_per_scene: int = None, group=None):
+        R = default_ranks_per_scene(world, n_cam) if ranks_per_scene is None else int(ranks_per_scene)
+        if R < 1 or n_cam % R != 0 or world % R != 0:
+            raise ValueError(f"ranks_per_scene={R} must divide both the number of camera views {n_cam} and the world size {world}")
         self.rank, self.world, self.n_cam, self.group = rank, world, n_cam, group
-        self.v_loc = n_cam // world
-        self.left = (rank - 1) % world
-        self.right = (rank + 1) % world
+        self.ranks_per_scene = R
+        self.n_groups = world // R
+        self.group_index = rank // R
+        self.group_rank = rank % R
+        self.v_loc = n_cam // R
+        base = self.group_index * R
+        self.left = base + (self.group_rank - 1) % R
+        self.right = base + (self.group_rank + 1) % R
+        self._side = None
 
     @property
     def views(self):
-        return list(range(self.rank * self.v_loc, (self.rank + 1) * self.v_loc))
+        return list(range(self.group_rank * self.v_loc, (self.group_rank + 1) * self.v_loc))
+
+    def scenes(self, total_scenes: int) -> range:
+        """the scenes of a call this rank's group works on"""
+        if total_scenes < self.n_groups:
+            raise ValueError(f"{total_scenes} scene(s) cannot feed {self.n_groups} groups of {self.ranks_per_scene} rank(s): "
+                             f"pass at least one scene per group (8 GPUs with 2 ranks per scene need 4 scenes)")
+        return shard_scenes(total_scenes, self.group_index, self.n_groups)
 
     def kv_rows(self, n_outer: int) -> int:
         """images in the K/V buffer: local images followed by the left and right halo views of every scene"""
@@ -122,7 +151,7 @@ class ViewShard:
         return torch.tensor(rows, dtype=torch.int32, device=device)
 
     def exchange(self, buf: torch.Tensor, n_outer: int, T: int) -> None:
-        """buf: [(n_loc + 2*n_outer) * T, W] projection rows; fills the halo tail in place."""
+        """buf: [(n_loc + 2*n_outer) * T, W] rows (local images, then the halo tail); fills the halo tail in place."""
         import torch.distributed as dist
         v, W = self.v_loc, buf.shape[1]
         n_loc = n_outer * v
@@ -131,11 +160,11 @@ class ViewShard:
         send_last = local[:, v - 1].contiguous()     # my last view   -> left halo of the right rank
         halo_left = buf[n_loc * T:(n_loc + n_outer) * T].view(n_outer, T, W)
         halo_right = buf[(n_loc + n_outer) * T:].view(n_outer, T, W)
-        if self.world == 1:
+        if self.ranks_per_scene == 1:
             halo_left.copy_(send_last)
             halo_right.copy_(send_first)
             return
-        # posting order matters when left == right (world 2): the peer's sends arrive in the order (first view,
+        # posting order matters when left == right (2 ranks per scene): the peer's sends arrive in the order (first view,
         # last view), which are my (right halo, left halo)
         ops = [dist.P2POp(dist.isend, send_first, self.left, self.group),
                dist.P2POp(dist.isend, send_last, self.right, self.group),
@@ -143,6 +172,25 @@ class ViewShard:
                dist.P2POp(dist.irecv, halo_left, self.left, self.group)]
         for r in dist.batch_isend_irecv(ops):
             r.wait()
+
+    def exchange_async(self, buf: torch.Tensor, n_outer: int, T: int) -> None:
+        """start `exchange` on a side stream ordered after the work already queued on the current stream (the LayerNorm that
+        produced `buf`); the caller keeps launching kernels that do not read the halo tail and calls `exchange_wait()` before
+        the first one that does.  CPU tensors (gloo tests) exchange synchronously."""
+        if not buf.is_cuda:
+            self.exchange(buf, n_outer, T)
+            return
+        main = torch.cuda.current_stream(buf.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(buf.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            self.exchange(buf, n_outer, T)
+        buf.record_stream(self._side)
+
+    def exchange_wait(self, device=None) -> None:
+        if self._side is not None:
+            torch.cuda.current_stream(device).wait_stream(self._side)
 
 
 class FrameShard:
@@ -183,9 +231,16 @@ def slice_frames(x: torch.Tensor, frames, n_frames: int, n_view: int = 6) -> tor
     return x.reshape(n_clip, n_frames, n_view, *x.shape[1:])[:, idx].reshape(n_clip * len(idx) * n_view, *x.shape[1:]).contiguous()
 
 
-def slice_views(inputs: dict, views, n_cam: int = 6) -> dict:
-    """select the camera views of one rank from full-scene step inputs (layouts of synthetic.make_inputs /
-    dataset/utils.py:390-445): per-view tensors are sliced, view-shared ones kept."""
+def slice_views(inputs: dict, views, n_cam: int = 6, scenes: range = None) -> dict:
+    """select the scenes (optional) and the camera views of one rank from full step inputs (layouts of synthetic.make_inputs
+    / dataset/utils.py:390-445): per-view tensors are sliced, view-shared ones kept.  `prompt_embeds` (uncond rows first,
+    then cond rows when it holds 2B rows) follows the scene selection."""
+    if scenes is not None:
+        B = inputs["latents"].shape[0]
+        inputs = slice_scenes(dict(inputs), scenes, B, n_cam)
+        pe = inputs.get("prompt_embeds")
+        if pe is not None and pe.shape[0] == 2 * B:
+            inputs["prompt_embeds"] = torch.cat([pe[scenes.start:scenes.stop], pe[B + scenes.start:B + scenes.stop]])
     idx = torch.as_tensor(list(views))
     out = dict(inputs)
     out["latents"] = inputs["latents"][:, idx].contiguous()

@@ -169,6 +169,72 @@ def test_view_sharded_crossview_three_ranks_gloo():
     _run_view_sharding(3)
 
 
+def _group_worker(rank, world, port, q_out):
+    """ranks in groups of R per scene (ViewShard with world 4 -> 2 groups of 2): the scenes are dealt to the groups, the
+    LayerNorm rows of the halo views are exchanged inside the group and their K/V projections recomputed locally"""
+    from dualdiff_b200.sharding import ViewShard, default_ranks_per_scene
+    from oracle.dualdiff_oracle import mha
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scenes, n_cam, T, C, heads = 4, 6, 5, 16, 2
+    g = torch.Generator().manual_seed(0)
+    ln = torch.randn(scenes * n_cam, T, C, generator=g)
+    wq, wk, wv = (torch.randn(C, C, generator=g) * 0.3 for _ in range(3))
+    ref = _xview_reference(ln @ wq.T, ln @ wk.T, ln @ wv.T, scenes, n_cam, heads)
+    vs = ViewShard(rank, world, n_cam)
+    assert vs.ranks_per_scene == default_ranks_per_scene(world, n_cam)
+    mine = vs.scenes(scenes)
+    sel = torch.tensor([o * n_cam + c for o in mine for c in vs.views])
+    n_outer, n_loc = len(mine), len(sel)
+    ln_ext = torch.zeros(vs.kv_rows(n_outer) * T, C)
+    ln_ext[: n_loc * T] = ln[sel].reshape(n_loc * T, C)
+    vs.exchange_async(ln_ext, n_outer, T)        # CPU tensors: synchronous
+    vs.exchange_wait()
+    ext = ln_ext.reshape(-1, T, C)
+    q, k, v = ext[:n_loc] @ wq.T, ext @ wk.T, ext @ wv.T    # K/V of the halo views recomputed from their LayerNorm rows
+    kv_map = vs.kv_map(n_outer)
+    out = torch.zeros(n_loc, T, C)
+    for s in range(2):
+        idx = kv_map[:, s].long()
+        out += mha(q, k[idx], v[idx], heads)
+    q_out.put((rank, (out - ref[sel]).abs().max().item(), vs.group_index, list(mine), vs.views, (vs.left, vs.right)))
+    dist.destroy_process_group()
+
+
+def test_view_shard_groups_four_ranks_gloo():
+    world = 4
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_group_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, grp, mine, views, peers in res:
+        assert err < 1e-4, (rank, err)
+        assert grp == rank // 2 and mine == [2 * grp, 2 * grp + 1] and views == [3 * (rank % 2) + i for i in range(3)]
+        assert peers == (rank ^ 1, rank ^ 1)          # exchanges stay inside the group
+
+
+def test_view_shard_world_sizes():
+    from dualdiff_b200.sharding import ViewShard, default_ranks_per_scene
+    import pytest
+    assert [default_ranks_per_scene(w) for w in (1, 2, 3, 4, 6, 8, 12)] == [1, 2, 3, 2, 6, 2, 6]
+    for world in (1, 2, 3, 4, 6, 8):
+        shards = [ViewShard(r, world) for r in range(world)]
+        R = shards[0].ranks_per_scene
+        scenes = 2 * (world // R)
+        units = sorted((s, v) for vs in shards for s in vs.scenes(scenes) for v in vs.views)
+        assert units == [(s, v) for s in range(scenes) for v in range(6)]          # every (scene, view) exactly once
+    with pytest.raises(ValueError):
+        ViewShard(0, 8).scenes(3)                    # 4 groups need at least 4 scenes
+    with pytest.raises(ValueError):
+        ViewShard(0, 8, ranks_per_scene=3)
+
+
 def test_view_shard_kv_map_and_slicing():
     from dualdiff_b200.sharding import ViewShard, slice_views
     from dualdiff_b200 import synthetic as S
