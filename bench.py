@@ -2,12 +2,19 @@
 """bench.py — DualDiff denoising-step throughput on B200 (contract in the task statement / DESIGN.md §Measurement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--scenes B] [--impl ours|reference]
+                    [--workload scenes|viewshard|frameshard] [--total-scenes S] [--no-extra]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one loop body of the sampler (pipeline_bev_controlnet.py:381-504) over a batch of B six-view
 224x400 scenes per GPU: ControlNet-bg + ControlNet-fg + multi-view UNet + CFG + UniPC update, bf16 kernels.
 Workload at N=1 = BASELINE.json configs[1] (B=8 scenes, CFG, UniPC) — `value` is scene-steps/s over all ranks
-(weak scaling: B scenes per GPU, scenes are independent, no collectives).  Prints ONE JSON line on rank 0.
+(weak scaling: B scenes per GPU, scenes are independent, no collectives; `--total-scenes S` fixes the job instead:
+strong scaling, BASELINE configs[2] as written with S = 64).  Prints ONE JSON line on rank 0.
+
+The two configurations that need a collective are measured by the same code: `--workload viewshard` (configs[3]: 448x800,
+camera views split over the ranks of a scene group, neighbour-view exchange over NCCL) and `--workload frameshard`
+(configs[4]: 16-frame x 6-view clips, frames split over the ranks, temporal K/V all-gather).  The default run appends a
+short measurement of both under `extra_workloads` (skip with --no-extra), so the driver's 1/2/4/8 scaling runs record them.
 """
 import argparse
 import json
@@ -97,45 +104,100 @@ def dist_env():
 # -------------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------------
-def run_ours(args):
+WORKLOADS = {
+    "scenes": "BASELINE.json configs[1]: UniPC+CFG sampling steps, batch {B} six-view 224x400 scenes per GPU (latent 28x50, "
+              "n={n} images/step), bf16 kernels, random-init SDv1.5-shaped weights",
+    "viewshard": "BASELINE.json configs[3]: UniPC+CFG sampling steps of six-view 448x800 scenes (latent 56x100), camera views "
+                 "split over the {R} rank(s) of a scene group, {B} scene(s) per group, n={n} images/step per GPU, neighbour-view "
+                 "exchange for the cross-view attention over NCCL/NVLink",
+    "frameshard": "BASELINE.json configs[4]: UniPC+CFG sampling steps of {clips} video clip(s) of 16 frames x 6 views (224x400), "
+                  "frames split over the ranks ({fl} frames of every clip per GPU, n={n} images/step per GPU), temporal K/V "
+                  "all-gather over NCCL/NVLink",
+}
+
+
+class Workload:
+    """one configuration of the hot path on this rank: the denoiser, how to (re)load its inputs, and how many six-view
+    scenes the whole job advances per step"""
+
+    def __init__(self, name, args, rank, world, dev, models):
+        import torch
+        import common
+        from dualdiff_b200 import synthetic as S
+        from dualdiff_b200.pipeline import DualDiffDenoiser
+        from dualdiff_b200.sharding import FrameShard, ViewShard, shard_scenes
+        self.name, self.world = name, world
+        unet, nets = models["unet"], models["nets"]
+        self.parallelism, self.scaling, kw, prep_kw = f"scene-sharded x{world}, no collectives", "weak", {}, {}
+        if name == "scenes":
+            self.h, self.w = H, W
+            if args.total_scenes:
+                mine = shard_scenes(args.total_scenes, rank, world)
+                B, self.scenes_per_step, self.scaling = len(mine), args.total_scenes, "strong"
+                if B == 0:
+                    raise SystemExit(f"--total-scenes {args.total_scenes} leaves rank {rank} of {world} without a scene")
+            else:
+                B, self.scenes_per_step = args.scenes, world * args.scenes
+            seed = 1 + rank
+            self.desc = WORKLOADS[name].format(B=B, n=12 * B)
+        elif name == "viewshard":
+            self.h, self.w = 2 * H, 2 * W
+            vs = ViewShard(rank, world) if world > 1 else None
+            R = vs.ranks_per_scene if vs is not None else 1
+            B = R * args.hd_scenes                     # scenes of this rank's group; every rank holds B * 6 / R views (x2 CFG)
+            self.scenes_per_step = world * args.hd_scenes
+            seed = 101 + (vs.group_index if vs is not None else 0)
+            kw, prep_kw = dict(view_shard=vs), (dict(scenes_sliced=True) if vs is not None else {})
+            self.parallelism = (f"{world // R} group(s) x {R} rank(s) per scene: (scene, view) units, LayerNorm rows of the 2 halo "
+                                f"views exchanged per cross-view block by NCCL send/recv on a side stream") if vs is not None else \
+                "one GPU: all six views local, no exchange"
+            self.desc = WORKLOADS[name].format(B=B, R=R, n=12 * args.hd_scenes)
+        elif name == "frameshard":
+            self.h, self.w = H, W
+            F = 16
+            if F % world:
+                raise SystemExit(f"frameshard: world size {world} must divide {F} frames")
+            unet = models["video_unet"]()
+            unet.frame_shard = FrameShard(rank, world, F) if world > 1 else None
+            clips, fl = world * args.clips, F // world
+            B = clips * fl                             # (clip, frame) pairs of this rank, frame-minor
+            self.scenes_per_step = clips * F
+            seed = 201 + rank
+            self.parallelism = f"frames of every clip split over {world} rank(s); all-gather of the temporal K/V rows per block" \
+                if world > 1 else "one GPU: all 16 frames local, no exchange"
+            self.desc = WORKLOADS[name].format(clips=clips, fl=fl, n=12 * B)
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        self.B = B
+        self.inp_cpu = S.make_inputs(B, self.h, self.w, seed=seed, L_bg=28, L_fg=32)
+        self.inp = common.to_dev(self.inp_cpu, dev)
+        self.den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=True, **kw)
+        if args.serial_branches:
+            self.den.parallel_branches = False
+        self.unet, self.nets, self.prep_kw = unet, nets, prep_kw
+
+    def prepare(self, den=None, steps=4):
+        i = self.inp
+        (den or self.den).prepare(i["latents"], i["prompt_embeds"], i["camera_param"], [i["boxes_bg"], i["boxes_fg"]],
+                                  [i["cond_bg"], i["cond_fg"]], num_inference_steps=max(steps, 4),
+                                  **(self.prep_kw if den is None else {}))
+
+    def host_latents(self):
+        """this rank's latents as the denoiser keeps them ((scene, local view) images, fp32 NCHW), in pinned host memory"""
+        return self.den.latents.detach().float().cpu().contiguous().pin_memory()
+
+
+def measure(wl, K, Wm, barrier, rank, local, sample_clocks=True):
+    """device-resident and end-to-end timing of K sampler steps of one workload (W warm-up steps each); returns a dict"""
     import torch
-    import common
-    from dualdiff_b200 import _lib, ops, synthetic as S
-    from dualdiff_b200.pipeline import DualDiffDenoiser
-
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — dualdiff_b200 has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    B, K, Wm = args.scenes, args.steps, args.warmup
-    unet, nets, sds = common.build_models()
-    for m in [unet] + nets:
-        m.pack(dev)
-    inp_cpu = S.make_inputs(B, H, W, seed=1 + rank, L_bg=28, L_fg=32)
-    inp = common.to_dev(inp_cpu, dev)
-    total_steps = Wm + K
-    den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=True)
-
-    def prepare():
-        den.prepare(inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]],
-                    [inp["cond_bg"], inp["cond_fg"]], num_inference_steps=max(total_steps, 4))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    den = wl.den
     # ---- device-resident timed region: K sampler steps, latents already in HBM -----------------------
-    prepare()
+    wl.prepare(steps=Wm + K)
     for i in range(Wm):
         den.step(i)
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -143,16 +205,15 @@ def run_ours(args):
         den.step(i)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and sample_clocks else None
     ms = e0.elapsed_time(e1)
-    launches = den.launches_per_step * K
     final_lat = den.latents.float().cpu()
     assert torch.isfinite(final_lat).all(), "non-finite latents after the timed steps"
 
     # ---- end-to-end through the public API with HOST buffers: per step H2D(latents) + step + D2H(latents)
-    host_lat = inp_cpu["latents"].reshape(B * 6, 4, H, W).float().contiguous().pin_memory()
+    wl.prepare(steps=Wm + K)
+    host_lat = wl.host_latents()
     host_out = torch.empty_like(host_lat).pin_memory()
-    prepare()
     for i in range(Wm):
         den.latents.copy_(host_lat, non_blocking=True)
         den.step(i)
@@ -168,29 +229,93 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()                                 # the host really has it
     f1.record()
     barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    wall_e2e = (time.perf_counter() - t0) * 1e3
-    ms_e2e = max(ms_e2e, wall_e2e)
+    ms_e2e = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3)
+    return dict(ms=ms, ms_e2e=ms_e2e, clocks=clocks, launches=den.launches_per_step * K if den._graph is not None else None,
+                h2d=host_lat.numel() * 4, d2h=host_out.numel() * 4, cuda_graph=den._graph is not None, graph_note=den.graph_note)
 
+
+def run_ours(args):
+    import torch
+    import common
+    from dualdiff_b200 import _lib, ops, synthetic as S
+    from dualdiff_b200.pipeline import DualDiffDenoiser
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — dualdiff_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
     if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(tt[0]), float(tt[1])
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    unet, nets, sds = common.build_models()
+    for m in [unet] + nets:
+        m.pack(dev)
 
-    # ---- roofline pass (rank 0): per-launch CUDA events on the launching stream, eager replay of one step
-    roof, breakdown = None, None
-    if rank == 0:
-        den2 = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=False)
+    def video_unet():
+        """the multi-view UNet with temporal blocks (16-frame clips): same seeded weights plus the temporal projections"""
+        from dualdiff_b200.networks import UNet2DConditionModelMultiview
+        with torch.device("meta"):
+            vu = UNet2DConditionModelMultiview(cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS, temporal_frames=16)
+        man = S.manifest_of(vu)
+        sd = {k: (sds["unet"][k] if k in sds["unet"] else S.init_tensor(k, tuple(shape), common.SEEDS["unet"]))
+              for k, shape in man.items()}
+        vu.load_state_dict(sd, strict=True, assign=True)
+        vu.eval()
+        vu.pack(dev)
+        return vu
+
+    models = dict(unet=unet, nets=nets, video_unet=video_unet)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(*vals):
+        if world == 1:
+            return vals
+        tt = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tuple(float(x) for x in tt)
+
+    wl = Workload(args.workload, args, rank, world, dev, models)
+    m = measure(wl, K, Wm, barrier, rank, local)
+    ms, ms_e2e = reduce_max(m["ms"], m["ms_e2e"])
+    launches = m["launches"]
+    if launches is None:      # eager launches (a refused capture): count one step
+        n0 = _lib.lib().dd_launch_count()
+        wl.den.step(0)
+        torch.cuda.synchronize()
+        launches = (_lib.lib().dd_launch_count() - n0) * K
+
+    # ---- roofline pass (rank 0): per-launch CUDA events on the launching stream, eager SERIAL replay of one step of the
+    #      main workload (not the timed graph: the graph overlaps the three branches on three streams)
+    roof, breakdown, sub = None, None, None
+    if rank == 0 and wl.den.view_shard is None and getattr(wl.unet, "frame_shard", None) is None:
+        den2 = DualDiffDenoiser(wl.unet, wl.nets, guidance_scale=2.0, use_cuda_graph=False)
         den2.parallel_branches = False   # serial launch order: clean per-kernel device times
-        den2.prepare(inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]],
-                     [inp["cond_bg"], inp["cond_fg"]], num_inference_steps=4)
+        wl.prepare(den2)
         for _ in range(2):
             den2.step(0)
         torch.cuda.synchronize()
+        # sub-metrics (SURVEY §8d): CUDA events around the three sub-networks and the CFG + scheduler kernel
+        den2.phase_events = []
+        torch.cuda._sleep(int(0.08 * 1.9e9))
+        den2.step(1)
+        torch.cuda.synchronize()
+        ev = den2.phase_events
+        den2.phase_events = None
+        names = ("ms_controlnet_bg", "ms_controlnet_fg", "ms_unet", "ms_cfg_sched")
+        sub = {n: round(ev[i].elapsed_time(ev[i + 1]), 3) for i, n in enumerate(names)}
+        sub["note"] = ("serial eager replay of one step (branches one after the other); the timed CUDA graph overlaps the two "
+                       "ControlNet branches with the UNet encoder on three streams, so ms_per_step < the sum")
         # give the host a head start so the per-launch event intervals are pure device time (kernels back to back)
         torch.cuda._sleep(int(0.08 * 1.9e9))
         ops.profile_start()
-        den2.step(1)
+        den2.step(2)
         rec = ops.profile_stop()
         if os.environ.get("DD_BENCH_SHAPES"):
             agg = {}
@@ -215,43 +340,166 @@ def run_ours(args):
                 "traffic": ncu_traffic("gemm_tcgen05_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_launches_traffic.json)",
                 "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
                 "share_of_step": round(g["ms"] / tot, 3),
-                "flops_per_step": g["flops"], "note": "algorithmic 2*M*N*K per launch summed over one step / summed CUDA-event durations"}
+                "flops_per_step": g["flops"],
+                "note": "algorithmic 2*M*N*K per launch summed over one step / summed CUDA-event durations, measured in a serial "
+                        "EAGER replay of one step after the timed region (per-launch events cannot be recorded inside the timed graph)"}
         breakdown = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 3), "launches": v["launches"],
                          "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
                          "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] and not v["flops"] else None}
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        del den2
+
+    # ---- the two configurations with a collective, measured briefly in the same run (all ranks take part)
+    extra = None
+    if args.workload == "scenes" and not args.no_extra and not args.total_scenes:
+        extra = {}
+        main_den = wl.den
+        wl.den = None
+        del main_den
+        torch.cuda.empty_cache()
+        for name in ("viewshard", "frameshard"):
+            try:
+                if name == "frameshard" and 16 % world:
+                    raise RuntimeError(f"world size {world} does not divide 16 frames")
+                w2 = Workload(name, args, rank, world, dev, models)
+                k2 = max(3, min(K, args.extra_steps))
+                m2 = measure(w2, k2, 3, barrier, rank, local, sample_clocks=False)
+                ms2, ms2e = reduce_max(m2["ms"], m2["ms_e2e"])
+                extra[name] = {"value": round(w2.scenes_per_step * k2 / (ms2 * 1e-3), 3), "unit": UNIT, "n_gpus": world,
+                               "steps": k2, "warmup": 3, "ms_per_step": round(ms2 / k2, 3), "scaling": w2.scaling,
+                               "e2e": {"value": round(w2.scenes_per_step * k2 / (ms2e * 1e-3), 3), "unit": UNIT,
+                                       "h2d_bytes_per_step": m2["h2d"], "d2h_bytes_per_step": m2["d2h"]},
+                               "config": {"workload": w2.desc, "scenes_per_step_all_gpus": w2.scenes_per_step,
+                                          "parallelism": w2.parallelism, "cuda_graph": m2["cuda_graph"]}}
+                if m2["graph_note"]:
+                    extra[name]["config"]["graph_note"] = m2["graph_note"]
+                del w2
+                torch.cuda.empty_cache()
+            except Exception as e:     # an extra must never lose the main line
+                extra[name] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    break              # the ranks may no longer be in step: no further collectives
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    value = world * B * K / (ms * 1e-3)
+    value = wl.scenes_per_step * K / (ms * 1e-3)
     pk = peaks()
+    res_scale = (wl.h * wl.w) / (H * W)
     out = {
-        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if wl.h == H else METRIC.replace("224x400", f"{8 * wl.h}x{8 * wl.w}"),
+        "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE.json configs[1]: UniPC+CFG sampling steps, batch {B} six-view 224x400 scenes per GPU "
-                               f"(latent 28x50, n={12 * B} images/step), bf16 kernels, random-init SDv1.5-shaped weights",
-                   "scenes_per_gpu": B, "cfg": True, "guidance_scale": 2.0, "scheduler": "UniPC(bh2, order 2)",
+        "config": {"workload": wl.desc, "scenes_per_gpu": wl.B if args.workload == "scenes" else None,
+                   "scenes_per_step_all_gpus": wl.scenes_per_step, "cfg": True, "guidance_scale": 2.0,
+                   "scheduler": "UniPC(bh2, order 2)",
                    "l2": "inputs larger than L2 (3.3 GB bf16 weights + >1 GB activations per step vs 126 MB L2)",
-                   "cuda_graph": True, "parallelism": f"scene-sharded x{world}, no collectives"},
-        "tflops_per_scene_step": TFLOP_PER_SCENE_STEP_CFG,
-        "model_tflops": round(value * TFLOP_PER_SCENE_STEP_CFG, 1),
-        "model_frac_of_peak": round(value * TFLOP_PER_SCENE_STEP_CFG / world / pk["tf_sustained"], 4),
-        "e2e": {"value": round(world * B * K / (ms_e2e * 1e-3), 3), "unit": UNIT,
-                "h2d_bytes_per_step": host_lat.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+                   "cuda_graph": m["cuda_graph"], "parallelism": wl.parallelism,
+                   "branch_streams": 1 if args.serial_branches else 3},
+        "e2e": {"value": round(wl.scenes_per_step * K / (ms_e2e * 1e-3), 3), "unit": UNIT,
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                 "ms_per_step": round(ms_e2e / K, 3)},
         "gpu_launches": int(launches),
-        "clocks": clocks,
+        "clocks": m["clocks"],
         "roofline": roof,
         "kernel_breakdown": breakdown,
+        "sub_metrics": sub,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if m["graph_note"]:
+        out["config"]["graph_note"] = m["graph_note"]
+    if args.warmup_requested != Wm:
+        out["config"]["warmup_note"] = f"--warmup {args.warmup_requested} raised to {Wm} (minimum of the timing rules)"
+    if args.workload == "scenes":
+        out["tflops_per_scene_step"] = TFLOP_PER_SCENE_STEP_CFG
+        out["model_tflops"] = round(value * TFLOP_PER_SCENE_STEP_CFG, 1)
+        out["model_frac_of_peak"] = round(value * TFLOP_PER_SCENE_STEP_CFG / world / pk["tf_sustained"], 4)
+    if extra is not None:
+        out["extra_workloads"] = extra
+    if world == 1 and args.workload == "scenes" and not args.no_library_baseline:
+        out["library_gpu_baseline"] = library_gpu_baseline(sds, dev, wl.B, budget_s=args.library_budget)
+    if world == 1 and not args.no_cpu_baseline and args.workload == "scenes":
         out["cpu_baseline"] = cpu_baseline(sds, budget_s=args.cpu_budget)
     emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------------------------
+# "library GPU" line (SURVEY §8d last row): the SAME step through the oracle restatement, moved to the B200 in bf16 with
+# torch's own kernels (cuDNN convolutions, cuBLAS GEMMs, F.scaled_dot_product_attention = flash attention) -- what the
+# reference's PyTorch path would get from stock libraries on this box.  Test infrastructure, timed after the product
+# numbers; never on the product path.
+# -------------------------------------------------------------------------------------------------------
+def library_gpu_baseline(sds, dev, scenes, budget_s=60.0):
+    import torch
+    import torch.nn.functional as F
+    from dualdiff_b200 import synthetic as S
+    import common
+    try:
+        from oracle import dualdiff_oracle as O
+    except Exception as e:
+        return {"unavailable": f"oracle not importable: {e}"}
+    keep = {n: getattr(O, n) for n in ("mha", "_lin", "_conv", "_gn", "_ln")}
+    try:
+        def cast_first(fn):      # the oracle is written for one dtype: bring the input to the layer's (bf16) weight dtype
+            def wrapped(sd, p, x, *a, **k):
+                return fn(sd, p, x.to(sd[p + ".weight"].dtype), *a, **k)
+            return wrapped
+        for n in ("_lin", "_conv", "_gn", "_ln"):
+            setattr(O, n, cast_first(keep[n]))
+
+        def sdpa(q, k, v, heads):
+            b, lq, c = q.shape
+            d = c // heads
+            qh, kh, vh = (t.reshape(b, t.shape[1], heads, d).transpose(1, 2) for t in (q, k, v))
+            return F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b, lq, c)
+        O.mha = sdpa
+        bf = torch.bfloat16
+        gsd = {n: {k: v.to(dev, bf) for k, v in sd.items()} for n, sd in sds.items()}
+        with torch.no_grad(), torch.device(dev):
+            sch = O.UniPC()
+            sch.set_timesteps(25)
+            times, used = [], scenes
+            while used >= 1:
+                try:
+                    with torch.device("cpu"):
+                        inp = S.make_inputs(used, H, W, seed=1, L_bg=28, L_fg=32)
+                    inp = common.to_dev(inp, dev)
+                    inp = {k: ({kk: (vv.to(bf) if vv.is_floating_point() else vv) for kk, vv in v.items()} if isinstance(v, dict)
+                               else v.to(bf)) for k, v in inp.items()}
+                    lat = inp["latents"]
+                    t_start = time.perf_counter()
+                    for r in range(4):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        out = O.noise_prediction(gsd["unet"], gsd["bg"], gsd["fg"], lat, int(sch.timesteps[r]), inp, 2.0, True)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        times.append(e0.elapsed_time(e1))
+                        if time.perf_counter() - t_start > budget_s:
+                            break
+                    finite = bool(torch.isfinite(out["eps"].float()).all())
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    times, used = [], used // 2
+                    torch.cuda.empty_cache()
+        if not times:
+            return {"unavailable": "out of memory at one scene"}
+        t = min(times[1:]) if len(times) > 1 else times[0]
+        return {"value": round(used / (t * 1e-3), 3), "unit": UNIT, "ms_per_step": round(t, 2), "scenes_per_step": used,
+                "kind": "oracle restatement on the GPU: bf16, eager torch ops (cuDNN conv, cuBLAS GEMM, SDPA flash attention), "
+                        "no CUDA graph, ControlNet K/V and condition embedding recomputed every step as the reference does; "
+                        "noise prediction + CFG only (scheduler update excluded)",
+                "finite": finite, "torch": torch.__version__, "note": "test infrastructure, timed on the same B200 after the product numbers; "
+                                                    "best of the steps after the first"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        for n, fn in keep.items():
+            setattr(O, n, fn)
+        torch.cuda.empty_cache()
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -345,12 +593,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=8, help="six-view scenes per GPU per step (BASELINE configs[1]: 8)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="scenes", choices=["scenes", "viewshard", "frameshard"])
+    ap.add_argument("--total-scenes", type=int, default=0, help="strong scaling: this many scenes per step over ALL ranks "
+                    "(BASELINE configs[2]: 64) instead of --scenes per GPU")
+    ap.add_argument("--hd-scenes", type=int, default=2, help="viewshard: 448x800 scenes per step per GPU-equivalent of work")
+    ap.add_argument("--clips", type=int, default=1, help="frameshard: 16-frame clips per step per GPU-equivalent of work")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short viewshard / frameshard measurements of the default run")
+    ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--serial-branches", action="store_true", help="A/B: launch the two condition branches and the UNet encoder "
+                    "on ONE stream instead of three (default: three streams inside the CUDA graph)")
+    ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--library-budget", type=float, default=45.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--cpu-budget-total", type=float, default=150.0)
     args = ap.parse_args()
+    args.warmup_requested = args.warmup
     if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3
+        args.warmup = 3      # timing rule: at least 3 warm-up steps; the line reports the value used and the one requested
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -380,6 +380,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float sl2 = p.scale_log2e;
     const uint64_t SL2 = pack_f32x2(sl2, sl2);
     uint32_t k = 0;                               // key tiles processed by this warpgroup (parity of the per-tile barriers)
+    bool s_ready = false;                         // s_full of tile k already seen complete (probed one tile ahead)
     int item = blockIdx.x;
     while (item < n_items && !tile_active(item, t)) item += stride;
 #pragma unroll 1
@@ -392,7 +393,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll 1
         for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++k) {
           DD_TR(0, k);
-          mbar_wait(bs_full, k & 1);
+          if (!s_ready) mbar_wait(bs_full, k & 1);   // usually probed already while the previous tile's P store was in flight
           tc_fence_after();
           DD_TR(1, k);
           uint32_t sv[BN];
@@ -402,6 +403,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           } else {
 #pragma unroll
             for (int c = 0; c < BN; c += 32) tmem_ld_32x32(tmem_S + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+          }
+          // the previous tile's P V must have retired before P is overwritten / O is rescaled: it was issued a whole tile ago, so
+          // this wait only costs the latency of the barrier test -- which hides behind the TMEM load in flight
+          if (k > 0) {
+            mbar_wait(bo_full, (k - 1) & 1);
+            tc_fence_after();
           }
           tmem_ld_wait();
           tc_fence_before();
@@ -460,11 +467,6 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             l += s0 + s1;
           }
           DD_TR(3, k);
-          // the previous tile's P V must have retired before P is overwritten / O is rescaled
-          if (k > 0) {
-            mbar_wait(bo_full, (k - 1) & 1);
-            tc_fence_after();
-          }
           DD_TR(4, k);
           if (grow && jt > 0) {
 #pragma unroll
@@ -485,6 +487,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           } else {
             tmem_st_32x16(tmem_P, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
           }
+          s_ready = mbar_test_wait(bs_full, (k + 1) & 1);   // S of the next tile (issued when this one reached the registers)
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bp_full);
@@ -511,9 +514,15 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// attn_v2_kernel: one query tile per CTA (head_dim 80 / 160).  Key tiles are 64 wide so that S + O + P fit 256 TMEM
+// attn_v2_kernel: one query tile per work item (head_dim 80 / 160).  Key tiles are 64 wide so that S + O + P fit 256 TMEM
 // columns and two CTAs share an SM; the softmax loop reads the whole S tile, reduces its maximum on four independent
 // FMNMX3 chains, and runs scale/subtract and the row sum as packed FFMA2 / FADD2.
+// The CTAs walk the items  blockIdx.x, blockIdx.x + gridDim.x, ...  (item = (image, head, query tile), tile fastest) as ONE
+// stream of K/V tiles through the TMA ring: levels 1-3 have 1-6 key tiles per item (350 / 91 / 28 tokens), so with one CTA
+// per item the barrier set-up, the TMEM allocation and the first Q / K / V round trip were most of a CTA's life (ncu: 102 us
+// per level-1 self-attention launch against a 24 us MUFU bound).  Run persistently they are paid once per CTA, the K/V tiles
+// of the next item stream in during the epilogue of the current one, and its query tile is reloaded while the softmax
+// warps work on the last key tile.  With gridDim.x == number of items the same code is the one-item-per-CTA kernel.
 // Measured dead ends (profiles/README.md): two softmax warpgroups splitting the columns of ONE tile, chunk-wise software
 // pipelining of the TMEM loads (the former DD_ATTN_PIPE variant), staggering the two CTAs of an SM, ex2.approx.f16x2.
 // ---------------------------------------------------------------------------------------------------------------
@@ -552,7 +561,10 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if ((smem_base & 1023u) != 0) __trap();
 
   const int warp = threadIdx.x >> 5;
-  const int q_tile = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
+  const int n_q_tiles = (p.Lq + ATT_BM - 1) / ATT_BM;
+  const int n_items = n_q_tiles * p.heads * p.n_img;    // item = (image, head, query tile), tile fastest
+  const int stride = gridDim.x;
+  const int total = p.n_src * p.n_kv_tiles;             // key tiles per item
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -577,23 +589,33 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + O_COL;
   const uint32_t tmem_P = tmem_base + P_COL;
-  const int total = p.n_src * p.n_kv_tiles;
   if (warp == ISSUER) {
     // ---------------- TMA producer + UMMA issuer (warp-uniform control flow, one elected lane issues) ----------------
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, QCH * Q_CHUNK);
-      for (int c = 0; c < QCH; ++c)
-        tma_load_3d(sQ + c * Q_CHUNK, &tmQ, q_full, p.q_col0 + head * p.q_hs + c * 64, q_tile * ATT_BM, img);
     }
     __syncwarp();
-    auto produce = [&](int g) {
-      const int s = g % STAGES;
-      const uint32_t ph = (g / STAGES) & 1;
-      mbar_wait(kv_empty + 8 * s, ph ^ 1);
-      const int src = g / p.n_kv_tiles, jt = g - src * p.n_kv_tiles;
+    auto load_q = [&](int item) {
+      const int r = item / n_q_tiles;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, QCH * Q_CHUNK);
+        for (int c = 0; c < QCH; ++c)
+          tma_load_3d(sQ + c * Q_CHUNK, &tmQ, q_full, p.q_col0 + (r % p.heads) * p.q_hs + c * 64, (item % n_q_tiles) * ATT_BM,
+                      r / p.heads);
+      }
+      __syncwarp();
+    };
+    // K/V tiles of ALL items of this CTA in stream order; gp counts the tiles produced (ring stage / phase)
+    int p_item = blockIdx.x, p_t = 0, gp = 0;
+    auto produce = [&]() {
+      if (p_item >= n_items) return;
+      const int s = gp % STAGES;
+      mbar_wait(kv_empty + 8 * s, ((gp / STAGES) & 1) ^ 1);
+      const int r = p_item / n_q_tiles;
+      const int head = r % p.heads, img = r / p.heads;
+      const int src = p_t / p.n_kv_tiles, jt = p_t - src * p.n_kv_tiles;
       const int kv_img = p.kv_map ? p.kv_map[img * p.n_src + src] : img;
       const uint32_t sK = sKV + s * KV_STAGE_BYTES;
       const uint32_t sV = sK + QCH * K_CHUNK;
@@ -605,6 +627,8 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tma_load_3d(sV + c * K_CHUNK, &tmV, kv_full + 8 * s, p.v_col0 + head * p.v_hs + c * 64, jt * BN, kv_img);
       }
       __syncwarp();
+      ++gp;
+      if (++p_t == total) { p_t = 0; p_item += stride; }
     };
     auto issue_qk = [&](int g) {
       const int s = g % STAGES;
@@ -621,38 +645,58 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       __syncwarp();
     };
+    load_q(blockIdx.x);                                  // gridDim.x <= n_items: every CTA has a first item
 #pragma unroll 1
-    for (int g = 0; g < STAGES && g < total; ++g) produce(g);
-    mbar_wait(q_full, 0);
-    issue_qk(0);
+    for (int i = 0; i < STAGES; ++i) produce();
+    int g = 0;                                           // key tiles issued by this CTA (parity of the per-tile barriers)
+    uint32_t n_q = 0;                                    // query tiles loaded so far (parity of q_full)
 #pragma unroll 1
-    for (int g = 0; g < total; ++g) {
-      const int s = g % STAGES;
-      // S(g+1) = Q K(g+1)^T is issued as soon as the softmax threads hold S(g) in registers
-      if (STAGES > 1 && g + 1 < total) {
-        mbar_wait(s_free, g & 1);
+    for (int item = blockIdx.x; item < n_items; item += stride) {
+      mbar_wait(q_full, n_q & 1);
+      ++n_q;
+      if (g > 0) {                                       // S of the previous item's last tile is in registers
+        mbar_wait(s_free, (g - 1) & 1);
         tc_fence_after();
-        issue_qk(g + 1);
       }
-      mbar_wait(p_full, g & 1);
-      tc_fence_after();
-      const uint32_t sV = sKV + s * KV_STAGE_BYTES + QCH * K_CHUNK;
-      // O += P V : A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk) {
-          umma_bf16_ts(tmem_O, tmem_P + kk * 8, umma_smem_desc(sV + kk * 16 * 128, K_CHUNK, 1024, 2), IDESC_O,
-                       (kk != 0 || (g % p.n_kv_tiles) != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
+      issue_qk(g);
+      int jt = 0;
+#pragma unroll 1
+      for (int i = 0; i < total; ++i, ++g) {
+        const int s = g % STAGES;
+        const bool last = (i + 1 == total);
+        // S(g+1) = Q K(g+1)^T is issued as soon as the softmax threads hold S(g) in registers; after the last key tile of
+        // the item every Q K^T has retired by then, and the query tile of the next item is loaded instead
+        if (!last) {
+          if (STAGES > 1) {
+            mbar_wait(s_free, g & 1);
+            tc_fence_after();
+            issue_qk(g + 1);
+          }
+        } else if (item + stride < n_items) {
+          mbar_wait(s_free, g & 1);
+          load_q(item + stride);
         }
-        umma_commit(kv_empty + 8 * s);
-        umma_commit(o_full);
-      }
-      __syncwarp();
-      if (g + STAGES < total) produce(g + STAGES);   // stage s is free once P(g) V(g) retires (kv_empty)
-      if (STAGES == 1 && g + 1 < total) {            // single stage: K(g+1) only lands after P(g) V(g) has retired
-        mbar_wait(s_free, g & 1);
+        mbar_wait(p_full, g & 1);
         tc_fence_after();
-        issue_qk(g + 1);
+        const uint32_t sV = sKV + s * KV_STAGE_BYTES + QCH * K_CHUNK;
+        // O += P V : A = P from TMEM (8 packed columns per 16 keys), B = V (MN-major: rows = keys, 64-wide dv chunks)
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk) {
+            umma_bf16_ts(tmem_O, tmem_P + kk * 8, umma_smem_desc(sV + kk * 16 * 128, K_CHUNK, 1024, 2), IDESC_O,
+                         (kk != 0 || jt != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
+          }
+          umma_commit(kv_empty + 8 * s);
+          umma_commit(o_full);
+        }
+        __syncwarp();
+        if (++jt == p.n_kv_tiles) jt = 0;
+        produce();                                     // stage s is free once P(g) V(g) retires (kv_empty)
+        if (STAGES == 1 && !last) {                    // single stage: K(g+1) only lands after P(g) V(g) has retired
+          mbar_wait(s_free, g & 1);
+          tc_fence_after();
+          issue_qk(g + 1);
+        }
       }
     }
   } else {
@@ -661,22 +705,32 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // cycles of the 16-lane MUFU pipe and ~730 cycles of the TMEM read port (tcgen05.ld moves ~90 B/clk/SM,
     // profiles/micro/tmem_bench.cu; the S tile is 64 KB) — both shared by the two CTAs of an SM.
     const int row = threadIdx.x;                // == TMEM lane
-    const int q_row = q_tile * ATT_BM + row;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     const float sl2 = p.scale_log2e;
     const uint64_t SL2 = pack_f32x2(sl2, sl2);
-    bf16* orow = p.out + ((long long)img * p.Lq + q_row) * p.out_ld + head * p.o_hs;
     constexpr int NC = BN / 2;                  // S columns per pass (P is published in two passes)
     int g = 0;
+    bool s_ready = false;                       // s_full of tile g already seen complete (probed one tile ahead)
+#pragma unroll 1
+    for (int item = blockIdx.x; item < n_items; item += stride) {
+      const int r = item / n_q_tiles;
+      const int q_row = (item % n_q_tiles) * ATT_BM + row;
+      bf16* orow = p.out + ((long long)(r / p.heads) * p.Lq + q_row) * p.out_ld + (r % p.heads) * p.o_hs;
     for (int src = 0; src < p.n_src; ++src) {
       float m = -INFINITY, l = 0.f;
 #pragma unroll 1
       for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
-        mbar_wait(s_full, g & 1);
+        if (!s_ready) mbar_wait(s_full, g & 1);    // usually probed already while the previous tile's P store was in flight
         tc_fence_after();
         uint32_t sv[BN];
 #pragma unroll
         for (int c = 0; c < BN; c += 32) tmem_ld_32x32(tmem_S + lane_sel + c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
+        // the previous tile's P V must have retired before P is overwritten / O is rescaled: it was issued a whole tile ago,
+        // so this wait costs only the latency of the barrier test, hidden behind the TMEM load in flight
+        if (g > 0) {
+          mbar_wait(o_full, (g - 1) & 1);
+          tc_fence_after();
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(s_free);                       // S(g) now lives in registers -> the issuer starts S(g+1)
@@ -727,11 +781,6 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             pk[(jj >> 1) - pass * (NC / 2)] = pack_bf16(p0, p1);
           }
           if (pass == 0) {
-            // the previous tile's P V must have retired before P is overwritten / O is rescaled
-            if (g > 0) {
-              mbar_wait(o_full, (g - 1) & 1);
-              tc_fence_after();
-            }
             if (grow && jt > 0) {
 #pragma unroll
               for (int c = 0; c < DVP; c += 16) {
@@ -756,15 +805,18 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
           l += s0 + s1;
         }
+        s_ready = mbar_test_wait(s_full, (g + 1) & 1);   // S of the next tile (issued when this one reached the registers)
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full);
       }
-      // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first)
+      // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first).  The issuer is
+      // already loading the next source / item; its first P V waits for this thread's next p_full arrival.
       mbar_wait(o_full, (g - 1) & 1);
       tc_fence_after();
       store_o_row<DV, DVP>(tmem_O + lane_sel, 1.f / l, orow, q_row < p.Lq, src > 0);
       tc_fence_before();
+    }
     }
   }
   tc_fence_before();
@@ -794,7 +846,17 @@ static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t st
   if (rc) return rc;
   p.n_kv_tiles = (a->lk + BN - 1) / BN;
   if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB>), (int)smem)) return e;
-  dim3 grid((a->lq + ATT_BM - 1) / ATT_BM, a->heads, a->n_img);
+  const long long n_items = (long long)((a->lq + ATT_BM - 1) / ATT_BM) * a->heads * a->n_img;
+  DD_CHECK(n_items < (1ll << 30), -1, "dd_attention: too many work items");
+  // Short K/V streams (levels 1-3: at most 12 key tiles per item) run persistently on MINB CTAs per SM, every CTA taking the
+  // same number of items (+-1); long streams launch one CTA per item and leave the balancing to the hardware scheduler.
+  const long long slots = (long long)MINB * num_sms();
+  long long ctas = n_items;
+  if (a->variant != 1 && (long long)a->n_src * p.n_kv_tiles <= 16 && n_items > slots) {
+    const long long rounds = (n_items + slots - 1) / slots;
+    ctas = (n_items + rounds - 1) / rounds;
+  }
+  dim3 grid((unsigned)ctas);
   attn_v2_kernel<DQK, DV, DVP, BN, STAGES, MINB><<<grid, ATT_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
   DD_CUDA(cudaGetLastError());
   return 0;
@@ -852,8 +914,12 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   p.heads = a->heads; p.n_img = a->n_img;
   switch (a->head_dim) {
     case 40:
-      DD_CHECK(a->q_head_stride >= 48 && a->k_head_stride >= 48, -1,
-               "dd_attention: head_dim 40 needs Q/K heads zero-padded to a 48-column stride");
+      // The 48-wide Q.K^T reads 8 columns beyond a 40-wide head.  Either side may keep unpadded (stride 40) heads as long as the
+      // OTHER side is zero-padded to 48: the extra columns then meet zeros (txt_con_XFormersAttn_plus feeds the output of one
+      // attention -- 8 heads of 40 columns -- as the queries of the next).
+      DD_CHECK(a->q_head_stride >= 40 && a->k_head_stride >= 40 && (a->q_head_stride >= 48 || a->k_head_stride >= 48) &&
+                   (a->q_head_stride == 40 || a->q_head_stride >= 48) && (a->k_head_stride == 40 || a->k_head_stride >= 48),
+               -1, "dd_attention: head_dim 40 needs the Q or the K heads zero-padded to a 48-column stride");
       if (a->variant == 1) return launch_attn_v2<48, 40, 48, 128, 3, 2>(a, p, stream);   // testing hook: one-tile kernel
       if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 6, 0>(a, p, stream);     // testing hook: all ex2 on MUFU
       return launch_attn_pp<48, 40, 48, 48, 6, 1>(a, p, stream);

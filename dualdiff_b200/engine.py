@@ -201,6 +201,15 @@ def pack_sfa(pk: "Packer", p="txt_con_fusion"):
     pk.lin(p + ".to_out.0")
 
 
+def pack_sfa_plus(pk: "Packer", p="txt_con_fusionp"):
+    """txt_con_XFormersAttn_plus (txt_con_fusion.py:184-208): the three condition projections as ONE weight
+    [q (heads padded to 48) | k (padded) | v] and the two text projections as one [k (padded) | v]"""
+    f = lambda n: pk.sd[f"{p}.{n}.weight"].detach().float()
+    pk.put(p + ".occ.w", torch.cat([pad_heads(f("to_q_occ"), 40, 48), pad_heads(f("to_k_occ"), 40, 48), f("to_v_occ")], 0).to(BF))
+    pk.put(p + ".txt.w", torch.cat([pad_heads(f("to_k_txt"), 40, 48), f("to_v_txt")], 0).to(BF))
+    pk.lin(p + ".to_out.0")
+
+
 def pack_cond_embedding(pk: "Packer", e="controlnet_cond_embedding"):
     """ControlNetConditioningEmbedding (map_embedder.py:81-112): conv_in (3 -> 16, channels padded to 8), 6 blocks, conv_out"""
     pk.conv3(e + ".conv_in", pad_cin_to=8)
@@ -209,7 +218,8 @@ def pack_cond_embedding(pk: "Packer", e="controlnet_cond_embedding"):
     pk.conv3(e + ".conv_out")
 
 
-def pack_controlnet(sd, device, use_occ_3d: bool):
+def pack_controlnet(sd, device, use_occ_3d: bool, fusion: str = "sfa"):
+    """fusion: "sfa" (txt_con_fusion, the dual-branch configs) or "sfa_plus" (txt_con_fusionp, occ_bg_fusionp.yaml)"""
     pk = Packer(sd, device)
     tl: List[str] = []
     pk.encoder(False, tl)
@@ -224,10 +234,14 @@ def pack_controlnet(sd, device, use_occ_3d: bool):
         pk.lin32("bbox_embedder." + n)
     for n in ("_class_tokens", "null_class_feature", "null_pos_feature"):
         pk.put("bbox_embedder." + n, pk.f32(sd["bbox_embedder." + n]))
-    pack_sfa(pk)
+    if fusion == "sfa_plus":
+        pack_sfa_plus(pk)
+    else:
+        pack_sfa(pk)
     if not use_occ_3d:
         pack_cond_embedding(pk)
     pk.out["use_occ_3d"] = use_occ_3d
+    pk.out["fusion"] = fusion
     return pk.out
 
 
@@ -563,11 +577,25 @@ def sfa_rows(P, cond_rows, txt_rows, n, T, L, p="txt_con_fusion") -> torch.Tenso
     return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond_rows)
 
 
+def sfa_plus_rows(P, cond_rows, txt_rows, n, T, L, p="txt_con_fusionp") -> torch.Tensor:
+    """txt_con_XFormersAttn_plus on rows (txt_con_fusion.py:289-335): q' = MHA(W_q cond, W_kt txt, W_vt txt) gathers the text,
+    then out = cond + W_o MHA(q', W_k cond, W_v cond) + b_o.  q' leaves the first attention as 8 heads of 40 columns and is
+    read by the second one with a 40-column head stride: the 8 columns the 48-wide Q tile takes from the next head meet the
+    zero padding of the keys."""
+    proj = ops.gemm(cond_rows, P[p + ".occ.w"])                  # [n*T, 384 | 384 | 320] = q | k_occ | v_occ
+    kv = ops.gemm(txt_rows, P[p + ".txt.w"])                     # [n*L, 384 | 320]
+    q2 = ops.attention(proj, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48, q_cols=8 * 48)
+    a = ops.attention(q2, proj, proj, n_img=n, lq=T, lk=T, heads=8, head_dim=40, q_hs=40, k_col0=8 * 48, v_col0=16 * 48)
+    return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond_rows)
+
+
 def sfa(P, cond: Act, enc_rows, lk_total, n) -> torch.Tensor:
     """Semantic Fusion Attention inside a branch.  enc_rows: [n*(78+L), 768]; the 77 text tokens are rows 1..77 of each image
     (camera token dropped, unet_addon_rawbox.py:977).  A strided window cannot be addressed as [n*77, ld]: the 77-token window
     is copied once (plumbing, timestep-invariant)."""
     txt = enc_rows.reshape(n, lk_total, enc_rows.shape[1])[:, 1:78].contiguous().reshape(n * 77, enc_rows.shape[1])
+    if P.get("fusion", "sfa") == "sfa_plus":
+        return sfa_plus_rows(P, cond.rows, txt, n, cond.H * cond.W, 77)
     return sfa_rows(P, cond.rows, txt, n, cond.H * cond.W, 77)
 
 

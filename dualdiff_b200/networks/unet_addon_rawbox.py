@@ -168,12 +168,13 @@ class BEVControlNetModel(_tree.ModelBase):
             raise RuntimeError("dualdiff_b200 has no CPU path: move the model to a CUDA device (sm_100a) before use")
         if getattr(self, "use_cam_in_temb", False):
             raise NotImplementedError("use_cam_in_temb: the reference itself asserts False here (:953-954)")
-        if not getattr(self, "use_txt_con_fusion", False) or getattr(self, "use_txt_con_fusionp", False):
-            raise NotImplementedError("the DualDiff branches run with use_txt_con_fusion=True, use_txt_con_fusionp=False "
-                                      "(configs/exp/dual_branch_augloss_fusion_8pts.yaml:44-45)")
+        sfa, sfap = bool(getattr(self, "use_txt_con_fusion", False)), bool(getattr(self, "use_txt_con_fusionp", False))
+        if sfa == sfap:      # the reference asserts they are exclusive (:972) and adds nothing to the condition with neither
+            raise NotImplementedError("exactly one of use_txt_con_fusion (configs/exp/dual_branch_augloss_fusion_8pts.yaml:44) and "
+                                      "use_txt_con_fusionp (configs/exp/occ_bg_fusionp.yaml) must be set")
         if getattr(self, "use_box_adapter", False):
             raise NotImplementedError("use_box_adapter is incompatible with the dual branch (multiview_runner.py:240)")
-        self._packed = engine.pack_controlnet(self.state_dict(), device, bool(self.use_occ_3d))
+        self._packed = engine.pack_controlnet(self.state_dict(), device, bool(self.use_occ_3d), "sfa_plus" if sfap else "sfa")
         self._packed_versions = self._param_versions()
         self._prep_cache = None
         return self

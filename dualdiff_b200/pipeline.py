@@ -29,9 +29,9 @@ class DualDiffDenoiser:
         self.scheduler = scheduler if scheduler is not None else UniPCMultistepScheduler()
         self.scheduler.guidance_scale = guidance_scale
         self.view_shard = view_shard               # sharding.ViewShard: camera views split across ranks (config 4)
-        # The view-sharded step is captured like the unsharded one (NCCL send/recv and the side-stream fork/join are
-        # capturable); the frame-sharded video configuration still launches eagerly (its all-gather sizes follow the clip).
-        self.use_cuda_graph = use_cuda_graph and getattr(unet, "frame_shard", None) is None
+        # The view- and frame-sharded steps are captured like the unsharded one: NCCL send/recv, all-gather and the
+        # side-stream fork/join are capturable.  A capture the NCCL build refuses falls back to eager launches (graph_note).
+        self.use_cuda_graph = use_cuda_graph
         self.graph_note = None                     # why a requested CUDA graph was not used (capture failed), if so
         self._graph = None
         self.device = None
@@ -40,19 +40,23 @@ class DualDiffDenoiser:
         # (grids below one wave of 148 SMs) overlap instead of serialising.
         self.parallel_branches = True
         self._side = None
+        # measurement hook: when a list, the serial (parallel_branches = False) step records a CUDA event at the start and
+        # after ControlNet-bg, ControlNet-fg, the UNet and the CFG + scheduler kernel (bench.py's sub_metrics)
+        self.phase_events = None
 
     # -------------------------------------------------------------------------------------------------
     def prepare(self, latents, prompt_embeds, camera_param, bboxes_3d_data: List[Dict[str, torch.Tensor]], images,
-                num_inference_steps: int):
+                num_inference_steps: int, scenes_sliced: bool = False):
         """latents (B, 6, 4, h, w) fp32; prompt_embeds (2B, 77, 768) uncond first (or (B, ...) without CFG);
         camera_param (B, 6, 3, 7); bboxes_3d_data = [bg boxes, fg map vectors]; images = [bg panorama
-        (B, 3, 8h, 48w), fg ORS (B*6, 320, h, w)]."""
+        (B, 3, 8h, 48w), fg ORS (B*6, 320, h, w)].
+        View-sharded: every rank passes the full inputs of the call (`scenes_sliced`: only the scenes of its group)."""
         if self.view_shard is not None:
             # every rank passes the FULL inputs of the call and keeps the scenes of its group and its own camera views
             from .sharding import slice_scenes, slice_views
             vs = self.view_shard
             B_all = latents.shape[0]
-            mine = vs.scenes(B_all)
+            mine = range(B_all) if scenes_sliced else vs.scenes(B_all)
             full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
                         cond_fg=images[1], prompt_embeds=prompt_embeds)
             loc = slice_views(full, vs.views, latents.shape[1], scenes=mine)
@@ -130,18 +134,29 @@ class DualDiffDenoiser:
         """one loop body (pipeline:381-504) on the current stream; reads t / coefficients from device buffers"""
         B6, H, W, G = self.B * self.n_cam, self.H, self.W, self.G
         Pu = self.unet._packed
+        ev = self.phase_events if not self.parallel_branches else None
+
+        def mark():
+            if ev is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append(e)
+
         if not self.parallel_branches:
             acc = None
+            mark()
             for net, prep in zip(self.nets, self.preps):
                 down, mid = engine.controlnet_forward(net._packed, prep, self.latents, G, B6, H, W, self.t_cur,
                                                       None if acc is None else acc)
                 acc = down + [mid]
+                mark()
             temb = engine.time_embedding(Pu, self.t_cur)
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
                                  lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
             self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
             eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
+            mark()
         else:
             main = torch.cuda.current_stream()
             if self._side is None:
@@ -168,6 +183,7 @@ class DualDiffDenoiser:
                                       before_residuals=join)
         ops.cfg_sched_step(eps, self.latents, self.last, self.m0, self.m1, self.coef_cur, n_img=B6, c=4, hw=H * W,
                            cfg=self.cfg, eps_nchw=False)
+        mark()
         self.eps_rows = eps
         return eps
 
@@ -196,10 +212,10 @@ class DualDiffDenoiser:
                         self._step_kernels()
                     self._graph = graph
                 except Exception as e:      # a capture the driver / NCCL build refuses: launch eagerly, and say so
-                    if self.view_shard is None:
+                    if self.view_shard is None and getattr(self.unet, "frame_shard", None) is None:
                         raise
                     import logging
-                    self.graph_note = f"CUDA graph capture of the view-sharded step failed ({type(e).__name__}: {e}); eager launches"
+                    self.graph_note = f"CUDA graph capture of the sharded step failed ({type(e).__name__}: {e}); eager launches"
                     logging.getLogger(__name__).warning(self.graph_note)
                     self.use_cuda_graph = False
                     torch.cuda.synchronize()

@@ -116,8 +116,9 @@ typedef struct dd_attention_args {
   int q_head_stride, k_head_stride, v_head_stride;
   int n_img, n_kv_img, heads, head_dim, lq, lk, n_src;
   float scale;
-  int variant;                /* testing hook (head_dim 40): 0 = auto (two query tiles per CTA, 25 % of the exponentials on
-                                 the FMA pipe), 1 = one-tile kernel, 2 = two-tile kernel with every exponential on MUFU */
+  int variant;                /* testing hook: 0 = auto.  head_dim 40: 0 = two query tiles per CTA, 25 % of the exponentials on
+                                 the FMA pipe, 1 = one-tile kernel, 2 = two-tile kernel with every exponential on MUFU;
+                                 head_dim 80 / 160: 1 = one CTA per work item instead of the persistent item loop */
 } dd_attention_args;
 DD_API int dd_attention(const dd_attention_args* args, void* stream);
 

@@ -255,6 +255,19 @@ def sfa(sd: SD, cond, txt, p="txt_con_fusion"):
     return o.transpose(1, 2).reshape(n, c, h, w) + cond
 
 
+# networks/txt_con_fusion.py:184-337 — txt_con_XFormersAttn_plus (config use_txt_con_fusionp, occ_bg_fusionp.yaml)
+def sfa_plus(sd: SD, cond, txt, p="txt_con_fusionp"):
+    """two chained attentions (:313-318): the condition queries first gather the text (keys / values = text tokens), and the
+    result -- still split into the 8 heads -- is the QUERY of a self-attention over the condition's own keys / values; then
+    the output projection and the residual (:324-335)."""
+    n, c, h, w = cond.shape
+    x = cond.reshape(n, c, h * w).transpose(1, 2)
+    q = mha(_lin(sd, p + ".to_q_occ", x, False), _lin(sd, p + ".to_k_txt", txt, False), _lin(sd, p + ".to_v_txt", txt, False), 8)
+    o = mha(q, _lin(sd, p + ".to_k_occ", x, False), _lin(sd, p + ".to_v_occ", x, False), 8)
+    o = _lin(sd, p + ".to_out.0", o)
+    return o.transpose(1, 2).reshape(n, c, h, w) + cond
+
+
 # networks/map_embedder.py:114-138 — ControlNetConditioningEmbedding (bg branch)
 def cond_embedding(sd: SD, cond, p="controlnet_cond_embedding"):
     per_w = cond.shape[-1] // 6
@@ -296,7 +309,10 @@ def controlnet_forward(sd: SD, sample, timestep, camera_param, bboxes_3d_data, e
         emb = emb.repeat_interleave(n_cam, dim=0)                               # :951-952
     x = _conv(sd, "conv_in", x)                                                 # :965
     cond = controlnet_cond if use_occ_3d else cond_embedding(sd, controlnet_cond)   # :967-970
-    cond = sfa(sd, cond, enc_cam[:, 1:])                                        # :973-978 (camera token dropped)
+    if "txt_con_fusionp.to_q_occ.weight" in sd:                                 # use_txt_con_fusionp (:981-986)
+        cond = sfa_plus(sd, cond, enc_cam[:, 1:])
+    else:
+        cond = sfa(sd, cond, enc_cam[:, 1:])                                    # :973-978 (camera token dropped)
     x = x + cond                                                                # :990
     enc = torch.cat([enc_cam, tok], dim=1)                                      # :1007
     x, skips = _down_path(sd, x, emb, enc, False)                               # :998-1015

@@ -53,6 +53,8 @@ def main():
               f"rel_l2(max over ranks)={float(t[0]):.3e} block ms(max over ranks)={float(t[1]):.2f}", flush=True)
     if os.environ.get("VIDEO_UNET", "0") == "1":
         video_unet(rank, world, dev, F, h, w)
+    if os.environ.get("VIDEO_STEP", "0") == "1":
+        video_step(rank, world, dev, F, h, w)
     dist.destroy_process_group()
 
 
@@ -93,6 +95,55 @@ def video_unet(rank, world, dev, F, h, w):
         ok = float(t[0]) < 2e-2
         print(f"VIDEOUNET {'OK' if ok else 'FAIL'} world={world} frames={F} views=6 latent={h}x{w} rel_l2(max over ranks)="
               f"{float(t[0]):.3e} UNet forward ms(max over ranks, eager launches + NCCL all-gathers)={float(t[1]):.2f}", flush=True)
+
+
+def video_step(rank, world, dev, F, h, w):
+    """the whole sampler step (both condition branches + video UNet + CFG + UniPC) of one clip, frames sharded over the
+    ranks and the step captured in a CUDA graph with its all-gathers: every rank's latents after two steps must equal its
+    frames of the single-GPU run.  Prints 'VIDEOSTEP OK ...'."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import common
+    from dualdiff_b200.networks import UNet2DConditionModelMultiview
+    from dualdiff_b200.pipeline import DualDiffDenoiser
+    _, nets, _ = common.build_models()
+    with torch.device("meta"):
+        unet = UNet2DConditionModelMultiview(cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS, temporal_frames=F)
+    unet.load_state_dict(S.init_state_dict(S.manifest_of(unet), seed=0), strict=True, assign=True)
+    for m in [unet] + nets:
+        m.pack(dev)
+    inp = common.to_dev(S.make_inputs(F, h, w, seed=4, L_bg=28, L_fg=32, same_noise_across_views=False), dev)   # scene = frame
+    fs = FrameShard(rank, world, F)
+
+    def run(inputs, shard):
+        unet.frame_shard = shard
+        den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=shard is not None)
+        den.prepare(inputs["latents"], inputs["prompt_embeds"], inputs["camera_param"], [inputs["boxes_bg"], inputs["boxes_fg"]],
+                    [inputs["cond_bg"], inputs["cond_fg"]], num_inference_steps=8)
+        for i in range(2):
+            den.step(i)
+        torch.cuda.synchronize()
+        return den
+
+    full = run(inp, None).latents.reshape(F, 6, 4, h, w)[fs.frames].clone()
+    fr = fs.frames
+    B = F
+    loc = {k: inp[k][fr[0]:fr[-1] + 1] for k in ("latents", "camera_param", "cond_bg")}
+    loc["cond_fg"] = inp["cond_fg"][fr[0] * 6:(fr[-1] + 1) * 6]
+    loc["prompt_embeds"] = torch.cat([inp["prompt_embeds"][fr[0]:fr[-1] + 1], inp["prompt_embeds"][B + fr[0]:B + fr[-1] + 1]])
+    for k in ("boxes_bg", "boxes_fg"):
+        loc[k] = {kk: v[fr[0]:fr[-1] + 1] for kk, v in inp[k].items()}
+    den = run(loc, fs)
+    part = den.latents.reshape(len(fr), 6, 4, h, w)
+    rel = ((part - full).norm() / full.norm()).item()
+    t = torch.tensor([rel], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ok = float(t[0]) < 2e-2
+        print(f"VIDEOSTEP {'OK' if ok else 'FAIL'} world={world} frames={F} latent={h}x{w} cuda_graph={den._graph is not None} "
+              f"rel_l2 of the latents after 2 steps (max over ranks)={float(t[0]):.3e}", flush=True)
+        if den.graph_note:
+            print(den.graph_note, flush=True)
+    unet.frame_shard = None
 
 
 if __name__ == "__main__":

@@ -21,14 +21,14 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     h, w = (int(x) for x in os.environ.get("LATENT", "28x50").split("x"))
-    B, steps = int(os.environ.get("SCENES", "1")), 2
+    vs = ViewShard(rank, world)
+    B, steps = int(os.environ.get("SCENES", str(vs.n_groups))), 2      # at least one scene per group of ranks
     unet, nets, _ = common.build_models()
     for m in [unet] + nets:
         m.pack(dev)
     inp = common.to_dev(S.make_inputs(B, h, w, seed=1, L_bg=28, L_fg=32), dev)
     args = (inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]],
             [inp["cond_bg"], inp["cond_fg"]])
-    vs = ViewShard(rank, world)
     den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, view_shard=vs)
     den.prepare(*args, num_inference_steps=8)
     for i in range(steps):
@@ -45,13 +45,14 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     den.latents.copy_(shard_lat)
-    shard = den.latents.reshape(B, vs.v_loc, 4, h, w)
+    mine = vs.scenes(B)
+    shard = den.latents.reshape(len(mine), vs.v_loc, 4, h, w)
     # reference: the same two steps unsharded on this rank's GPU
     ref = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=False)
     ref.prepare(*args, num_inference_steps=8)
     for i in range(steps):
         ref.step(i)
-    full = ref.latents.reshape(B, 6, 4, h, w)[:, vs.views].clone()
+    full = ref.latents.reshape(B, 6, 4, h, w)[mine.start:mine.stop][:, vs.views].clone()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(steps, steps + 3):
@@ -64,8 +65,11 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         ok = float(t[0]) < 2e-2
-        print(f"VIEWSHARD {'OK' if ok else 'FAIL'} world={world} latent={h}x{w} scenes={B} rel_l2(max over ranks)={float(t[0]):.3e} "
-              f"ms/step(max over ranks)={float(t[1]):.2f} unsharded on one GPU (eager)={float(t[2]):.2f}", flush=True)
+        print(f"VIEWSHARD {'OK' if ok else 'FAIL'} world={world} ranks_per_scene={vs.ranks_per_scene} latent={h}x{w} scenes={B} "
+              f"cuda_graph={den._graph is not None} rel_l2(max over ranks)={float(t[0]):.3e} "
+              f"ms/step(max over ranks)={float(t[1]):.2f} all scenes unsharded on one GPU (eager)={float(t[2]):.2f}", flush=True)
+        if den.graph_note:
+            print(den.graph_note, flush=True)
     dist.destroy_process_group()
 
 

@@ -215,3 +215,40 @@ def test_patch_weight_packing_reproduces_the_convolution():
     out = rows @ wp.float().T + b
     ref = torch.nn.functional.conv2d(x, w.to(torch.bfloat16).float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, 16)
     assert (out - ref).abs().max() < 1e-4
+
+
+def _sfa_plus_case():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden_sfa_plus as MG
+    from dualdiff_b200.networks.txt_con_fusion import txt_con_XFormersAttn_plus
+    fix = torch.load(os.path.join(common.GOLDEN, "sfa_plus_small.pt"))
+    with torch.device("meta"):
+        m = txt_con_XFormersAttn_plus()
+    sd = S.init_state_dict(S.manifest_of(m), fix["weight_seed"])
+    cond, txt = MG.inputs(fix["input_seed"])
+    assert tuple(cond.shape) == tuple(fix["shape"])
+    return fix, sd, cond, txt
+
+
+def test_sfa_plus_oracle_matches_reference_golden():
+    """txt_con_XFormersAttn_plus (txt_con_fusion.py:184-337): the oracle restatement reproduces the output of the reference's
+    own class (golden made by oracle/make_golden_sfa_plus.py)"""
+    fix, sd, cond, txt = _sfa_plus_case()
+    with torch.no_grad():
+        out = O.sfa_plus({"txt_con_fusionp." + k: v for k, v in sd.items()}, cond, txt)
+    assert ((out - fix["out"]).abs().max() / fix["out"].abs().max()).item() < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/MD_txt_con_fusion"), reason="reference tree only exists in the build container")
+def test_sfa_plus_oracle_matches_reference_class_live():
+    from oracle import reference_model as RM
+    RM._paths()
+    from magicdrive.networks.txt_con_fusion import txt_con_XFormersAttn_plus as Ref
+    fix, sd, cond, txt = _sfa_plus_case()
+    ref = Ref()
+    ref.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        want = ref(None, cond, encoder_hidden_states=txt)
+        out = O.sfa_plus({"txt_con_fusionp." + k: v for k, v in sd.items()}, cond, txt)
+    assert torch.equal(want, fix["out"])
+    assert ((out - want).abs().max() / want.abs().max()).item() < 1e-5
