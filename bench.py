@@ -349,13 +349,68 @@ def run_ours(args):
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         del den2
 
+    # ---- the line of the main workload is complete here (rank 0); what follows can only add to it
+    out = None
+    if rank == 0:
+        value = wl.scenes_per_step * K / (ms * 1e-3)
+        pk = peaks()
+        out = {
+            "metric": METRIC if wl.h == H else METRIC.replace("224x400", f"{8 * wl.h}x{8 * wl.w}"),
+            "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl.desc, "scenes_per_gpu": wl.B if args.workload == "scenes" else None,
+                       "scenes_per_step_all_gpus": wl.scenes_per_step, "cfg": True, "guidance_scale": 2.0,
+                       "scheduler": "UniPC(bh2, order 2)",
+                       "l2": "inputs larger than L2 (3.3 GB bf16 weights + >1 GB activations per step vs 126 MB L2)",
+                       "cuda_graph": m["cuda_graph"], "parallelism": wl.parallelism,
+                       "branch_streams": 1 if args.serial_branches else 3},
+            "e2e": {"value": round(wl.scenes_per_step * K / (ms_e2e * 1e-3), 3), "unit": UNIT,
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "ms_per_step": round(ms_e2e / K, 3)},
+            "gpu_launches": int(launches),
+            "clocks": m["clocks"],
+            "roofline": roof,
+            "kernel_breakdown": breakdown,
+            "sub_metrics": sub,
+        }
+        if m["graph_note"]:
+            out["config"]["graph_note"] = m["graph_note"]
+        if args.warmup_requested != Wm:
+            out["config"]["warmup_note"] = f"--warmup {args.warmup_requested} raised to {Wm} (minimum of the timing rules)"
+        if args.workload == "scenes":
+            out["tflops_per_scene_step"] = TFLOP_PER_SCENE_STEP_CFG
+            out["model_tflops"] = round(value * TFLOP_PER_SCENE_STEP_CFG, 1)
+            out["model_frac_of_peak"] = round(value * TFLOP_PER_SCENE_STEP_CFG / world / pk["tf_sustained"], 4)
+
+    # A captured step with NCCL nodes keeps the communicator busy (destroy_process_group() waits for it): release it now.
+    wl.den.release_graph()
+
+    # Watchdog: the additions below (multi-rank extras, process-group teardown) must never lose the line above.  When it
+    # fires, rank 0 prints the line as it stands and every rank leaves without further collectives.
+    import threading
+    state = {"done": False}
+
+    def bail():
+        if state["done"]:
+            return
+        state["done"] = True
+        if out is not None:
+            out.setdefault("extra_workloads", {})["watchdog"] = f"extras / teardown exceeded {args.extra_budget:.0f} s; line printed by the watchdog"
+            emit(out)
+        os._exit(0)
+
+    dog = threading.Timer(args.extra_budget, bail)
+    dog.daemon = True
+    dog.start()
+
     # ---- the two configurations with a collective, measured briefly in the same run (all ranks take part)
     extra = None
     if args.workload == "scenes" and not args.no_extra and not args.total_scenes:
         extra = {}
-        main_den = wl.den
+        if out is not None:
+            out["extra_workloads"] = extra
         wl.den = None
-        del main_den
         torch.cuda.empty_cache()
         for name in ("viewshard", "frameshard"):
             try:
@@ -373,6 +428,7 @@ def run_ours(args):
                                           "parallelism": w2.parallelism, "cuda_graph": m2["cuda_graph"]}}
                 if m2["graph_note"]:
                     extra[name]["config"]["graph_note"] = m2["graph_note"]
+                w2.den.release_graph()
                 del w2
                 torch.cuda.empty_cache()
             except Exception as e:     # an extra must never lose the main line
@@ -380,50 +436,24 @@ def run_ours(args):
                 if world > 1:
                     break              # the ranks may no longer be in step: no further collectives
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    value = wl.scenes_per_step * K / (ms * 1e-3)
-    pk = peaks()
-    res_scale = (wl.h * wl.w) / (H * W)
-    out = {
-        "metric": METRIC if wl.h == H else METRIC.replace("224x400", f"{8 * wl.h}x{8 * wl.w}"),
-        "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": wl.desc, "scenes_per_gpu": wl.B if args.workload == "scenes" else None,
-                   "scenes_per_step_all_gpus": wl.scenes_per_step, "cfg": True, "guidance_scale": 2.0,
-                   "scheduler": "UniPC(bh2, order 2)",
-                   "l2": "inputs larger than L2 (3.3 GB bf16 weights + >1 GB activations per step vs 126 MB L2)",
-                   "cuda_graph": m["cuda_graph"], "parallelism": wl.parallelism,
-                   "branch_streams": 1 if args.serial_branches else 3},
-        "e2e": {"value": round(wl.scenes_per_step * K / (ms_e2e * 1e-3), 3), "unit": UNIT,
-                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
-                "ms_per_step": round(ms_e2e / K, 3)},
-        "gpu_launches": int(launches),
-        "clocks": m["clocks"],
-        "roofline": roof,
-        "kernel_breakdown": breakdown,
-        "sub_metrics": sub,
-    }
-    if m["graph_note"]:
-        out["config"]["graph_note"] = m["graph_note"]
-    if args.warmup_requested != Wm:
-        out["config"]["warmup_note"] = f"--warmup {args.warmup_requested} raised to {Wm} (minimum of the timing rules)"
-    if args.workload == "scenes":
-        out["tflops_per_scene_step"] = TFLOP_PER_SCENE_STEP_CFG
-        out["model_tflops"] = round(value * TFLOP_PER_SCENE_STEP_CFG, 1)
-        out["model_frac_of_peak"] = round(value * TFLOP_PER_SCENE_STEP_CFG / world / pk["tf_sustained"], 4)
-    if extra is not None:
-        out["extra_workloads"] = extra
-    if world == 1 and args.workload == "scenes" and not args.no_library_baseline:
-        out["library_gpu_baseline"] = library_gpu_baseline(sds, dev, wl.B, budget_s=args.library_budget)
-    if world == 1 and not args.no_cpu_baseline and args.workload == "scenes":
-        out["cpu_baseline"] = cpu_baseline(sds, budget_s=args.cpu_budget)
-    emit(out)
+    if rank == 0:
+        if world == 1 and args.workload == "scenes" and not args.no_library_baseline:
+            dog.cancel()               # single process: nothing below can wait for another rank
+            out["library_gpu_baseline"] = library_gpu_baseline(sds, dev, wl.B, budget_s=args.library_budget)
+        if world == 1 and not args.no_cpu_baseline and args.workload == "scenes":
+            dog.cancel()
+            out["cpu_baseline"] = cpu_baseline(sds, budget_s=args.cpu_budget)
+        if not state["done"]:
+            state["done"] = True
+            emit(out)
     if world > 1:
+        # the line is out; a teardown that hangs is cut short by a second timer
+        t2 = threading.Timer(30.0, lambda: os._exit(0))
+        t2.daemon = True
+        t2.start()
         dist.destroy_process_group()
+        t2.cancel()
+    dog.cancel()
 
 
 # -------------------------------------------------------------------------------------------------------
@@ -600,6 +630,8 @@ def main():
     ap.add_argument("--clips", type=int, default=1, help="frameshard: 16-frame clips per step per GPU-equivalent of work")
     ap.add_argument("--no-extra", action="store_true", help="skip the short viewshard / frameshard measurements of the default run")
     ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--extra-budget", type=float, default=240.0, help="seconds the extras + teardown may take before the "
+                    "watchdog prints the main line and exits")
     ap.add_argument("--serial-branches", action="store_true", help="A/B: launch the two condition branches and the UNet encoder "
                     "on ONE stream instead of three (default: three streams inside the CUDA graph)")
     ap.add_argument("--no-library-baseline", action="store_true")

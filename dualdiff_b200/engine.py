@@ -376,18 +376,22 @@ def temporal_step(P, p, h, n, T, ctx: StepCtx):
     n_clip = n // (F_loc * V)
     assert n_clip * F_loc * V == n, (n, F_loc, V)
     ln = ops.layernorm(h, P[p + ".norm_temp.g"], P[p + ".norm_temp.b"])
-    qkv = ops.gemm(ln, P[p + ".attn_temp.qkv.w"])
-    kw = dict(n_outer=n_clip, n_view=V, tokens=T, heads=HEADS, head_dim=d, frames_q=F_loc, q_col0=0,
-              k_col0=HEADS * dp, v_col0=2 * HEADS * dp)
+    w_qkv = P[p + ".attn_temp.qkv.w"]
+    kw = dict(n_outer=n_clip, n_view=V, tokens=T, heads=HEADS, head_dim=d, frames_q=F_loc)
     fs = ctx.frame_shard
     if fs is None or fs.world == 1:
-        a = ops.temporal_attention(qkv, qkv, qkv, **kw)
+        qkv = ops.gemm(ln, w_qkv)
+        a = ops.temporal_attention(qkv, qkv, qkv, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, **kw)
     else:
-        # frames sharded over ranks: the one exchange step is an all-gather of the projected rows (K and V columns are
-        # used, Q columns ride along); rank blocks are addressed in place
-        allkv = fs.gather(qkv)
-        a = ops.temporal_attention(qkv, allkv, allkv, frames_kv=F_loc * fs.world, frames_per_rank=F_loc,
-                                   kv_rank_stride=n, **kw)
+        # frames sharded over ranks: the one exchange step is an all-gather of the projected K and V rows.  They are projected
+        # into their own contiguous buffer (the queries stay local: a third less NVLink traffic than gathering the fused
+        # projection); the kernel addresses the gathered rank blocks in place
+        q_cols = HEADS * dp
+        q = ops.gemm(ln, w_qkv[:q_cols])
+        kv = ops.gemm(ln, w_qkv[q_cols:])
+        allkv = fs.gather(kv)
+        a = ops.temporal_attention(q, allkv, allkv, frames_kv=F_loc * fs.world, frames_per_rank=F_loc,
+                                   kv_rank_stride=n, q_col0=0, k_col0=0, v_col0=HEADS * dp, **kw)
     return ops.gemm(a, P[p + ".attn_temp.to_out.0.w"], bias=P[p + ".attn_temp.to_out.0.b"], res1=h)
 
 

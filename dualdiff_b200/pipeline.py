@@ -230,6 +230,14 @@ class DualDiffDenoiser:
         self.step_index = i + 1
         return self.latents
 
+    def release_graph(self):
+        """drop the captured step.  A graph that contains NCCL operations (view- / frame-sharded steps) keeps the communicator
+        busy: `dist.destroy_process_group()` waits for it, so sharded callers release the graph before tearing the group down."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            torch.cuda.synchronize()
+
     def run(self):
         for i in range(len(self.scheduler.timesteps)):
             self.step(i)

@@ -55,7 +55,12 @@ def main():
         video_unet(rank, world, dev, F, h, w)
     if os.environ.get("VIDEO_STEP", "0") == "1":
         video_step(rank, world, dev, F, h, w)
+    import threading
+    t = threading.Timer(30.0, lambda: os._exit(0))     # teardown must not be able to hang the test
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
+    t.cancel()
 
 
 def video_unet(rank, world, dev, F, h, w):
@@ -143,6 +148,7 @@ def video_step(rank, world, dev, F, h, w):
               f"rel_l2 of the latents after 2 steps (max over ranks)={float(t[0]):.3e}", flush=True)
         if den.graph_note:
             print(den.graph_note, flush=True)
+    den.release_graph()            # graphs with NCCL nodes must be gone before the process group is destroyed
     unet.frame_shard = None
 
 

@@ -70,7 +70,21 @@ def main():
               f"ms/step(max over ranks)={float(t[1]):.2f} all scenes unsharded on one GPU (eager)={float(t[2]):.2f}", flush=True)
         if den.graph_note:
             print(den.graph_note, flush=True)
+    # a captured graph with NCCL send / recv nodes keeps the communicator busy: release it before the group is destroyed
+    # (round-2 finding: destroy_process_group() never returned while the graph was alive)
+    den.release_graph()
+    del den, ref
+    torch.cuda.synchronize()
+    common_shutdown()
+
+
+def common_shutdown():
+    import threading
+    t = threading.Timer(30.0, lambda: os._exit(0))     # teardown must not be able to hang the test
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
+    t.cancel()
 
 
 if __name__ == "__main__":

@@ -73,7 +73,7 @@ def test_multiview_block_with_temporal_attention_matches_oracle():
 def test_frame_sharded_block_matches_single_gpu():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "run_frameshard.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     assert "FRAMESHARD OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 

@@ -14,5 +14,5 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_view_sharded_step_matches_single_gpu():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "run_viewshard.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     assert "VIEWSHARD OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
