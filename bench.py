@@ -13,7 +13,7 @@ strong scaling, BASELINE configs[2] as written with S = 64).  Prints ONE JSON li
 
 The two configurations that need a collective are measured by the same code: `--workload viewshard` (configs[3]: 448x800,
 camera views split over the ranks of a scene group, neighbour-view exchange over NCCL) and `--workload frameshard`
-(configs[4]: 16-frame x 6-view clips, frames split over the ranks, temporal K/V all-gather).  The default run appends a
+(configs[4]: 16-frame x 6-view clips, frames split over the ranks, temporal attention between two all-to-alls).  The default run appends a
 short measurement of both under `extra_workloads` (skip with --no-extra), so the driver's 1/2/4/8 scaling runs record them.
 """
 import argparse
@@ -111,8 +111,8 @@ WORKLOADS = {
                  "split over the {R} rank(s) of a scene group, {B} scene(s) per group, n={n} images/step per GPU, neighbour-view "
                  "exchange for the cross-view attention over NCCL/NVLink",
     "frameshard": "BASELINE.json configs[4]: UniPC+CFG sampling steps of {clips} video clip(s) of 16 frames x 6 views (224x400), "
-                  "frames split over the ranks ({fl} frames of every clip per GPU, n={n} images/step per GPU), temporal K/V "
-                  "all-gather over NCCL/NVLink",
+                  "frames split over the ranks ({fl} frames of every clip per GPU, n={n} images/step per GPU), temporal "
+                  "attention token-sharded between two all-to-alls over NCCL/NVLink",
 }
 
 
@@ -163,7 +163,8 @@ class Workload:
             B = clips * fl                             # (clip, frame) pairs of this rank, frame-minor
             self.scenes_per_step = clips * F
             seed = 201 + rank
-            self.parallelism = f"frames of every clip split over {world} rank(s); all-gather of the temporal K/V rows per block" \
+            self.parallelism = f"frames of every clip split over {world} rank(s); per temporal block the LayerNorm rows go all-to-all to " \
+                f"token shards (all frames, 1/{world} of the tokens), attention output all-to-all back" \
                 if world > 1 else "one GPU: all 16 frames local, no exchange"
             self.desc = WORKLOADS[name].format(clips=clips, fl=fl, n=12 * B)
         else:

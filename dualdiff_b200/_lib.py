@@ -66,6 +66,7 @@ class TemporalAttentionArgs(C.Structure):
         ("n_outer", _i), ("n_view", _i), ("tokens", _i), ("heads", _i), ("head_dim", _i),
         ("frames_q", _i), ("frames_kv", _i), ("frames_per_rank", _i),
         ("kv_rank_stride", _ll), ("scale", _f),
+        ("frames_q_per_rank", _i), ("q_rank_stride", _ll),
     ]
 
 

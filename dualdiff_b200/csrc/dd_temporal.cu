@@ -22,7 +22,9 @@ struct TemporalDev {
   long long q_ld, k_ld, v_ld, out_ld;
   int q_col0, k_col0, v_col0, q_hs, k_hs, v_hs;
   int n_outer, n_view, T, heads;
-  int fq;                 // query frames held locally
+  int fq;                 // query frames
+  int fq_per_rank;        // ... per rank block of the query / output buffers (= fq when they are one block)
+  long long q_rank_stride;   // images between two rank blocks of the query / output buffers
   int fkv, fkv_per_rank;  // key/value frames in total, and per gathered rank block
   long long kv_rank_stride;  // images between two rank blocks of the gathered K/V buffer
   float scale_log2e;
@@ -72,7 +74,8 @@ temporal_attn_kernel(const TemporalDev p) {
   const long long ov = seq / p.T;
   const int v = (int)(ov % p.n_view);
   const long long o = ov / p.n_view;
-  const long long qimg = (o * p.fq + fi) * p.n_view + v;
+  const int rkq = fi / p.fq_per_rank, flq = fi - rkq * p.fq_per_rank;
+  const long long qimg = rkq * p.q_rank_stride + (o * p.fq_per_rank + flq) * p.n_view + v;
   const bf16* qp = p.q + (qimg * p.T + t) * p.q_ld + p.q_col0 + h * p.q_hs;
   const uint8_t* kbase = tsm + (size_t)tl * vec_per_tok * 16;
   auto kv_vec = [&](int f, int which, int vec) {
@@ -149,6 +152,9 @@ int temporal_attention_run(const dd_temporal_attention_args* a, cudaStream_t str
   p.n_outer = a->n_outer; p.n_view = a->n_view; p.T = a->tokens; p.heads = a->heads;
   p.fq = a->frames_q; p.fkv = a->frames_kv; p.fkv_per_rank = a->frames_per_rank;
   p.kv_rank_stride = a->kv_rank_stride;
+  p.fq_per_rank = a->frames_q_per_rank > 0 ? a->frames_q_per_rank : a->frames_q;
+  p.q_rank_stride = a->q_rank_stride;
+  DD_CHECK(a->frames_q % p.fq_per_rank == 0, -1, "dd_temporal_attention: frames_q must be a multiple of frames_q_per_rank");
   p.scale_log2e = a->scale * 1.4426950408889634f;
   const int per_tok = a->heads * a->frames_q;
   const size_t tok_bytes = (size_t)a->frames_kv * 2 * a->heads * a->head_dim * 2;

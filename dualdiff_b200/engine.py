@@ -383,15 +383,22 @@ def temporal_step(P, p, h, n, T, ctx: StepCtx):
         qkv = ops.gemm(ln, w_qkv)
         a = ops.temporal_attention(qkv, qkv, qkv, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, **kw)
     else:
-        # frames sharded over ranks: the one exchange step is an all-gather of the projected K and V rows.  They are projected
-        # into their own contiguous buffer (the queries stay local: a third less NVLink traffic than gathering the fused
-        # projection); the kernel addresses the gathered rank blocks in place
-        q_cols = HEADS * dp
-        q = ops.gemm(ln, w_qkv[:q_cols])
-        kv = ops.gemm(ln, w_qkv[q_cols:])
-        allkv = fs.gather(kv)
-        a = ops.temporal_attention(q, allkv, allkv, frames_kv=F_loc * fs.world, frames_per_rank=F_loc,
-                                   kv_rank_stride=n, q_col0=0, k_col0=0, v_col0=HEADS * dp, **kw)
+        # frames sharded over ranks: the exchange is a pair of all-to-alls around the attention (sharding.FrameShard).  The
+        # LayerNorm rows travel (C columns, not the 3C' of the projections) from "my frames, all tokens" to "all frames, my
+        # tokens"; the Q/K/V projection runs on the received rows -- the same number of rows as before, only other ones --
+        # and the kernel addresses the [rank][clip][F_loc][view] blocks through its rank strides.
+        t_me = len(fs.token_range(T))
+        tok_rows = fs.to_token_shards(ln, n, T)
+        if t_me > 0:
+            qkv = ops.gemm(tok_rows, w_qkv)
+            F = F_loc * fs.world
+            a_tok = ops.temporal_attention(qkv, qkv, qkv, n_outer=n_clip, n_view=V, tokens=t_me, heads=HEADS, head_dim=d,
+                                           frames_q=F, frames_kv=F, frames_per_rank=F_loc, kv_rank_stride=n,
+                                           frames_q_per_rank=F_loc, q_rank_stride=n, q_col0=0, k_col0=HEADS * dp,
+                                           v_col0=2 * HEADS * dp)
+        else:
+            a_tok = torch.empty((0, C), device=h.device, dtype=BF)
+        a = fs.from_token_shards(a_tok, n, T)
     return ops.gemm(a, P[p + ".attn_temp.to_out.0.w"], bias=P[p + ".attn_temp.to_out.0.b"], res1=h)
 
 

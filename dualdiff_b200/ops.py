@@ -219,9 +219,10 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
 
 def temporal_attention(q, k, v, *, n_outer, n_view, tokens, heads, head_dim, frames_q, frames_kv=None,
                        frames_per_rank=None, kv_rank_stride=0, out=None, q_col0=0, k_col0=0, v_col0=0,
-                       q_hs=None, k_hs=None, v_hs=None, scale=None):
+                       q_hs=None, k_hs=None, v_hs=None, scale=None, frames_q_per_rank=None, q_rank_stride=0):
     """attention over the frames of a clip at every (outer, view, token).  q: [n_outer*frames_q*n_view*tokens, *];
-    k/v: frames_kv frames as blocks of [n_outer, frames_per_rank, n_view] images (kv_rank_stride images apart)."""
+    k/v: frames_kv frames as blocks of [n_outer, frames_per_rank, n_view] images (kv_rank_stride images apart); with
+    frames_q_per_rank / q_rank_stride the queries and the output are laid out in rank blocks the same way."""
     _req(q, torch.bfloat16, "q")
     _req(k, torch.bfloat16, "k")
     hs_qk = 48 if head_dim == 40 else head_dim
@@ -240,6 +241,8 @@ def temporal_attention(q, k, v, *, n_outer, n_view, tokens, heads, head_dim, fra
     a.n_outer = n_outer; a.n_view = n_view; a.tokens = tokens; a.heads = heads; a.head_dim = head_dim
     a.frames_q = frames_q; a.frames_kv = frames_kv; a.frames_per_rank = frames_per_rank
     a.kv_rank_stride = kv_rank_stride
+    a.frames_q_per_rank = 0 if frames_q_per_rank is None else frames_q_per_rank
+    a.q_rank_stride = q_rank_stride
     a.scale = float(head_dim) ** -0.5 if scale is None else scale
     nb = 2.0 * heads * head_dim * tokens * n_outer * n_view * (2 * frames_q + 2 * frames_kv)
     with _Rec("temporal_attn", 0.0, nb, f"d{head_dim}_F{frames_q}of{frames_kv}_T{tokens}"):

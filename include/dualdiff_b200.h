@@ -139,6 +139,11 @@ typedef struct dd_temporal_attention_args {
   int frames_q, frames_kv, frames_per_rank;
   long long kv_rank_stride;
   float scale;
+  /* Query / output frames in rank blocks as well (the token-sharded layout after FrameShard's all-to-all, where a rank holds
+   * ALL frames of its share of the tokens): frames_q frames as blocks of [n_outer, frames_q_per_rank, n_view] images,
+   * q_rank_stride images apart.  0 / 0 = one block (queries are this rank's own frames). */
+  int frames_q_per_rank;
+  long long q_rank_stride;
 } dd_temporal_attention_args;
 DD_API int dd_temporal_attention(const dd_temporal_attention_args* args, void* stream);
 

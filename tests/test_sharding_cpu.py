@@ -303,6 +303,54 @@ def test_frame_sharded_temporal_attention_two_ranks_gloo():
         assert err < 1e-5, (rank, err)
 
 
+def _frame_a2a_worker(rank, world, port, q_out):
+    """token-sharded temporal attention: all-to-all of the LayerNorm rows, projection + attention over ALL frames on this
+    rank's share of the tokens (addressing the received rank blocks like csrc/dd_temporal.cu), all-to-all back"""
+    from dualdiff_b200.sharding import FrameShard, slice_frames
+    from oracle.dualdiff_oracle import mha
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_clip, F, V, T, C, heads = 2, 4, 3, 5, 16, 2          # T = 5 over 2 ranks: uneven token shares (3 + 2)
+    g = torch.Generator().manual_seed(0)
+    ln = torch.randn(n_clip * F * V, T, C, generator=g)
+    wq, wk, wv = (torch.randn(C, C, generator=g) * 0.3 for _ in range(3))
+
+    def seq(t):
+        return t.reshape(n_clip, F, V, T, C).permute(0, 2, 3, 1, 4).reshape(n_clip * V * T, F, C)
+    ref = mha(seq(ln @ wq.T), seq(ln @ wk.T), seq(ln @ wv.T), heads)
+    ref = ref.reshape(n_clip, V, T, F, C).permute(0, 3, 1, 2, 4).reshape(n_clip * F * V, T, C)
+    fs = FrameShard(rank, world, F)
+    loc = slice_frames(ln, fs.frames, F, V)                  # [n_loc, T, C], images (clip, local frame, view)
+    n_loc = loc.shape[0]
+    t_me = len(fs.token_range(T))
+    tok = fs.to_token_shards(loc.reshape(n_loc * T, C), n_loc, T)          # [world * n_loc * t_me, C]
+    blk = tok.reshape(world, n_clip, fs.f_loc, V, t_me, C)                   # rank blocks, as the kernel addresses them
+    allf = blk.permute(1, 3, 4, 0, 2, 5).reshape(n_clip * V * t_me, F, C)    # sequences over global frames (rank-major = frame order)
+    o = mha(allf @ wq.T, allf @ wk.T, allf @ wv.T, heads)
+    a_tok = o.reshape(n_clip, V, t_me, world, fs.f_loc, C).permute(3, 0, 4, 1, 2, 5).reshape(world * n_loc * t_me, C)
+    out = fs.from_token_shards(a_tok, n_loc, T).reshape(n_loc, T, C)
+    want = slice_frames(ref, fs.frames, F, V)
+    q_out.put((rank, (out - want).abs().max().item(), t_me))
+    dist.destroy_process_group()
+
+
+def test_frame_sharded_temporal_attention_all_to_all_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_frame_a2a_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[2] for r in res] == [3, 2]
+    for rank, err, _ in res:
+        assert err < 1e-5, (rank, err)
+
+
 def test_frame_shard_partition():
     from dualdiff_b200.sharding import FrameShard
     import pytest

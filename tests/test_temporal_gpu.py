@@ -42,6 +42,15 @@ def test_temporal_attention_kernel(d, F, n_clip, V, T, split):
                                      q_hs=d, k_hs=d, v_hs=d)
         want = block(ref, r)
         assert _rel(out, want) < 2e-2, (r, _rel(out, want))
+    if split > 1:
+        # the token-sharded layout (FrameShard.to_token_shards): the QUERIES and the output are in rank blocks as well, all
+        # frames in one launch
+        qg = torch.cat([block(q, r) for r in range(split)]).cuda()
+        out = ops.temporal_attention(qg, kg, vg, n_outer=n_clip, n_view=V, tokens=T, heads=heads, head_dim=d, frames_q=F,
+                                     frames_kv=F, frames_per_rank=f_loc, kv_rank_stride=n_clip * f_loc * V,
+                                     frames_q_per_rank=f_loc, q_rank_stride=n_clip * f_loc * V, q_hs=d, k_hs=d, v_hs=d)
+        want = torch.cat([block(ref, r) for r in range(split)])
+        assert _rel(out, want) < 2e-2, _rel(out, want)
 
 
 def test_multiview_block_with_temporal_attention_matches_oracle():
