@@ -146,14 +146,19 @@ __device__ __forceinline__ void store_o_row(uint32_t tmem_o_row, float inv, bf16
 //   * POLY: one pair of every four is exponentiated on the FMA pipe (exp2_poly_pair) instead of the MUFU pipe, which then
 //     has 25 % fewer operations; with four warps per scheduler the polynomial of one warp overlaps the MUFU stream of the
 //     others (the all-or-nothing and same-warp forms measured slower in round 1).
+//   * ONES: the V heads carry 1.0 in column DV (written by the bias of the value projection), so O[:, DV] = sum_k P[:, k]: the
+//     softmax denominator is accumulated by the tensor core together with the numerator -- from the same bf16-rounded P --
+//     and is rescaled with it; the softmax warps drop the packed row-sum adds (a sixth of the per-element instructions of
+//     a loop that ncu shows issue-limited: 58 % issue slots busy, MUFU 54 %, profiles/r02_ncu_attn_L0_self.txt).
 // TMEM columns of query tile t (base t * 128): S [0, BN) | P [BN, BN + BN/2) | O [BN + BN/2, BN + BN/2 + DVP).
 // ---------------------------------------------------------------------------------------------------------------
-template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
+template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY, int ONES>
 __global__ void __launch_bounds__(PP_THREADS, 2)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnDev p) {
   static_assert(DQK <= 64 && DVP <= 64 && DQK % 16 == 0 && DVP % 16 == 0, "one 64-column swizzle chunk per operand");
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 64 && STAGES >= 3 && STAGES <= 8, "key tile / ring geometry");
+  static_assert(ONES == 0 || DV < DVP, "the column of ones lives in the padding of the V heads");
   constexpr int Q_TILE = ATT_BM * 128;                  // bytes: 128 query rows x 64 bf16
   constexpr int K_TILE = BN * 128;                      // bytes: BN key rows x 64 bf16 (a multiple of the 1024-byte swizzle atom)
   constexpr int KV_STAGE_BYTES = 2 * K_TILE;
@@ -453,15 +458,17 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
-            const uint64_t PP = pack_f32x2(p0, p1);
-            const int u = jp & 3;
-            if (u == 0) acc0 = add_f32x2(acc0, PP);
-            if (u == 1) acc1 = add_f32x2(acc1, PP);
-            if (u == 2) acc2 = add_f32x2(acc2, PP);
-            if (u == 3) acc3 = add_f32x2(acc3, PP);
+            if constexpr (ONES == 0) {
+              const uint64_t PP = pack_f32x2(p0, p1);
+              const int u = jp & 3;
+              if (u == 0) acc0 = add_f32x2(acc0, PP);
+              if (u == 1) acc1 = add_f32x2(acc1, PP);
+              if (u == 2) acc2 = add_f32x2(acc2, PP);
+              if (u == 3) acc3 = add_f32x2(acc3, PP);
+            }
             pk[jp] = pack_bf16(p0, p1);
           }
-          {
+          if constexpr (ONES == 0) {
             float s0, s1;
             unpack_f32x2(add_f32x2(add_f32x2(acc0, acc1), add_f32x2(acc2, acc3)), s0, s1);
             l += s0 + s1;
@@ -497,6 +504,12 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // already feeding the next source / item: its first P V cannot start before this warpgroup's next p_full arrival.
         mbar_wait(bo_full, (k - 1) & 1);
         tc_fence_after();
+        if constexpr (ONES != 0) {       // the denominator sits in column DV of the row's O accumulator
+          uint32_t t16[16];
+          tmem_ld_32x16(tmem_O + (DV / 16) * 16, t16);
+          tmem_ld_wait();
+          l = __uint_as_float(t16[DV % 16]);
+        }
         store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0);
         tc_fence_before();
         DD_TR(6, k);
@@ -862,7 +875,7 @@ static int launch_attn_v2(const dd_attention_args* a, AttnDev p, cudaStream_t st
   return 0;
 }
 
-template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY>
+template <int DQK, int DV, int DVP, int BN, int STAGES, int POLY, int ONES>
 static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t stream) {
   constexpr size_t smem = (size_t)2 * ATT_BM * 128 + (size_t)STAGES * 2 * BN * 128 + 256;
   CUtensorMap tmQ, tmK, tmV;
@@ -877,7 +890,7 @@ static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t st
                          (uint64_t)a->lk * a->v_ld, 64, BN, 1);
   if (rc) return rc;
   p.n_kv_tiles = (a->lk + BN - 1) / BN;
-  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY>), (int)smem)) return e;
+  if (int e = ensure_dyn_smem(reinterpret_cast<const void*>(attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY, ONES>), (int)smem)) return e;
   const int n_q_tiles = (a->lq + ATT_BM - 1) / ATT_BM;
   const long long n_items = (long long)((n_q_tiles + 1) / 2) * a->heads * a->n_img;
   DD_CHECK(n_items < (1ll << 30), -1, "dd_attention: too many work items");
@@ -888,7 +901,7 @@ static int launch_attn_pp(const dd_attention_args* a, AttnDev p, cudaStream_t st
   const int slots = 2 * num_sms();
   const bool persistent = a->n_src * p.n_kv_tiles <= 8;
   dim3 grid((unsigned)((n_items < slots || !persistent) ? n_items : slots));
-  attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY><<<grid, PP_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+  attn_pp_kernel<DQK, DV, DVP, BN, STAGES, POLY, ONES><<<grid, PP_THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
   DD_CHECK(cudaGetLastError() == cudaSuccess, -2, "dd_attention: launch failed");
   return 0;
 }
@@ -904,6 +917,7 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
            "dd_attention: leading dims must be multiples of 8");
   DD_CHECK(a->n_kv_img > 0, -1, "dd_attention: n_kv_img missing");
   DD_CHECK(a->variant >= 0 && a->variant <= 2, -1, "dd_attention: variant must be 0 (auto), 1 or 2");
+  DD_CHECK(a->v_ones == 0 || a->head_dim == 40, -1, "dd_attention: v_ones is a head_dim-40 layout");
   AttnDev p;
   p.Lq = a->lq; p.Lk = a->lk; p.n_src = a->n_src; p.n_kv_tiles = 0;
   p.kv_map = a->kv_map;
@@ -920,9 +934,11 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
       DD_CHECK(a->q_head_stride >= 40 && a->k_head_stride >= 40 && (a->q_head_stride >= 48 || a->k_head_stride >= 48) &&
                    (a->q_head_stride == 40 || a->q_head_stride >= 48) && (a->k_head_stride == 40 || a->k_head_stride >= 48),
                -1, "dd_attention: head_dim 40 needs the Q or the K heads zero-padded to a 48-column stride");
+      DD_CHECK(a->v_ones == 0 || a->v_head_stride >= 48, -1, "dd_attention: v_ones needs V heads on a 48-column stride");
       if (a->variant == 1) return launch_attn_v2<48, 40, 48, 128, 3, 2>(a, p, stream);   // testing hook: one-tile kernel
-      if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 6, 0>(a, p, stream);     // testing hook: all ex2 on MUFU
-      return launch_attn_pp<48, 40, 48, 48, 6, 1>(a, p, stream);
+      if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 6, 0, 0>(a, p, stream);  // testing hook: all ex2 on MUFU
+      if (a->v_ones) return launch_attn_pp<48, 40, 48, 48, 6, 1, 1>(a, p, stream);
+      return launch_attn_pp<48, 40, 48, 48, 6, 1, 0>(a, p, stream);
     case 80: return launch_attn_v2<80, 80, 80, 64, 2, 2>(a, p, stream);
     case 160: return launch_attn_v2<160, 160, 160, 64, 1, 2>(a, p, stream);
   }

@@ -60,6 +60,17 @@ def pad_heads(w, d, dp):
     return out.reshape(h * dp, w.shape[1])
 
 
+def pad_v_ones(w, d, dp):
+    """value projection of head_dim-40 heads for the attention kernel's `v_ones` layout: [heads*d, in] -> weights
+    [heads*dp, in] with zero rows appended per head, and a bias [heads*dp] that is 1.0 in column d of every head (0 elsewhere).
+    The softmax denominator then falls out of P V as column d of the accumulator (csrc/dd_attention.cu, ONES)."""
+    h = w.shape[0] // d
+    wp = pad_heads(w, d, dp)
+    b = torch.zeros(h, dp)
+    b[:, d] = 1.0
+    return wp, b.reshape(-1)
+
+
 # ---------------------------------------------------------------------------------------------------
 # packing
 # ---------------------------------------------------------------------------------------------------
@@ -109,8 +120,21 @@ class Packer:
     def attn_self(self, p, d):
         dp = _dp(d)
         f = lambda n: self.sd[f"{p}.{n}.weight"].detach().float()
-        w = torch.cat([pad_heads(f("to_q"), d, dp), pad_heads(f("to_k"), d, dp), f("to_v")], 0)
+        if d == 40:   # V heads on the 48-column stride with a column of ones (pad_v_ones): the projection gets a bias
+            wv, bv = pad_v_ones(f("to_v"), d, dp)
+            self.put(p + ".qkv.b", self.f32(torch.cat([torch.zeros(2 * HEADS * dp), bv])))
+        else:
+            wv = f("to_v")
+        w = torch.cat([pad_heads(f("to_q"), d, dp), pad_heads(f("to_k"), d, dp), wv], 0)
         self.put(p + ".qkv.w", w.to(BF))
+
+    def kv_cross(self, name, wk, wv, d):
+        """[K | V] projection of a cross-attention's context tokens (text / camera / box tokens)"""
+        dp = _dp(d)
+        if d == 40:
+            wv, bv = pad_v_ones(wv, d, dp)
+            self.put(name + ".b", self.f32(torch.cat([torch.zeros(HEADS * dp), bv])))
+        self.put(name + ".w", torch.cat([pad_heads(wk, d, dp), wv], 0).to(BF))
 
     def tblock(self, p, multiview):
         c = self.sd[p + ".norm1.weight"].shape[0]
@@ -122,7 +146,7 @@ class Packer:
         self.attn_self(p + ".attn1", d)
         self.lin(p + ".attn1.to_out.0")
         self.put(p + ".attn2.q.w", pad_heads(f("attn2.to_q.weight"), d, dp).to(BF))
-        self.put(p + ".attn2.kv.w", torch.cat([pad_heads(f("attn2.to_k.weight"), d, dp), f("attn2.to_v.weight")], 0).to(BF))
+        self.kv_cross(p + ".attn2.kv", f("attn2.to_k.weight"), f("attn2.to_v.weight"), d)
         self.lin(p + ".attn2.to_out.0")
         if multiview:
             self.norm(p + ".norm4")
@@ -197,7 +221,7 @@ def pack_sfa(pk: "Packer", p="txt_con_fusion"):
     """Semantic Fusion Attention (txt_con_fusion.py:27-33): 8 heads x 40, Q/K heads zero-padded to 48 columns"""
     f = lambda n: pk.sd[f"{p}.{n}.weight"].detach().float()
     pk.put(p + ".q.w", pad_heads(f("to_q"), 40, 48).to(BF))
-    pk.put(p + ".kv.w", torch.cat([pad_heads(f("to_k"), 40, 48), f("to_v")], 0).to(BF))
+    pk.kv_cross(p + ".kv", f("to_k"), f("to_v"), 40)
     pk.lin(p + ".to_out.0")
 
 
@@ -205,8 +229,10 @@ def pack_sfa_plus(pk: "Packer", p="txt_con_fusionp"):
     """txt_con_XFormersAttn_plus (txt_con_fusion.py:184-208): the three condition projections as ONE weight
     [q (heads padded to 48) | k (padded) | v] and the two text projections as one [k (padded) | v]"""
     f = lambda n: pk.sd[f"{p}.{n}.weight"].detach().float()
-    pk.put(p + ".occ.w", torch.cat([pad_heads(f("to_q_occ"), 40, 48), pad_heads(f("to_k_occ"), 40, 48), f("to_v_occ")], 0).to(BF))
-    pk.put(p + ".txt.w", torch.cat([pad_heads(f("to_k_txt"), 40, 48), f("to_v_txt")], 0).to(BF))
+    wv, bv = pad_v_ones(f("to_v_occ"), 40, 48)
+    pk.put(p + ".occ.w", torch.cat([pad_heads(f("to_q_occ"), 40, 48), pad_heads(f("to_k_occ"), 40, 48), wv], 0).to(BF))
+    pk.put(p + ".occ.b", pk.f32(torch.cat([torch.zeros(16 * 48), bv])))
+    pk.kv_cross(p + ".txt", f("to_k_txt"), f("to_v_txt"), 40)
     pk.lin(p + ".to_out.0")
 
 
@@ -313,7 +339,7 @@ def resnet(P, p, x: Act, ctx: StepCtx, x2: Optional[torch.Tensor] = None) -> Act
 
 def text_kv(P, p_attn2, enc_rows):
     """K/V projection of the text/camera/box tokens for one attn2 layer (timestep-invariant)"""
-    return ops.gemm(enc_rows, P[p_attn2 + ".kv.w"])
+    return ops.gemm(enc_rows, P[p_attn2 + ".kv.w"], bias=P.get(p_attn2 + ".kv.b"))
 
 
 def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool):
@@ -321,41 +347,43 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
     d = C // HEADS
     dp = _dp(d)
     # 1. self-attention (blocks.py:163-172)
+    ones = d == 40          # V heads padded to 48 columns with a column of ones (pad_v_ones): the kernel reads the denominator from O
     ln = ops.layernorm(h, P[p + ".norm1.g"], P[p + ".norm1.b"])
-    qkv = ops.gemm(ln, P[p + ".attn1.qkv.w"])
+    qkv = ops.gemm(ln, P[p + ".attn1.qkv.w"], bias=P.get(p + ".attn1.qkv.b"))
     a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0, k_col0=HEADS * dp,
-                      v_col0=2 * HEADS * dp)
+                      v_col0=2 * HEADS * dp, v_ones=ones)
     h = ops.gemm(a, P[p + ".attn1.to_out.0.w"], bias=P[p + ".attn1.to_out.0.b"], res1=h)
     # 2. text cross-attention (blocks.py:175-188); K/V come from the per-sample cache
     ln = ops.layernorm(h, P[p + ".norm2.g"], P[p + ".norm2.b"])
     q = ops.gemm(ln, P[p + ".attn2.q.w"])
     kv = ctx.text_kv[p + ".attn2"]
-    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=ctx.lk, heads=HEADS, head_dim=d, k_col0=0, v_col0=HEADS * dp)
+    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=ctx.lk, heads=HEADS, head_dim=d, k_col0=0, v_col0=HEADS * dp, v_ones=ones)
     h = ops.gemm(a, P[p + ".attn2.to_out.0.w"], bias=P[p + ".attn2.to_out.0.b"], res1=h)
     # 3. cross-view attention over the two ring neighbours (blocks.py:190-222)
     if multiview:
         if ctx.view_shard is None:
             ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
-            qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"])
+            qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"], bias=P.get(p + ".attn4.qkv.b"))
             a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
-                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones)
         else:
             # camera views sharded across ranks (the only exchange step of the path): the norm4 rows of the first / last local
             # view travel to the ring neighbours on a side stream WHILE the local views are projected; the K/V projection of
             # the two halo views (rows behind the local ones) follows when they have arrived
             vs = ctx.view_shard
-            w_qkv = P[p + ".attn4.qkv.w"]
+            w_qkv, b_qkv = P[p + ".attn4.qkv.w"], P.get(p + ".attn4.qkv.b")
             wq, q_cols = w_qkv.shape[0], HEADS * dp
             n_kv = vs.kv_rows(ctx.n_outer)
             ln_ext = torch.empty((n_kv * T, C), device=h.device, dtype=BF)
             ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"], out=ln_ext[: n * T])
             vs.exchange_async(ln_ext, ctx.n_outer, T)
             buf = torch.empty((n_kv * T, wq), device=h.device, dtype=BF)
-            ops.gemm(ln_ext[: n * T], w_qkv, out=buf[: n * T])
+            ops.gemm(ln_ext[: n * T], w_qkv, bias=b_qkv, out=buf[: n * T])
             vs.exchange_wait(h.device)
-            ops.gemm(ln_ext[n * T:], w_qkv[q_cols:], out=buf[n * T:, q_cols:])      # halo views: K and V columns only
-            a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=n_kv, lq=T, lk=T, heads=HEADS,
-                              head_dim=d, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr)
+            ops.gemm(ln_ext[n * T:], w_qkv[q_cols:], bias=None if b_qkv is None else b_qkv[q_cols:],
+                     out=buf[n * T:, q_cols:])                                       # halo views: K and V columns only
+            a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=n_kv, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
     # 3b. temporal attention over the frames of the clip (no reference code: defined in csrc/dd_temporal.cu and
     #     oracle/dualdiff_oracle.py:temporal_attention); only packed for the video configuration
@@ -376,12 +404,12 @@ def temporal_step(P, p, h, n, T, ctx: StepCtx):
     n_clip = n // (F_loc * V)
     assert n_clip * F_loc * V == n, (n, F_loc, V)
     ln = ops.layernorm(h, P[p + ".norm_temp.g"], P[p + ".norm_temp.b"])
-    w_qkv = P[p + ".attn_temp.qkv.w"]
+    w_qkv, b_qkv = P[p + ".attn_temp.qkv.w"], P.get(p + ".attn_temp.qkv.b")   # packed like the other self-attentions (V stride dp)
     kw = dict(n_outer=n_clip, n_view=V, tokens=T, heads=HEADS, head_dim=d, frames_q=F_loc)
     fs = ctx.frame_shard
     if fs is None or fs.world == 1:
-        qkv = ops.gemm(ln, w_qkv)
-        a = ops.temporal_attention(qkv, qkv, qkv, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, **kw)
+        qkv = ops.gemm(ln, w_qkv, bias=b_qkv)
+        a = ops.temporal_attention(qkv, qkv, qkv, q_col0=0, k_col0=HEADS * dp, v_col0=2 * HEADS * dp, v_hs=dp, **kw)
     else:
         # frames sharded over ranks: the exchange is a pair of all-to-alls around the attention (sharding.FrameShard).  The
         # LayerNorm rows travel (C columns, not the 3C' of the projections) from "my frames, all tokens" to "all frames, my
@@ -390,12 +418,12 @@ def temporal_step(P, p, h, n, T, ctx: StepCtx):
         t_me = len(fs.token_range(T))
         tok_rows = fs.to_token_shards(ln, n, T)
         if t_me > 0:
-            qkv = ops.gemm(tok_rows, w_qkv)
+            qkv = ops.gemm(tok_rows, w_qkv, bias=b_qkv)
             F = F_loc * fs.world
             a_tok = ops.temporal_attention(qkv, qkv, qkv, n_outer=n_clip, n_view=V, tokens=t_me, heads=HEADS, head_dim=d,
                                            frames_q=F, frames_kv=F, frames_per_rank=F_loc, kv_rank_stride=n,
                                            frames_q_per_rank=F_loc, q_rank_stride=n, q_col0=0, k_col0=HEADS * dp,
-                                           v_col0=2 * HEADS * dp)
+                                           v_col0=2 * HEADS * dp, v_hs=dp)
         else:
             a_tok = torch.empty((0, C), device=h.device, dtype=BF)
         a = fs.from_token_shards(a_tok, n, T)
@@ -583,8 +611,8 @@ def sfa_rows(P, cond_rows, txt_rows, n, T, L, p="txt_con_fusion") -> torch.Tenso
     """cond + W_o MHA(W_q cond, W_k txt, W_v txt) + b_o on rows: cond_rows [n*T, 320], txt_rows [n*L, 768] (the L text tokens
     of every image, camera token already dropped) -> [n*T, 320]   (txt_con_fusion.py:110-177)"""
     q = ops.gemm(cond_rows, P[p + ".q.w"])
-    kv = ops.gemm(txt_rows, P[p + ".kv.w"])
-    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48)
+    kv = ops.gemm(txt_rows, P[p + ".kv.w"], bias=P[p + ".kv.b"])
+    a = ops.attention(q, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48, v_ones=True)
     return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond_rows)
 
 
@@ -593,10 +621,12 @@ def sfa_plus_rows(P, cond_rows, txt_rows, n, T, L, p="txt_con_fusionp") -> torch
     then out = cond + W_o MHA(q', W_k cond, W_v cond) + b_o.  q' leaves the first attention as 8 heads of 40 columns and is
     read by the second one with a 40-column head stride: the 8 columns the 48-wide Q tile takes from the next head meet the
     zero padding of the keys."""
-    proj = ops.gemm(cond_rows, P[p + ".occ.w"])                  # [n*T, 384 | 384 | 320] = q | k_occ | v_occ
-    kv = ops.gemm(txt_rows, P[p + ".txt.w"])                     # [n*L, 384 | 320]
-    q2 = ops.attention(proj, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48, q_cols=8 * 48)
-    a = ops.attention(q2, proj, proj, n_img=n, lq=T, lk=T, heads=8, head_dim=40, q_hs=40, k_col0=8 * 48, v_col0=16 * 48)
+    proj = ops.gemm(cond_rows, P[p + ".occ.w"], bias=P[p + ".occ.b"])   # [n*T, 384 | 384 | 384] = q | k_occ | v_occ (+ ones)
+    kv = ops.gemm(txt_rows, P[p + ".txt.w"], bias=P[p + ".txt.b"])      # [n*L, 384 | 384]
+    q2 = ops.attention(proj, kv, kv, n_img=n, lq=T, lk=L, heads=8, head_dim=40, k_col0=0, v_col0=8 * 48, q_cols=8 * 48,
+                       v_ones=True)
+    a = ops.attention(q2, proj, proj, n_img=n, lq=T, lk=T, heads=8, head_dim=40, q_hs=40, k_col0=8 * 48, v_col0=16 * 48,
+                      v_ones=True)
     return ops.gemm(a, P[p + ".to_out.0.w"], bias=P[p + ".to_out.0.b"], res1=cond_rows)
 
 

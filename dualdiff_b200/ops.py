@@ -188,14 +188,18 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_col0=0, v_col0=0,
               q_hs=None, k_hs=None, v_hs=None, kv_map=None, n_src=1, n_kv_img=None, scale=None,
-              q_cols=None, k_cols=None, v_cols=None, variant=0):
+              q_cols=None, k_cols=None, v_cols=None, variant=0, v_ones=False):
     """q: [n_img*lq, *], k/v: [n_kv_img*lk, *] bf16 (may be column views of one fused projection output).
-    variant: testing hook of the head_dim-40 kernel (include/dualdiff_b200.h), 0 = auto."""
+    variant: testing hook of the head_dim-40 kernel (include/dualdiff_b200.h), 0 = auto.
+    v_ones (head_dim 40): V heads have a 48-column stride with 1.0 in column 40 -- the softmax denominator comes out of the
+    P V product."""
     _req(q, torch.bfloat16, "q")
     hs_qk = 48 if head_dim == 40 else head_dim
     q_hs = hs_qk if q_hs is None else q_hs
     k_hs = hs_qk if k_hs is None else k_hs
-    v_hs = head_dim if v_hs is None else v_hs
+    if v_ones and head_dim != 40:
+        raise ValueError("v_ones is a head_dim-40 layout")
+    v_hs = (48 if v_ones else head_dim) if v_hs is None else v_hs
     n_kv_img = n_img if n_kv_img is None else n_kv_img
     if out is None:
         out = torch.empty((n_img * lq, heads * head_dim), device=q.device, dtype=torch.bfloat16)
@@ -211,6 +215,7 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
     a.lq = lq; a.lk = lk; a.n_src = n_src
     a.scale = float(head_dim) ** -0.5 if scale is None else scale
     a.variant = variant
+    a.v_ones = 1 if v_ones else 0
     with _Rec("attn_tcgen05", 4.0 * n_img * lq * lk * heads * head_dim * n_src,
               2.0 * heads * head_dim * (2 * n_img * lq + 2 * n_kv_img * lk), f"d{head_dim}_Lq{lq}_Lk{lk}_s{n_src}"):
         check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")

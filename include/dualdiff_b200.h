@@ -119,6 +119,9 @@ typedef struct dd_attention_args {
   int variant;                /* testing hook: 0 = auto.  head_dim 40: 0 = two query tiles per CTA, 25 % of the exponentials on
                                  the FMA pipe, 1 = one-tile kernel, 2 = two-tile kernel with every exponential on MUFU;
                                  head_dim 80 / 160: 1 = one CTA per work item instead of the persistent item loop */
+  int v_ones;                 /* head_dim 40 only: the V heads are padded to a 48-column stride and column 40 of every head
+                                 holds 1.0 (the projection's bias writes it).  O[:, 40] = sum_k P[:, k] is then the softmax
+                                 denominator, accumulated by the tensor core: the kernel keeps no row sum of its own. */
 } dd_attention_args;
 DD_API int dd_attention(const dd_attention_args* args, void* stream);
 

@@ -1,4 +1,4 @@
-"""torchrun entry: the frames of a video clip sharded over WORLD_SIZE GPUs with the temporal K/V all-gather over NCCL
+"""torchrun entry: the frames of a video clip sharded over WORLD_SIZE GPUs with the temporal all-to-all exchange over NCCL
 (BASELINE config 5) must reproduce the single-GPU multi-view + temporal transformer block.  Rank 0 prints
 'FRAMESHARD OK ...' on success."""
 import os
@@ -35,7 +35,7 @@ def main():
     fs = FrameShard(rank, world, F)
     xs, es = slice_frames(x, fs.frames, F), slice_frames(enc, fs.frames, F)
     for _ in range(2):
-        part = blk(xs, encoder_hidden_states=es, frame_shard=fs)            # this rank's frames + NCCL all-gather of K/V
+        part = blk(xs, encoder_hidden_states=es, frame_shard=fs)            # this rank's frames + the two NCCL all-to-alls
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -99,12 +99,12 @@ def video_unet(rank, world, dev, F, h, w):
         # bf16-vs-fp32 step parity (rel-L2 <= 2e-2)
         ok = float(t[0]) < 2e-2
         print(f"VIDEOUNET {'OK' if ok else 'FAIL'} world={world} frames={F} views=6 latent={h}x{w} rel_l2(max over ranks)="
-              f"{float(t[0]):.3e} UNet forward ms(max over ranks, eager launches + NCCL all-gathers)={float(t[1]):.2f}", flush=True)
+              f"{float(t[0]):.3e} UNet forward ms(max over ranks, eager launches + NCCL all-to-alls)={float(t[1]):.2f}", flush=True)
 
 
 def video_step(rank, world, dev, F, h, w):
     """the whole sampler step (both condition branches + video UNet + CFG + UniPC) of one clip, frames sharded over the
-    ranks and the step captured in a CUDA graph with its all-gathers: every rank's latents after two steps must equal its
+    ranks and the step captured in a CUDA graph with its all-to-alls: every rank's latents after two steps must equal its
     frames of the single-GPU run.  Prints 'VIDEOSTEP OK ...'."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import common

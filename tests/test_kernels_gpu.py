@@ -132,15 +132,49 @@ def test_head_dim_40_kernel_variants(lq, lk, n_src, variant):
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("lq,lk,n_src", [(128, 48, 1), (257, 96, 1), (1400, 1400, 2), (640, 1, 1), (1400, 106, 1), (100, 145, 2)])
+def test_head_dim_40_denominator_from_ones_column(lq, lk, n_src):
+    """`v_ones` layout: V heads on a 48-column stride with 1.0 in column 40, so the softmax denominator is column 40 of the
+    P V accumulator (the kernel keeps no row sum).  The rising logits force O (and with it the denominator) to be rescaled."""
+    from dualdiff_b200 import ops
+    d, heads, n = 40, 8, 3
+    C = heads * d
+    g = torch.Generator().manual_seed(21)
+    ramp = torch.linspace(0, 1, lk).repeat(n)[:, None]
+    q = _mk((n * lq, C), 11)
+    k = (_mk((n * lk, C), 12, 2.0).cpu().float() * (0.3 + 3.0 * ramp)).to(torch.bfloat16).cuda()
+    v = _mk((n * lk, C), 13)
+    vp = torch.zeros(n * lk, heads, 48, dtype=torch.bfloat16, device="cuda")
+    vp[:, :, :d] = v.reshape(n * lk, heads, d)
+    vp[:, :, d] = 1.0
+    kv = torch.cat([_heads_pad(k, heads, d, 48), vp.reshape(n * lk, heads * 48)], dim=1).contiguous()
+    kv_map = torch.tensor([[(i + 1) % n, (i + 2) % n] for i in range(n)], dtype=torch.int32).cuda() if n_src == 2 else None
+    out = ops.attention(_heads_pad(q, heads, d, 48), kv, kv, n_img=n, lq=lq, lk=lk, heads=heads, head_dim=d,
+                        k_col0=0, v_col0=heads * 48, kv_map=kv_map, n_src=n_src, v_ones=True)
+    qh, kh, vh = _ref_attn(q, k, v, n, lq, lk, heads, d)
+    if n_src == 1:
+        ref = F.scaled_dot_product_attention(qh, kh, vh)
+    else:
+        ref = sum(F.scaled_dot_product_attention(qh, kh[kv_map[:, s].long()], vh[kv_map[:, s].long()]) for s in range(2))
+    ref = ref.transpose(1, 2).reshape(n * lq, C)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+    # the same inputs through the kernel's own row sum agree to bf16 rounding
+    base = ops.attention(_heads_pad(q, heads, d, 48), kv, kv, n_img=n, lq=lq, lk=lk, heads=heads, head_dim=d,
+                         k_col0=0, v_col0=heads * 48, v_hs=48, kv_map=kv_map, n_src=n_src)
+    assert _rel(out, base) < 1e-2
+
+
 @pytest.mark.parametrize("two_pass", [False, True])
 @pytest.mark.parametrize("n,H,W,c1,c2,padded,silu,eps", [
     (3, 28, 50, 320, 0, True, True, 1e-5), (2, 14, 25, 640, 0, False, False, 1e-6), (2, 7, 13, 1280, 1280, True, True, 1e-5),
     (2, 14, 25, 1280, 640, True, True, 1e-5), (2, 28, 50, 640, 320, True, True, 1e-5), (2, 4, 7, 1280, 0, True, True, 1e-5),
     (5, 28, 50, 320, 0, False, False, 1e-6), (1, 56, 100, 320, 0, True, True, 1e-5), (3, 1, 1, 1280, 1280, True, True, 1e-5),
-    (2, 5, 7, 256, 0, True, True, 1e-6), (2, 9, 11, 128, 0, True, True, 1e-6)])
+    (2, 5, 7, 256, 0, True, True, 1e-6), (2, 9, 11, 128, 0, True, True, 1e-6),
+    (1, 27, 50, 320, 0, True, True, 1e-5), (2, 27, 50, 320, 0, False, True, 1e-5), (1, 15, 25, 1280, 640, True, False, 1e-6)])
 def test_groupnorm_silu(n, H, W, c1, c2, padded, silu, eps, two_pass):
-    """both forms of the operator: the single-pass cluster kernel (the image lives in the shared memory of a cluster) and the
-    two-kernel fallback (forced here; taken on its own for images too large for a cluster, e.g. 640 channels at 28x50, or
+    """both forms of the operator: the single-pass kernel (a [rows x few groups] slab in shared memory; 28x50 / 27x50 / 56x100
+    maps split their rows over a cluster of 2 / 2 / 8 CTAs, odd row counts unevenly) and the two-kernel fallback (forced here; taken on its own for images too large for a cluster, e.g. 640 channels at 28x50, or
     fewer than 8 channels per group, e.g. the VAE's 128-channel layers)"""
     from dualdiff_b200 import ops, packing
     x1 = _mk((n * H * W, c1), 1) * 2 + 0.5
