@@ -936,7 +936,11 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
                -1, "dd_attention: head_dim 40 needs the Q or the K heads zero-padded to a 48-column stride");
       DD_CHECK(a->v_ones == 0 || a->v_head_stride >= 48, -1, "dd_attention: v_ones needs V heads on a 48-column stride");
       if (a->variant == 1) return launch_attn_v2<48, 40, 48, 128, 3, 2>(a, p, stream);   // testing hook: one-tile kernel
-      if (a->variant == 2) return launch_attn_pp<48, 40, 48, 48, 6, 0, 0>(a, p, stream);  // testing hook: all ex2 on MUFU
+      if (a->variant == 2)   // testing hook: all ex2 on MUFU
+        return a->v_ones ? launch_attn_pp<48, 40, 48, 48, 6, 0, 1>(a, p, stream) : launch_attn_pp<48, 40, 48, 48, 6, 0, 0>(a, p, stream);
+      // short K/V streams (text / SFA: <= 8 key tiles, persistent CTAs) run faster with every exponential on MUFU
+      // (105 vs 112 us per level-0 text launch); long ones with a quarter of them on the FMA pipe (509 vs 532 us)
+      if (a->v_ones && a->n_src * ((a->lk + 47) / 48) <= 8) return launch_attn_pp<48, 40, 48, 48, 6, 0, 1>(a, p, stream);
       if (a->v_ones) return launch_attn_pp<48, 40, 48, 48, 6, 1, 1>(a, p, stream);
       return launch_attn_pp<48, 40, 48, 48, 6, 1, 0>(a, p, stream);
     case 80: return launch_attn_v2<80, 80, 80, 64, 2, 2>(a, p, stream);

@@ -166,10 +166,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
   tc_fence_before();
-  // CTA barrier first: it orders this CTA's read of tmem_ptr_smem after tcgen05.alloc's write (barrier.cluster does too, but
-  // compute-sanitizer's racecheck only models the CTA barrier); the cluster barrier then covers the peer's barriers / TMEM
-  __syncthreads();
-  if constexpr (CG == 2) cluster_sync_all();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_ptr_smem;
   // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the

@@ -226,6 +226,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+// 16-byte load from a shared-window address (the generic-pointer form made the compiler split it and re-derive the window)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -265,7 +271,6 @@ gn_slab_kernel(const GnSlabDev p) {
   const int n_lo = on ? min(8, (glo + 1) * p.cpg - c0) : 8;      // channels of the octet that belong to the lo group
   cp_async_wait_all();
   __syncthreads();
-  const uint8_t* my = slab + 16 * j;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // CTA-level reduction of per-thread (lo, hi) values to per-group totals (one warp per group, fixed order)
   auto group_totals = [&](const float (&v)[8], float* dst, bool finish_rstd) {
@@ -294,22 +299,54 @@ gn_slab_kernel(const GnSlabDev p) {
     }
     __syncthreads();
   };
-  // ---- pass A: per-channel sums (one FADD per element; folded into the two groups once, above) -> group means
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  if (on) {
-    for (int r = sub; r < HW; r += rpi) {
-      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)r * pitch);
+  // ---- ONE pass over the slab for both moments.  Every channel is centred on a pivot -- its value in row 0 of the image, the
+  //      same for all threads that share the channel -- and a thread accumulates A = sum(x - s) and B = sum((x - s)^2) over its
+  //      rows as packed FADD2 / FFMA2 (ncu: the kernel is issue-bound, and the two separate passes were 40 % of its
+  //      instructions).  With n rows per thread:   sum x = n s + A,   sum (x - mu)^2 = B + 2 (s - mu) A + n (s - mu)^2   -- exact
+  //      algebra; the pivot keeps every term at the scale of the group's spread (no E[x^2] - mean^2 cancellation).
+  const uint32_t my_s = smem_u32(slab) + 16u * (uint32_t)j;
+  float piv[8], av[8], bv[8];
+  float n_rows = 0.f;
+  {
+    uint64_t NS[4], A2[4], B2[4];
+    {
+      const uint4 v = lds128(my_s);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_bf16(w[e]);
-        acc[2 * e] += f.x;
-        acc[2 * e + 1] += f.y;
+        piv[2 * e] = f.x;
+        piv[2 * e + 1] = f.y;
+        NS[e] = pack_f32x2(-f.x, -f.y);
+        A2[e] = 0ull;
+        B2[e] = 0ull;
       }
     }
+    if (on) {
+      int cnt = 0;
+#pragma unroll 4
+      for (int r = sub; r < HW; r += rpi, ++cnt) {
+        const uint4 v = lds128(my_s + (uint32_t)r * pitch);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16(w[e]);
+          const uint64_t D = add_f32x2(pack_f32x2(f.x, f.y), NS[e]);
+          A2[e] = add_f32x2(A2[e], D);
+          B2[e] = fma_f32x2(D, D, B2[e]);
+        }
+      }
+      n_rows = (float)cnt;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unpack_f32x2(A2[e], av[2 * e], av[2 * e + 1]);
+      unpack_f32x2(B2[e], bv[2 * e], bv[2 * e + 1]);
+    }
   }
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(n_rows, piv[e], av[e]);      // this thread's share of sum x per channel
   group_totals(acc, gmean, false);
   float mu[8];                               // mean of each channel's group
   {
@@ -317,21 +354,8 @@ gn_slab_kernel(const GnSlabDev p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       mu[e] = e < n_lo ? mean_lo : mean_hi;
-      acc[e] = 0.f;
-    }
-  }
-  // ---- pass B: squared deviations from the group mean
-  if (on) {
-    for (int r = sub; r < HW; r += rpi) {
-      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)r * pitch);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(w[e]);
-        const float d0 = f.x - mu[2 * e], d1 = f.y - mu[2 * e + 1];
-        acc[2 * e] = fmaf(d0, d0, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(d1, d1, acc[2 * e + 1]);
-      }
+      const float dm = piv[e] - mu[e];
+      acc[e] = bv[e] + dm * (2.f * av[e] + n_rows * dm);                  // ... of sum (x - mu)^2
     }
   }
   group_totals(acc, grstd, true);
@@ -358,21 +382,25 @@ gn_slab_kernel(const GnSlabDev p) {
     }
   }
   // ---- normalise the image's output rows from shared memory (the padded layout interleaves zero halo rows / columns)
-  bf16* obase = p.out + (size_t)img * p.rows_out_img * p.out_ld + c0;
+  bf16* optr = p.out + ((size_t)img * p.rows_out_img + sub) * p.out_ld + c0;
+  const size_t ostep = (size_t)rpi * p.out_ld;
   const int Wp = p.W + 1;
   int hp = 0, wp = sub;                      // padded (row, column) of output row rr, carried without divisions
   if (p.padded) { hp = sub / Wp; wp = sub - hp * Wp; }
   const int dh = rpi / Wp, dw = rpi - dh * Wp;
-  for (int rr = sub; rr < p.rows_out_img; rr += rpi) {
+  for (int rr = sub; rr < p.rows_out_img; rr += rpi, optr += ostep) {
     int src = rr;
     bool live = true;
     if (p.padded) {
       live = (hp < p.H) && (wp < p.W);
       src = hp * p.W + wp;
+      hp += dh;
+      wp += dw;
+      if (wp >= Wp) { wp -= Wp; ++hp; }
     }
     uint4 o = make_uint4(0u, 0u, 0u, 0u);   // halo rows / columns of the padded layout are zeros
     if (live) {
-      const uint4 v = *reinterpret_cast<const uint4*>(my + (size_t)src * pitch);
+      const uint4 v = lds128(my_s + (uint32_t)src * pitch);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
       uint32_t pk[4];
 #pragma unroll
@@ -389,12 +417,7 @@ gn_slab_kernel(const GnSlabDev p) {
       }
       o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    *reinterpret_cast<uint4*>(obase + (size_t)rr * p.out_ld) = o;
-    if (p.padded) {
-      hp += dh;
-      wp += dw;
-      if (wp >= Wp) { wp -= Wp; ++hp; }
-    }
+    *reinterpret_cast<uint4*>(optr) = o;
   }
 }
 
@@ -590,6 +613,80 @@ layernorm_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm, packed form for the row widths of the path (C = 8 * LPR * VPL): 32 / LPR rows per warp, LPR lanes per row, VPL
+// 16-byte vectors per lane with EVERY lane busy (320 channels: 4 rows per warp, 8 lanes x 5 vectors; 640: 2 rows, 16 x 5;
+// 1280: 1 row, 32 x 5; 768 (CLIP): 1 row, 32 x 3).  ncu on the generic kernel above at 320 channels: 276 warp instructions per
+// row, issue slots 76 % busy at 3.4 TB/s -- instruction-bound (a quarter of the lanes idle in the second vector, scalar
+// arithmetic, per-row parameter loads).  Here sums, deviations, squares and the affine map run as packed FADD2 / FFMA2, the
+// rows of a warp share each shuffle instruction, and the deviations stay in registers between the variance and the output.
+// ---------------------------------------------------------------------------------------------------
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_packed_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ out, long long out_ld,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps) {
+  constexpr int RPW = 32 / LPR;                 // rows per warp
+  constexpr int C = 8 * LPR * VPL;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane - sub * LPR;
+  const long long row = ((long long)((blockIdx.x * blockDim.x + threadIdx.x) >> 5)) * RPW + sub;
+  const bool live = row < rows;
+  const bf16* xr = x + (live ? row : 0) * x_ld + l * 8;
+  uint64_t v[VPL][4];
+  uint64_t S = 0ull;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint4 u = live ? *reinterpret_cast<const uint4*>(xr + i * (LPR * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16(w[e]);
+      v[i][e] = pack_f32x2(f.x, f.y);
+      S = add_f32x2(S, v[i][e]);
+    }
+  }
+  float s0, s1;
+  unpack_f32x2(S, s0, s1);
+  float sum = s0 + s1;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / (float)C);
+  const uint64_t NM = pack_f32x2(-mean, -mean);
+  uint64_t Q = 0ull;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[i][e] = add_f32x2(v[i][e], NM);         // deviations from the mean, kept for the output
+      Q = fma_f32x2(v[i][e], v[i][e], Q);
+    }
+  }
+  unpack_f32x2(Q, s0, s1);
+  float sq = s0 + s1;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.f / (float)C) + eps);
+  const uint64_t R = pack_f32x2(rstd, rstd);
+  if (!live) return;
+  bf16* orow = out + row * out_ld + l * 8;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (l + i * LPR) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const uint64_t G[4] = {pack_f32x2(g0.x, g0.y), pack_f32x2(g0.z, g0.w), pack_f32x2(g1.x, g1.y), pack_f32x2(g1.z, g1.w)};
+    const uint64_t B[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y), pack_f32x2(b1.z, b1.w)};
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float y0, y1;
+      unpack_f32x2(fma_f32x2(fma_f32x2(v[i][e], R, 0ull), G[e], B[e]), y0, y1);   // ((x - mean) * rstd) * gamma + beta
+      pk[e] = pack_bf16(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(orow + i * (LPR * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 int layernorm_run(const dd_layernorm_args* a, cudaStream_t stream) {
   DD_CHECK(a != nullptr && a->rows > 0 && a->c > 0, -1, "dd_layernorm: bad args");
   DD_CHECK(a->c % 8 == 0 && a->c <= 2048, -1, "dd_layernorm: C=%d must be a multiple of 8 and <= 2048", a->c);
@@ -599,6 +696,21 @@ int layernorm_run(const dd_layernorm_args* a, cudaStream_t stream) {
   const int grid = (int)(((long long)a->rows * 32 + threads - 1) / threads);
   const bf16* x = reinterpret_cast<const bf16*>(a->x);
   bf16* out = reinterpret_cast<bf16*>(a->out);
+  // the packed kernel for the widths of the path (transformer levels 320 / 640 / 1280, CLIP 768), the generic one otherwise
+#define DD_LNP(LPR, VPL)                                                                                            \
+  do {                                                                                                              \
+    const long long warps = ((long long)a->rows + (32 / LPR) - 1) / (32 / LPR);                                     \
+    layernorm_packed_kernel<LPR, VPL><<<(unsigned)((warps * 32 + threads - 1) / threads), threads, 0, stream>>>(    \
+        x, a->x_ld, out, a->out_ld, a->gamma, a->beta, a->rows, a->eps);                                            \
+    DD_CUDA(cudaGetLastError());                                                                                    \
+    count_launch(1);                                                                                                \
+    return 0;                                                                                                       \
+  } while (0)
+  if (a->c == 320) DD_LNP(8, 5);
+  if (a->c == 640) DD_LNP(16, 5);
+  if (a->c == 1280) DD_LNP(32, 5);
+  if (a->c == 768) DD_LNP(32, 3);
+#undef DD_LNP
 #define DD_LN(V)                                                                                         \
   layernorm_kernel<V><<<grid, threads, 0, stream>>>(x, a->x_ld, out, a->out_ld, a->gamma, a->beta, a->rows, \
                                                     a->c, a->eps)

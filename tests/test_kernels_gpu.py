@@ -210,8 +210,11 @@ def test_groupnorm_large_offset_activations():
     assert _rel(out, ref.float()) < 2e-2, _rel(out, ref.float())
 
 
-@pytest.mark.parametrize("rows,C", [(1400, 320), (701, 640), (91, 1280), (5, 1280)])
+@pytest.mark.parametrize("rows,C", [(1400, 320), (701, 640), (91, 1280), (5, 1280), (1403, 320), (3, 320), (77, 768), (130, 512),
+                                    (9, 2048)])
 def test_layernorm(rows, C):
+    """the packed kernel (320 / 640 / 1280 / 768 channels: 4 / 2 / 1 / 1 rows per warp, row counts that leave the last warp
+    partly empty) and the generic one (512, 2048)"""
     from dualdiff_b200 import ops
     x = _mk((rows, C), 1) * 3 + 1
     gamma = (1 + 0.1 * torch.randn(C, generator=torch.Generator().manual_seed(3))).cuda()
