@@ -45,11 +45,12 @@ def peaks():
 
 def ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel`, from the committed ncu launch list of one step (profiles/); None if absent"""
-    p = os.path.join(ROOT, "profiles", "r01_launches_traffic.json")
-    try:
-        return round(json.load(open(p))[kernel]["traffic_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_launches_traffic.json", "r01_launches_traffic.json"):
+        try:
+            return round(json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]["traffic_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -338,7 +339,7 @@ def run_ours(args):
         roof = {"kernel": "gemm_tcgen05_kernel (Linear / 1x1 / implicit-GEMM 3x3 conv)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / pk["tf_sustained"], 4), "peak_source": f"{pk['src']} (bf16 sustained)",
-                "traffic": ncu_traffic("gemm_tcgen05_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_launches_traffic.json)",
+                "traffic": ncu_traffic("gemm_tcgen05_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r02_launches_traffic.json)",
                 "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
                 "share_of_step": round(g["ms"] / tot, 3),
                 "flops_per_step": g["flops"],

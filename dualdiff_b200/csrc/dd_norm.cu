@@ -218,7 +218,7 @@ struct GnSlabDev {
   int C1, C, H, W, groups, cpg, g_per_cta, silu, padded, rows_out_img;
   float eps;
 };
-constexpr int GN_SLAB_THREADS = 256;
+constexpr int GN_SLAB_THREADS = 256;            // (512 threads for the slabs that leave one CTA per SM: measured 27 % slower)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -240,6 +240,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 
 __global__ void __launch_bounds__(GN_SLAB_THREADS, 3)
 gn_slab_kernel(const GnSlabDev p) {
+  constexpr int NT = GN_SLAB_THREADS;
   extern __shared__ __align__(128) uint8_t gsm[];
   // layout: [group mean: 64 floats][group rstd: 64 floats][scratch: 256 x float2][slab: rows x width bf16]
   float* gmean = reinterpret_cast<float*>(gsm);
@@ -253,7 +254,7 @@ gn_slab_kernel(const GnSlabDev p) {
   const int width = ng * p.cpg;                          // channels of this CTA (a multiple of 8)
   const int wv = width >> 3;                             // 16-byte vectors per row
   const int HW = p.H * p.W;
-  const int rpi = GN_SLAB_THREADS / wv;                  // rows per iteration
+  const int rpi = NT / wv;                               // rows per iteration
   const int j = threadIdx.x % wv, sub = threadIdx.x / wv;
   const bool on = sub < rpi;
   const int c0 = ca + 8 * j;                             // my octet of channels
@@ -281,7 +282,7 @@ gn_slab_kernel(const GnSlabDev p) {
     }
     if (on) scratch[sub * wv + j] = make_float2(lo, hi);
     __syncthreads();
-    for (int gi = warp; gi < ng; gi += GN_SLAB_THREADS / 32) {
+    for (int gi = warp; gi < ng; gi += NT / 32) {
       const int g = g0 + gi;
       const int ja = (g * p.cpg - ca) >> 3, jb = ((g + 1) * p.cpg - 1 - ca) >> 3;     // octets overlapping the group
       const int n_oct = jb - ja + 1;
@@ -432,7 +433,7 @@ static int gn_slab_plan(int C, int groups, int HW, int n_img, size_t* smem_bytes
   while ((unit * cpg) % 8 != 0) ++unit;                 // 1, 2 or 4 groups
   if (unit > groups) return 0;
   const size_t hdr = 512 + GN_SLAB_THREADS * 8;
-  const size_t limit = 112 * 1024;
+  const size_t limit = 116 * 1024;
   int best = 0;
   for (int g = unit; g <= groups && g <= 64; g += unit) {
     const int width = g * cpg;
@@ -503,8 +504,8 @@ int groupnorm_run(const dd_groupnorm_args* a, cudaStream_t stream) {
       p.C1 = a->c1; p.C = C; p.H = a->h; p.W = a->w; p.groups = a->groups; p.cpg = C / a->groups; p.g_per_cta = gpc;
       p.silu = a->silu; p.padded = a->padded_out; p.rows_out_img = a->padded_out ? (a->h + 1) * (a->w + 1) : HW;
       p.eps = a->eps;
-      if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gn_slab_kernel), 113 * 1024)) return rc;
       dim3 grid((a->groups + gpc - 1) / gpc, a->n_img);
+      if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gn_slab_kernel), 116 * 1024)) return rc;
       gn_slab_kernel<<<grid, GN_SLAB_THREADS, smem, stream>>>(p);
       DD_CUDA(cudaGetLastError());
       count_launch(1);
@@ -622,7 +623,7 @@ layernorm_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ 
 // rows of a warp share each shuffle instruction, and the deviations stay in registers between the variance and the output.
 // ---------------------------------------------------------------------------------------------------
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)      // 70 registers, 3 CTAs per SM (capping at 64 for a 4th CTA measured 5 % slower)
 layernorm_packed_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ out, long long out_ld,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int rows, float eps) {
   constexpr int RPW = 32 / LPR;                 // rows per warp
