@@ -53,7 +53,7 @@ class AttentionArgs(C.Structure):
         ("q_col0", _i), ("k_col0", _i), ("v_col0", _i),
         ("q_head_stride", _i), ("k_head_stride", _i), ("v_head_stride", _i),
         ("n_img", _i), ("n_kv_img", _i), ("heads", _i), ("head_dim", _i), ("lq", _i), ("lk", _i), ("n_src", _i),
-        ("scale", _f), ("variant", _i), ("v_ones", _i),
+        ("scale", _f), ("variant", _i), ("v_ones", _i), ("concat", _i),
     ]
 
 

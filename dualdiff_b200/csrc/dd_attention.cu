@@ -42,6 +42,7 @@ struct AttnDev {
   long long out_ld;
   int q_col0, k_col0, v_col0, q_hs, k_hs, v_hs, o_hs;
   int heads, n_img;   // persistent kernel: item -> (image, head, query-tile pair)
+  int concat;         // 1: the n_src K/V sources form ONE key sequence (a single softmax over all of them)
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -365,7 +366,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // refill the ring while the softmax warpgroup is still exponentiating this tile
         if (producer) produce();
         DD_TR(15, k);
-        issue_pv(s_cur, jt != 0);
+        issue_pv(s_cur, p.concat ? (i != 0) : (jt != 0));
         DD_TR(16, k);
         if (++jt == p.n_kv_tiles) jt = 0;
         s_cur = s_nxt;
@@ -393,8 +394,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int r = item / n_pairs;
       const int q_row = ((item % n_pairs) * 2 + t) * ATT_BM + row;
       bf16* orow = p.out + ((long long)(r / p.heads) * p.Lq + q_row) * p.out_ld + (r % p.heads) * p.o_hs;
+      float m = -INFINITY, l = 0.f;
       for (int src = 0; src < p.n_src; ++src) {
-        float m = -INFINITY, l = 0.f;
+        if (!p.concat) { m = -INFINITY; l = 0.f; }          // one softmax per source, or one over the concatenated sources
+        const bool o_live = p.concat && src > 0;           // O already holds the earlier sources of this softmax
 #pragma unroll 1
         for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++k) {
           DD_TR(0, k);
@@ -475,7 +478,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           DD_TR(3, k);
           DD_TR(4, k);
-          if (grow && jt > 0) {
+          if (grow && (jt > 0 || o_live)) {
 #pragma unroll
             for (int c = 0; c < DVP; c += 16) {
               uint32_t ov[16];
@@ -500,6 +503,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_arrive(bp_full);
           DD_TR(5, k);
         }
+        if (p.concat && src + 1 < p.n_src) continue;        // concatenated sources: one epilogue after the last of them
         // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first).  The issuer is
         // already feeding the next source / item: its first P V cannot start before this warpgroup's next p_full arrival.
         mbar_wait(bo_full, (k - 1) & 1);
@@ -510,7 +514,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld_wait();
           l = __uint_as_float(t16[DV % 16]);
         }
-        store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0);
+        store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);
         tc_fence_before();
         DD_TR(6, k);
       }
@@ -697,7 +701,7 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < BN / 16; ++kk) {
             umma_bf16_ts(tmem_O, tmem_P + kk * 8, umma_smem_desc(sV + kk * 16 * 128, K_CHUNK, 1024, 2), IDESC_O,
-                         (kk != 0 || jt != 0) ? 1u : 0u);  // O accumulates in TMEM over one source
+                         (kk != 0 || (p.concat ? i != 0 : jt != 0)) ? 1u : 0u);  // O accumulates over one source (all, concatenated)
           }
           umma_commit(kv_empty + 8 * s);
           umma_commit(o_full);
@@ -729,8 +733,10 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int r = item / n_q_tiles;
       const int q_row = (item % n_q_tiles) * ATT_BM + row;
       bf16* orow = p.out + ((long long)(r / p.heads) * p.Lq + q_row) * p.out_ld + (r % p.heads) * p.o_hs;
+    float m = -INFINITY, l = 0.f;
     for (int src = 0; src < p.n_src; ++src) {
-      float m = -INFINITY, l = 0.f;
+      if (!p.concat) { m = -INFINITY; l = 0.f; }            // one softmax per source, or one over the concatenated sources
+      const bool o_live = p.concat && src > 0;
 #pragma unroll 1
       for (int jt = 0; jt < p.n_kv_tiles; ++jt, ++g) {
         if (!s_ready) mbar_wait(s_full, g & 1);    // usually probed already while the previous tile's P store was in flight
@@ -794,7 +800,7 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             pk[(jj >> 1) - pass * (NC / 2)] = pack_bf16(p0, p1);
           }
           if (pass == 0) {
-            if (grow && jt > 0) {
+            if (grow && (jt > 0 || o_live)) {
 #pragma unroll
               for (int c = 0; c < DVP; c += 16) {
                 uint32_t ov[16];
@@ -823,11 +829,12 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(p_full);
       }
+      if (p.concat && src + 1 < p.n_src) continue;          // concatenated sources: one epilogue after the last of them
       // epilogue of this source: O / l  (second source of the cross-view attention adds onto the first).  The issuer is
       // already loading the next source / item; its first P V waits for this thread's next p_full arrival.
       mbar_wait(o_full, (g - 1) & 1);
       tc_fence_after();
-      store_o_row<DV, DVP>(tmem_O + lane_sel, 1.f / l, orow, q_row < p.Lq, src > 0);
+      store_o_row<DV, DVP>(tmem_O + lane_sel, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);
       tc_fence_before();
     }
     }
@@ -911,8 +918,8 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   DD_CHECK(a->n_img > 0 && a->heads > 0 && a->lq > 0 && a->lk > 0, -1, "dd_attention: bad shape");
   DD_CHECK(a->head_dim == 40 || a->head_dim == 80 || a->head_dim == 160, -1,
            "dd_attention: head_dim %d unsupported (40, 80, 160 = SDv1.5 levels)", a->head_dim);
-  DD_CHECK(a->n_src == 1 || a->n_src == 2, -1, "dd_attention: n_src must be 1 or 2");
-  DD_CHECK(a->n_src == 1 || a->kv_map != nullptr, -1, "dd_attention: kv_map required for n_src == 2");
+  DD_CHECK(a->n_src >= 1 && a->n_src <= 8, -1, "dd_attention: n_src must be 1..8");
+  DD_CHECK(a->n_src == 1 || a->kv_map != nullptr, -1, "dd_attention: kv_map required for n_src > 1");
   DD_CHECK(a->q_ld % 8 == 0 && a->k_ld % 8 == 0 && a->v_ld % 8 == 0 && a->out_ld % 8 == 0, -1,
            "dd_attention: leading dims must be multiples of 8");
   DD_CHECK(a->n_kv_img > 0, -1, "dd_attention: n_kv_img missing");
@@ -926,6 +933,7 @@ int attention_run(const dd_attention_args* a, cudaStream_t stream) {
   p.q_col0 = a->q_col0; p.k_col0 = a->k_col0; p.v_col0 = a->v_col0;
   p.q_hs = a->q_head_stride; p.k_hs = a->k_head_stride; p.v_hs = a->v_head_stride; p.o_hs = a->head_dim;
   p.heads = a->heads; p.n_img = a->n_img;
+  p.concat = a->concat ? 1 : 0;
   switch (a->head_dim) {
     case 40:
       // The 48-wide Q.K^T reads 8 columns beyond a 40-wide head.  Either side may keep unpadded (stride 40) heads as long as the

@@ -28,6 +28,26 @@ HEADS = 8
 NEIGHBORS = {0: [5, 1], 1: [0, 2], 2: [1, 3], 3: [2, 4], 4: [3, 5], 5: [4, 0]}  # configs/dataset/Nuscenes.yaml:27-33 (default)
 
 
+XVIEW_MODES = ("add", "concat", "self")      # neighboring_attn_type (networks/blocks.py:112-140)
+
+
+def xview_plan(pairs, mode: str = "add"):
+    """(pairs, K/V sources per view, concatenated softmax?, how often to_out's bias is counted) of a cross-view attention:
+      add    -- one attention per (view, neighbour) pair, outputs summed AFTER to_out: n_nbr sources, bias n_nbr times
+      concat -- the neighbours' tokens form one key sequence: n_nbr sources under one softmax, bias once
+      self   -- every view attends to all views of its scene (blocks.py:134-137): n_cam sources under one softmax, bias once"""
+    if mode not in XVIEW_MODES:
+        raise NotImplementedError(f"Unknown type: {mode}")       # the reference's own message (blocks.py:139-140)
+    pairs, n_nbr = check_view_pairs(pairs)
+    if mode == "add":
+        return pairs, n_nbr, False, n_nbr
+    if mode == "concat":
+        return pairs, n_nbr, True, 1
+    if len(pairs) > 8:
+        raise NotImplementedError("neighboring_attn_type='self' with more than 8 views (dd_attention takes up to 8 K/V sources)")
+    return pairs, len(pairs), True, 1
+
+
 def check_view_pairs(pairs):
     """the cross-view topology the kernels can run: every view lists the same number (1 or 2) of neighbour views, all inside
     the view range.  Returns (pairs with int keys, neighbours per view).  Anything else raises instead of silently computing
@@ -77,7 +97,7 @@ def pad_v_ones(w, d, dp):
 class Packer:
     def __init__(self, sd: Dict[str, torch.Tensor], device, n_nbr: int = 2):
         self.sd, self.dev, self.out = sd, device, {}
-        self.n_nbr = n_nbr            # neighbour views summed by the cross-view attention (to_out's bias counts once per neighbour)
+        self.n_nbr = n_nbr            # how often the cross-view attention counts to_out's bias (xview_plan: once per summed output)
 
     def f32(self, t):
         return t.detach().float().contiguous().to(self.dev)
@@ -197,9 +217,9 @@ class Packer:
         self.out["temb_total"] = off
 
 
-def pack_unet(sd, device, neighboring_view_pair=None):
-    pairs, n_nbr = check_view_pairs(neighboring_view_pair)
-    pk = Packer(sd, device, n_nbr)
+def pack_unet(sd, device, neighboring_view_pair=None, neighboring_attn_type: str = "add"):
+    pairs, n_src, concat, n_bias = xview_plan(neighboring_view_pair, neighboring_attn_type)
+    pk = Packer(sd, device, n_bias)
     tl: List[str] = []
     pk.encoder(True, tl)
     for i in range(4):
@@ -213,7 +233,8 @@ def pack_unet(sd, device, neighboring_view_pair=None):
     pk.conv3("conv_out")
     pk.temb(tl)
     pk.out["view_pairs"] = pairs
-    pk.out["n_nbr"] = n_nbr
+    pk.out["n_nbr"] = n_src
+    pk.out["xview_mode"] = neighboring_attn_type
     return pk.out
 
 
@@ -299,7 +320,8 @@ class StepCtx:
     text_kv: Dict[str, torch.Tensor] = field(default_factory=dict)   # attn2 prefix -> [n*Lk, 8*dp + C]
     lk: int = 0
     kv_map: Optional[torch.Tensor] = None
-    n_nbr: int = 2                        # neighbour views per view (columns of kv_map)
+    n_nbr: int = 2                        # K/V sources per view of the cross-view attention (columns of kv_map)
+    xview_concat: bool = False            # one softmax over the concatenated sources (neighboring_attn_type concat / self)
     view_shard: Optional[object] = None   # sharding.ViewShard when camera views are split across ranks
     n_outer: int = 0                      # scenes x CFG halves (sharded mode)
     n_frames: int = 1                     # video clips: local frames per clip; images are ordered [clip][frame][view]
@@ -365,7 +387,8 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
             ln = ops.layernorm(h, P[p + ".norm4.g"], P[p + ".norm4.b"])
             qkv = ops.gemm(ln, P[p + ".attn4.qkv.w"], bias=P.get(p + ".attn4.qkv.b"))
             a = ops.attention(qkv, qkv, qkv, n_img=n, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
-                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones)
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones,
+                              concat=ctx.xview_concat)
         else:
             # camera views sharded across ranks (the only exchange step of the path): the norm4 rows of the first / last local
             # view travel to the ring neighbours on a side stream WHILE the local views are projected; the K/V projection of
@@ -383,7 +406,8 @@ def transformer_block(P, p, h: torch.Tensor, n, T, ctx: StepCtx, multiview: bool
             ops.gemm(ln_ext[n * T:], w_qkv[q_cols:], bias=None if b_qkv is None else b_qkv[q_cols:],
                      out=buf[n * T:, q_cols:])                                       # halo views: K and V columns only
             a = ops.attention(buf, buf, buf, n_img=n, n_kv_img=n_kv, lq=T, lk=T, heads=HEADS, head_dim=d, q_col0=0,
-                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones)
+                              k_col0=HEADS * dp, v_col0=2 * HEADS * dp, kv_map=ctx.kv_map, n_src=ctx.n_nbr, v_ones=ones,
+                              concat=ctx.xview_concat)
         h = ops.gemm(a, P[p + ".attn4.oc.w"], bias=P[p + ".attn4.oc.b"], res1=h)
     # 3b. temporal attention over the frames of the clip (no reference code: defined in csrc/dd_temporal.cu and
     #     oracle/dualdiff_oracle.py:temporal_attention); only packed for the video configuration
@@ -484,15 +508,19 @@ ATTN2_LAYERS_UNET = ATTN2_LAYERS_ENC + [f"up_blocks.{i}.attentions.{j}.transform
                                         for i in range(1, 4) for j in range(3)]
 
 
-def make_kv_map(n, pairs, device):
-    """kv image of (query image, neighbour slot); view index = image index mod n_cam (blocks.py:196-197).
-    `pairs`: the model's neighboring_view_pair table (an int = that many views of the default ring, for callers without a model)"""
+def make_kv_map(n, pairs, device, mode: str = "add"):
+    """kv image of (query image, source slot); view index = image index mod n_cam (blocks.py:196-197).
+    `pairs`: the model's neighboring_view_pair table (an int = that many views of the default ring, for callers without a model);
+    mode "self": the sources of a view are all views of its scene"""
     if isinstance(pairs, int):
         assert pairs == len(NEIGHBORS), "an integer view count selects the default 6-view ring"
         pairs = NEIGHBORS
     n_cam = len(pairs)
     assert n % n_cam == 0
-    rows = [[(i // n_cam) * n_cam + nb for nb in pairs[i % n_cam]] for i in range(n)]
+    if mode == "self":
+        rows = [[(i // n_cam) * n_cam + v for v in range(n_cam)] for i in range(n)]
+    else:
+        rows = [[(i // n_cam) * n_cam + nb for nb in pairs[i % n_cam]] for i in range(n)]
     return torch.tensor(rows, dtype=torch.int32, device=device)
 
 
@@ -567,7 +595,13 @@ def build_tokens(P, camera_param, text, bboxes_3d_data):
     1007,1066-1069).  Concats/expands here are pure data movement (torch), the arithmetic is in the kernels."""
     b, n_cam = camera_param.shape[:2]
     cam = camera_tokens(P, camera_param).reshape(b, n_cam, 1, 768)
-    txt = text.float()[:, None].expand(b, n_cam, text.shape[1], 768)
+    if text.shape[0] == b * n_cam and n_cam > 1:       # use_aug_text: one prompt per VIEW, '(b n) ... -> b n ...' (:351-352)
+        txt = text.float().reshape(b, n_cam, text.shape[1], 768)
+    elif text.shape[0] == b:                           # one prompt per scene, repeated over its views (:353-354)
+        txt = text.float()[:, None].expand(b, n_cam, text.shape[1], 768)
+    else:
+        raise ValueError(f"text embeddings: {text.shape[0]} rows for {b} scenes x {n_cam} views (one per scene, or one per view "
+                         "with use_aug_text)")
     if bboxes_3d_data is None:
         # the reference collate returns None when a batch has no visible box / map vector (dataset/utils.py:235-237) and
         # the branch then runs on [camera | text] tokens only (unet_addon_rawbox.py:892-895,1066-1069): zero box tokens

@@ -2,7 +2,8 @@
 
 Reference: networks/blocks.py:35-238.  The block adds `norm4`, `attn4` and a zero-initialised `connector`
 to diffusers' BasicTransformerBlock and, between the text cross-attention and the feed-forward, lets every
-camera view attend to its two ring neighbours (`neighboring_attn_type="add"`).
+camera view attend to its two ring neighbours (`neighboring_attn_type="add"`: one attention per neighbour, outputs summed;
+"concat": the neighbours' tokens under one softmax; "self": all views of the scene).
 """
 from typing import Dict, List, Optional
 
@@ -29,8 +30,8 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         if (activation_fn != "geglu" or num_embeds_ada_norm is not None or attention_bias or only_cross_attention
                 or double_self_attention or norm_type != "layer_norm" or not norm_elementwise_affine):
             raise NotImplementedError("dualdiff_b200 implements the SDv1.5 block configuration the reference uses")
-        if neighboring_attn_type != "add":
-            raise NotImplementedError(f"neighboring_attn_type={neighboring_attn_type!r}: only 'add' is on the hot path")
+        if neighboring_attn_type not in ("add", "concat", "self"):
+            raise NotImplementedError(f"Unknown type: {neighboring_attn_type}")       # blocks.py:139-140
         if zero_module_type != "zero_linear":
             raise TypeError(f"Unknown zero module type: {zero_module_type}")
         super().__init__(dim, num_attention_heads, attention_head_dim, cross_attention_dim)
@@ -61,11 +62,12 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
 
     def pack(self):
         from .. import engine
-        pairs, n_nbr = engine.check_view_pairs(self.neighboring_view_pair)
-        pk = engine.Packer({k: v for k, v in self.state_dict().items()}, next(self.parameters()).device, n_nbr)
+        pairs, n_src, concat, n_bias = engine.xview_plan(self.neighboring_view_pair, self.neighboring_attn_type)
+        pk = engine.Packer({k: v for k, v in self.state_dict().items()}, next(self.parameters()).device, n_bias)
         pk.sd = {"b." + k: v for k, v in pk.sd.items()}
         pk.tblock("b", True)
-        pk.out["n_nbr"] = n_nbr
+        pk.out["n_nbr"] = n_src
+        pk.out["xview_concat"] = concat
         self._packed = pk.out
         return self
 
@@ -89,7 +91,8 @@ class BasicMultiviewTransformerBlock(_tree.BasicTransformerBlock):
         enc = encoder_hidden_states.to(torch.bfloat16)
         lk = enc.shape[1]
         ctx = engine.StepCtx(n=n, temb=None, temb_rows_per_img_factor=1, lk=lk,
-                             kv_map=engine.make_kv_map(n, self.neighboring_view_pair, h.device), n_nbr=P["n_nbr"])
+                             kv_map=engine.make_kv_map(n, self.neighboring_view_pair, h.device, self.neighboring_attn_type),
+                             n_nbr=P["n_nbr"], xview_concat=P["xview_concat"])
         if self.temporal_frames > 1:
             ctx.n_view = self.n_cam
             ctx.frame_shard = frame_shard

@@ -135,7 +135,8 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
         device = torch.device(device) if device is not None else self.device
         if device.type != "cuda":
             raise RuntimeError("dualdiff_b200 has no CPU path: move the model to a CUDA device (sm_100a) before use")
-        self._packed = engine.pack_unet(self.state_dict(), device, self.config.neighboring_view_pair)
+        self._packed = engine.pack_unet(self.state_dict(), device, self.config.neighboring_view_pair,
+                                        self.config.neighboring_attn_type)
         self._packed_versions = self._param_versions()
         return self
 
@@ -179,7 +180,8 @@ class UNet2DConditionModelMultiview(_tree.ModelBase):
         lk = enc.shape[1]
         enc_rows = enc.reshape(n * lk, enc.shape[2]).contiguous()
         ctx = engine.StepCtx(n=n, temb=temb, temb_rows_per_img_factor=n // t.numel(), lk=lk,
-                             kv_map=engine.make_kv_map(n, P["view_pairs"], sample.device), n_nbr=P["n_nbr"],
+                             kv_map=engine.make_kv_map(n, P["view_pairs"], sample.device, P["xview_mode"]), n_nbr=P["n_nbr"],
+                             xview_concat=P["xview_mode"] != "add",
                              text_kv=engine.prepare_text(P, engine.ATTN2_LAYERS_UNET, enc_rows))
         self.video_ctx(ctx)
         lat = sample.contiguous() if sample.dtype in (torch.float32, torch.bfloat16) else sample.float().contiguous()

@@ -196,8 +196,9 @@ class BEVControlNetModel(_tree.ModelBase):
                 return_dict: bool = True, **kwargs):
         from .. import engine
         self.use_aug_text = kwargs["use_aug_text"]  # required keyword, as in the reference (:812)
-        if self.use_aug_text:
-            raise NotImplementedError("use_aug_text=True (configs/exp/occ_bg_augtext.yaml) is not on the dual-branch path")
+        rows = camera_param.shape[0] * (camera_param.shape[1] if self.use_aug_text else 1)
+        if encoder_hidden_states.shape[0] != rows:   # per-view prompts with use_aug_text (:351-352), else one per scene
+            raise ValueError(f"use_aug_text={bool(self.use_aug_text)}: expected {rows} prompt embeddings, got {encoder_hidden_states.shape[0]}")
         if guess_mode or attention_mask is not None or class_labels is not None or timestep_cond is not None:
             raise NotImplementedError("guess_mode / attention_mask / class_labels / timestep_cond are unused on the reference path")
         if not sample.is_cuda:

@@ -188,7 +188,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
 
 def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_col0=0, v_col0=0,
               q_hs=None, k_hs=None, v_hs=None, kv_map=None, n_src=1, n_kv_img=None, scale=None,
-              q_cols=None, k_cols=None, v_cols=None, variant=0, v_ones=False):
+              q_cols=None, k_cols=None, v_cols=None, variant=0, v_ones=False, concat=False):
     """q: [n_img*lq, *], k/v: [n_kv_img*lk, *] bf16 (may be column views of one fused projection output).
     variant: testing hook of the head_dim-40 kernel (include/dualdiff_b200.h), 0 = auto.
     v_ones (head_dim 40): V heads have a 48-column stride with 1.0 in column 40 -- the softmax denominator comes out of the
@@ -216,6 +216,7 @@ def attention(q, k, v, *, n_img, lq, lk, heads, head_dim, out=None, q_col0=0, k_
     a.scale = float(head_dim) ** -0.5 if scale is None else scale
     a.variant = variant
     a.v_ones = 1 if v_ones else 0
+    a.concat = 1 if concat else 0     # n_src > 1: one softmax over the concatenated sources instead of a sum of per-source attentions
     with _Rec("attn_tcgen05", 4.0 * n_img * lq * lk * heads * head_dim * n_src,
               2.0 * heads * head_dim * (2 * n_img * lq + 2 * n_kv_img * lk), f"d{head_dim}_Lq{lq}_Lk{lk}_s{n_src}"):
         check(_lib.lib().dd_attention(C.byref(a), _stream()), "dd_attention")

@@ -59,8 +59,13 @@ class DualDiffDenoiser:
             mine = range(B_all) if scenes_sliced else vs.scenes(B_all)
             full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
                         cond_fg=images[1], prompt_embeds=prompt_embeds)
-            loc = slice_views(full, vs.views, latents.shape[1], scenes=mine)
-            latents, camera_param, prompt_embeds = loc["latents"], loc["camera_param"], loc["prompt_embeds"]
+            n_all = latents.shape[1]
+            if prompt_embeds.shape[0] % (B_all * n_all) == 0 and n_all > 1:   # per-view prompts: keep this rank's scenes AND views
+                pe = prompt_embeds.reshape(-1, B_all, n_all, *prompt_embeds.shape[1:])[:, mine.start:mine.stop][:, :, vs.views]
+                full["prompt_embeds"] = None
+            loc = slice_views(full, vs.views, n_all, scenes=mine)
+            latents, camera_param = loc["latents"], loc["camera_param"]
+            prompt_embeds = loc["prompt_embeds"] if loc["prompt_embeds"] is not None else pe.reshape(-1, *pe.shape[3:]).contiguous()
             fg_boxes = bboxes_3d_data[1]            # map vectors are view-shared: only the scene selection applies
             fg_boxes = None if fg_boxes is None else slice_scenes(fg_boxes, mine, B_all, vs.n_cam)
             bboxes_3d_data = [loc["boxes_bg"], fg_boxes]
@@ -81,18 +86,23 @@ class DualDiffDenoiser:
             kw = self.nets[0].add_uncond_to_kwargs(camera_param=camera_param, bboxes_3d_data=bboxes_3d_data, image=None)
             cam, boxes = kw["camera_param"], kw["bboxes_3d_data"]
             text = prompt_embeds
-            assert text.shape[0] == 2 * B
+            # one prompt per scene, or one per view (use_aug_text, unet_addon_rawbox.py:351-352): uncond rows first either way
+            assert text.shape[0] in (2 * B, 2 * B * n_cam), (text.shape, B, n_cam)
         else:
             cam, boxes = camera_param, bboxes_3d_data
-            text = prompt_embeds[-B:]
+            per = n_cam if prompt_embeds.shape[0] % (B * n_cam) == 0 and n_cam > 1 else 1
+            text = prompt_embeds[-B * per:]
         # condition image / ORS tensor are identical in both CFG halves (pipeline:351-373 skips the uncond map)
         conds = [torch.cat([images[0]] * G) if G > 1 else images[0], torch.cat([images[1]] * G) if G > 1 else images[1]]
         preps = [net.prepare_condition(cam, text, boxes[i], conds[i], H, W) for i, net in enumerate(self.nets)]
         Pu = self.unet._packed
         unet_text_kv = engine.prepare_text(Pu, engine.ATTN2_LAYERS_UNET, preps[0].enc_rows)  # tokens of branch 0
         if self.view_shard is None:
-            kv_map = engine.make_kv_map(n, Pu["view_pairs"], dev)
+            kv_map = engine.make_kv_map(n, Pu["view_pairs"], dev, Pu["xview_mode"])
         else:
+            if Pu["xview_mode"] == "self":
+                raise NotImplementedError("camera-view sharding exchanges the two ring neighbours only: neighboring_attn_type='self' "
+                                          "needs every view of the scene on the rank")
             assert self.view_shard.v_loc == n_cam
             kv_map = self.view_shard.kv_map(G * B, dev)
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
@@ -152,7 +162,8 @@ class DualDiffDenoiser:
                 mark()
             temb = engine.time_embedding(Pu, self.t_cur)
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], view_shard=self.view_shard,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], xview_concat=Pu["xview_mode"] != "add",
+                                 view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
             self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
             eps = engine.unet_forward(Pu, self.latents, G, B6, H, W, ctx, acc[:12], acc[12])
@@ -171,7 +182,8 @@ class DualDiffDenoiser:
                 res.append((down, mid))
             temb = engine.time_embedding(Pu, self.t_cur)
             ctx = engine.StepCtx(n=self.n, temb=temb, temb_rows_per_img_factor=self.n, text_kv=self.unet_text_kv,
-                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], view_shard=self.view_shard,
+                                 lk=self.preps[0].lk, kv_map=self.kv_map, n_nbr=Pu["n_nbr"], xview_concat=Pu["xview_mode"] != "add",
+                                 view_shard=self.view_shard,
                                  n_outer=self.G * self.B)
             self.unet.video_ctx(ctx)   # video configuration: scenes are (clip, frame) pairs, frame-minor
 

@@ -242,8 +242,7 @@ class StableDiffusionBEVControlNetPipeline:
         if not isinstance(image, (list, tuple)) or len(image) != 2:
             raise ValueError("dual branch: `image` must be [bg occupancy panorama, fg ORS tensor]")
         bev_controlnet_kwargs = dict(bev_controlnet_kwargs)
-        if bev_controlnet_kwargs.get("use_aug_text", False):
-            raise NotImplementedError("use_aug_text=True (configs/exp/occ_bg_augtext.yaml) is not on the dual-branch path")
+        use_aug_text = bool(bev_controlnet_kwargs.get("use_aug_text", False))   # one prompt per VIEW (configs/exp/occ_bg_augtext.yaml)
         bboxes_3d_data = bev_controlnet_kwargs.get("bboxes_3d_data")
         if not isinstance(bboxes_3d_data, (list, tuple)) or len(bboxes_3d_data) != 2:
             raise ValueError("dual branch: bev_controlnet_kwargs['bboxes_3d_data'] must be [bg boxes, fg map vectors]")
@@ -252,9 +251,9 @@ class StableDiffusionBEVControlNetPipeline:
         if prompt is not None and isinstance(prompt, str):
             batch_size = 1
         elif prompt is not None and isinstance(prompt, list):
-            batch_size = len(prompt)
+            batch_size = len(prompt) if not use_aug_text else len(prompt) // 6      # reference :250
         else:
-            batch_size = prompt_embeds.shape[0]
+            batch_size = prompt_embeds.shape[0] if not use_aug_text else prompt_embeds.shape[0] // 6
         device = self.device
         if device.type != "cuda":
             raise RuntimeError("dualdiff_b200 has no CPU path: call pipe.to('cuda') first")

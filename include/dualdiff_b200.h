@@ -114,7 +114,7 @@ typedef struct dd_attention_args {
   int q_cols, k_cols, v_cols; /* logical widths of the q/k/v matrices (TMA bounds)             */
   int q_col0, k_col0, v_col0;
   int q_head_stride, k_head_stride, v_head_stride;
-  int n_img, n_kv_img, heads, head_dim, lq, lk, n_src;
+  int n_img, n_kv_img, heads, head_dim, lq, lk, n_src;   /* n_src: K/V sources per query image, 1..8 (kv_map columns) */
   float scale;
   int variant;                /* testing hook: 0 = auto.  head_dim 40: 0 = two query tiles per CTA, 25 % of the exponentials on
                                  the FMA pipe, 1 = one-tile kernel, 2 = two-tile kernel with every exponential on MUFU;
@@ -122,6 +122,9 @@ typedef struct dd_attention_args {
   int v_ones;                 /* head_dim 40 only: the V heads are padded to a 48-column stride and column 40 of every head
                                  holds 1.0 (the projection's bias writes it).  O[:, 40] = sum_k P[:, k] is then the softmax
                                  denominator, accumulated by the tensor core: the kernel keeps no row sum of its own. */
+  int concat;                 /* n_src > 1: 0 = one softmax per K/V source, outputs summed (neighboring_attn_type "add",
+                                 networks/blocks.py:112-121); 1 = the sources are ONE key sequence under a single softmax
+                                 ("concat", blocks.py:122-133; with all views of the scene as sources: "self", :134-137) */
 } dd_attention_args;
 DD_API int dd_attention(const dd_attention_args* args, void* stream);
 

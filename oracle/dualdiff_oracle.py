@@ -117,7 +117,7 @@ def temporal_attention(sd: SD, p: str, x, n_frames: int, n_cam=6):
     return o.reshape(n_clip, n_cam, T, n_frames, C).permute(0, 3, 1, 2, 4).reshape(n, T, C)
 
 
-def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames: int = 1, neighbors=None):
+def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames: int = 1, neighbors=None, attn_type="add"):
     x = x + attention(sd, p + ".attn1", _ln(sd, p + ".norm1", x))             # blocks.py:163-172
     x = x + attention(sd, p + ".attn2", _ln(sd, p + ".norm2", x), enc)        # blocks.py:175-188
     if multiview:
@@ -133,11 +133,22 @@ def transformer_block(sd: SD, p: str, x, enc, multiview: bool, n_cam=6, n_frames
         acc = torch.zeros_like(hv)
         nbr_table = NEIGHBORS if neighbors is None else neighbors       # neighboring_view_pair (blocks.py:112-121)
         n_nbr = len(next(iter(nbr_table.values())))
-        for cam, nbrs in nbr_table.items():
-            for nb in nbrs:
-                acc[:, cam] += mha(q[:, cam], k[:, nb], v[:, nb], HEADS)
+        if attn_type == "add":
+            for cam, nbrs in nbr_table.items():
+                for nb in nbrs:
+                    acc[:, cam] += mha(q[:, cam], k[:, nb], v[:, nb], HEADS)
+        elif attn_type == "concat":     # blocks.py:122-133: the neighbours' tokens form ONE key sequence, one pair per view
+            for cam, nbrs in nbr_table.items():
+                acc[:, cam] = mha(q[:, cam], torch.cat([k[:, nb] for nb in nbrs], dim=1), torch.cat([v[:, nb] for nb in nbrs], dim=1), HEADS)
+            n_nbr = 1
+        elif attn_type == "self":       # blocks.py:134-137: all views of a scene as one sequence of n_cam * T tokens
+            b_ = hv.shape[0]
+            acc = mha(q.reshape(b_, n_cam * T, C), k.reshape(b_, n_cam * T, C), v.reshape(b_, n_cam * T, C), HEADS).reshape(hv.shape)
+            n_nbr = 1
+        else:
+            raise NotImplementedError(f"Unknown type: {attn_type}")
         w_o, b_o = sd[p + ".attn4.to_out.0.weight"], sd[p + ".attn4.to_out.0.bias"]
-        out = F.linear(acc, w_o) + float(n_nbr) * b_o                  # to_out runs once per (view, neighbour) pair
+        out = F.linear(acc, w_o) + float(n_nbr) * b_o                  # "add": to_out runs once per (view, neighbour) pair
         out = _lin(sd, p + ".connector", out).reshape(bn, T, C)                # zero_linear connector, blocks.py:83,220
         x = x + out
     if n_frames > 1 and (p + ".attn_temp.to_q.weight") in sd:
@@ -289,7 +300,10 @@ def controlnet_forward(sd: SD, sample, timestep, camera_param, bboxes_3d_data, e
     fg (b*6, 320, h, w) ORS tensor.  Returns (12 residuals, mid residual, tokens (b*6, 78+L, 768))."""
     b, n_cam = camera_param.shape[:2]
     cam = camera_tokens(sd, camera_param)                                       # :832-837
-    txt = enc_text[:, None].expand(b, n_cam, *enc_text.shape[1:])               # use_aug_text False: repeat (:354)
+    if enc_text.shape[0] == b * n_cam and n_cam > 1:                            # use_aug_text: '(b n) ... -> b n ...' (:351-352)
+        txt = enc_text.reshape(b, n_cam, *enc_text.shape[1:])
+    else:
+        txt = enc_text[:, None].expand(b, n_cam, *enc_text.shape[1:])           # use_aug_text False: repeat (:354)
     enc_cam = torch.cat([cam[:, :, None], txt], dim=2)                          # (b, n, 78, 768)  :355-360
     if bboxes_3d_data is None:                                                  # bbox_emb = None: no box tokens (:892-895)
         tok = enc_cam.new_zeros((b, n_cam, 0, enc_cam.shape[-1]))
@@ -476,7 +490,8 @@ def noise_prediction(sd_unet: SD, sd_bg: SD, sd_fg: SD, latents, t, inputs, guid
     else:
         cam, box_bg, box_fg = inputs["camera_param"], inputs["boxes_bg"], inputs["boxes_fg"]
         cond_bg, cond_fg = inputs["cond_bg"], inputs["cond_fg"]
-        text = inputs["prompt_embeds"][B:] if inputs["prompt_embeds"].shape[0] == 2 * B else inputs["prompt_embeds"]
+        pe = inputs["prompt_embeds"]
+        text = pe[pe.shape[0] // 2:] if pe.shape[0] in (2 * B, 2 * B * n_cam) else pe
     d0, m0, enc = controlnet_forward(sd_bg, lat_in, tt, cam, box_bg, text, cond_bg, use_occ_3d=False)   # :405-420
     d1, m1, _ = controlnet_forward(sd_fg, lat_in, tt, cam, box_fg, text, cond_fg, use_occ_3d=True)
     down = [a + b for a, b in zip(d0, d1)]                                      # :422-429

@@ -161,3 +161,79 @@ def test_block_with_another_cross_view_topology(pairs):
     r = common.metrics(out, ref)
     print(f"block with {n_cam} views / {len(pairs[0])} neighbour(s) vs oracle:", r)
     assert r["cos"] >= 0.999 and r["rel_l2"] <= 2e-2, r
+
+
+@pytest.mark.parametrize("mode,dim,T", [("concat", 320, 150), ("self", 320, 150), ("concat", 640, 91), ("self", 1280, 28), ("add", 320, 150)])
+def test_block_neighboring_attn_types(mode, dim, T):
+    """neighboring_attn_type (networks/blocks.py:112-140): "concat" puts the two neighbours' tokens under ONE softmax, "self"
+    attends over all six views of the scene, "add" sums one attention per neighbour -- the same kernel with its K/V sources
+    concatenated or summed, against the oracle (itself equal to the reference's class in all three modes)"""
+    from dualdiff_b200.networks import BasicMultiviewTransformerBlock
+    from oracle import dualdiff_oracle as O
+    with torch.device("meta"):
+        blk = BasicMultiviewTransformerBlock(dim, 8, dim // 8, cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS,
+                                             neighboring_attn_type=mode)
+    sd = _seeded(blk, 9)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(12, T, dim, generator=g)
+    enc = torch.randn(12, 83, 768, generator=g)
+    with torch.no_grad():
+        ref = O.transformer_block({"b." + k: v for k, v in sd.items()}, "b", x, enc, True, attn_type=mode)
+        other = O.transformer_block({"b." + k: v for k, v in sd.items()}, "b", x, enc, True, attn_type="add" if mode != "add" else "concat")
+    assert (ref - other).abs().max() > 1e-2 * ref.abs().max()          # the modes really differ on these inputs
+    out = blk.to("cuda:0")(x.cuda(), encoder_hidden_states=enc.cuda()).float().cpu()
+    r = common.metrics(out, ref)
+    print(f"block with neighboring_attn_type={mode} (C={dim}) vs oracle:", r)
+    assert r["cos"] >= 0.999 and r["rel_l2"] <= 2e-2, r
+
+
+def test_unknown_neighboring_attn_type_raises():
+    from dualdiff_b200.networks import BasicMultiviewTransformerBlock
+    with pytest.raises(NotImplementedError, match="Unknown type"):
+        with torch.device("meta"):
+            BasicMultiviewTransformerBlock(320, 8, 40, cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS,
+                                           neighboring_attn_type="mean")
+
+
+def test_per_view_prompts_use_aug_text():
+    """use_aug_text (configs/exp/occ_bg_augtext.yaml; unet_addon_rawbox.py:351-352, pipeline_bev_controlnet.py:250): one prompt
+    per camera VIEW instead of one per scene -- a branch forward and a whole CFG noise prediction against the oracle"""
+    from dualdiff_b200 import synthetic as S
+    from dualdiff_b200.pipeline import DualDiffDenoiser
+    from oracle import dualdiff_oracle as O
+    unet, nets, sds = common.build_models()
+    h, w, B = 8, 12, 1
+    inp = S.make_inputs(B, h, w, seed=6, L_bg=5, L_fg=4)
+    g = torch.Generator().manual_seed(8)
+    inp["prompt_embeds"] = torch.randn(2 * B * 6, 77, 768, generator=g)          # uncond rows of all views first, then cond rows
+    dev = torch.device("cuda")
+    t = torch.tensor([500])
+    with torch.no_grad():
+        d_ref, m_ref, enc_ref = O.controlnet_forward(sds["bg"], inp["latents"], t, inp["camera_param"], inp["boxes_bg"],
+                                                     inp["prompt_embeds"][6:], inp["cond_bg"], use_occ_3d=False)
+        shared, _, _ = O.controlnet_forward(sds["bg"], inp["latents"], t, inp["camera_param"], inp["boxes_bg"],
+                                            inp["prompt_embeds"][6:7], inp["cond_bg"], use_occ_3d=False)
+    assert (d_ref[3] - shared[3]).abs().max() > 1e-3 * d_ref[3].abs().max()        # the views' prompts really differ
+    net = nets[0].cuda()
+    out = net(inp["latents"].to(dev), 500, camera_param=inp["camera_param"].to(dev), bboxes_3d_data=common.to_dev(inp["boxes_bg"], dev),
+              encoder_hidden_states=inp["prompt_embeds"][6:].to(dev), controlnet_cond=inp["cond_bg"].to(dev), use_aug_text=True)
+    r = common.metrics(out.mid_block_res_sample.float().cpu(), m_ref)
+    print("branch with per-view prompts, mid residual vs oracle:", r)
+    assert r["cos"] >= 0.999 and r["rel_l2"] <= 2e-2, r
+    assert torch.equal(out.encoder_hidden_states_with_cam.float().cpu()[:, 1:78], enc_ref[:, 1:78].to(torch.bfloat16).float())
+    with pytest.raises(ValueError, match="prompt embeddings"):
+        net(inp["latents"].to(dev), 500, camera_param=inp["camera_param"].to(dev), bboxes_3d_data=common.to_dev(inp["boxes_bg"], dev),
+            encoder_hidden_states=inp["prompt_embeds"][6:].to(dev), controlnet_cond=inp["cond_bg"].to(dev), use_aug_text=False)
+    # the sampler's noise prediction with CFG
+    den = DualDiffDenoiser(unet, nets, guidance_scale=2.0, use_cuda_graph=False)
+    d = common.to_dev(inp, dev)
+    den.prepare(d["latents"], d["prompt_embeds"], d["camera_param"], [d["boxes_bg"], d["boxes_fg"]], [d["cond_bg"], d["cond_fg"]],
+                num_inference_steps=4)
+    t0 = int(den.scheduler.timesteps[0])
+    den.step(0)
+    eps = den.eps_rows.float().cpu().reshape(2 * 6, h, w, 4).permute(0, 3, 1, 2)
+    with torch.no_grad():
+        ref = O.noise_prediction(sds["unet"], sds["bg"], sds["fg"], inp["latents"], t0, inp, 2.0, True)["eps_raw"]
+    r = common.metrics(eps, ref)
+    print("CFG noise prediction with per-view prompts vs oracle:", r)
+    assert r["cos"] >= 0.999 and r["rel_l2"] <= 2e-2, r

@@ -252,3 +252,23 @@ def test_sfa_plus_oracle_matches_reference_class_live():
         out = O.sfa_plus({"txt_con_fusionp." + k: v for k, v in sd.items()}, cond, txt)
     assert torch.equal(want, fix["out"])
     assert ((out - want).abs().max() / want.abs().max()).item() < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/MD_txt_con_fusion"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("mode", ["add", "concat", "self"])
+def test_oracle_block_matches_reference_class_for_every_neighboring_attn_type(mode):
+    """BasicMultiviewTransformerBlock of the reference (networks/blocks.py, unmodified, on the shim) in the three
+    neighboring_attn_type modes against oracle.transformer_block(attn_type=...)"""
+    from oracle import reference_model as RM
+    RM._paths()
+    from magicdrive.networks.blocks import BasicMultiviewTransformerBlock as Ref
+    ref = Ref(64, 8, 8, cross_attention_dim=768, neighboring_view_pair=common.NEIGHBORS, neighboring_attn_type=mode,
+              zero_module_type="zero_linear").eval()
+    sd = S.init_state_dict({k: tuple(v.shape) for k, v in ref.state_dict().items()}, seed=3)
+    ref.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(1)
+    x, enc = torch.randn(12, 10, 64, generator=g), torch.randn(12, 9, 768, generator=g)
+    with torch.no_grad():
+        want = ref(x, encoder_hidden_states=enc)
+        got = O.transformer_block({"b." + k: v for k, v in sd.items()}, "b", x, enc, True, attn_type=mode)
+    assert ((want - got).abs().max() / want.abs().max()).item() < 1e-6

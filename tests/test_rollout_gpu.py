@@ -170,7 +170,9 @@ def test_pipeline_rejects_unbuilt_options(world):
     base = dict(prompt=None, image=[None, None], camera_param=None, height=64, width=96)
     with pytest.raises(NotImplementedError, match="guess_mode"):
         pipe(**base, guess_mode=True)
-    with pytest.raises(NotImplementedError, match="use_aug_text"):
+    with pytest.raises(NotImplementedError, match="cross_attention_kwargs"):
+        pipe(**base, cross_attention_kwargs={"scale": 0.5})
+    with pytest.raises(ValueError, match="bboxes_3d_data"):       # use_aug_text itself is accepted (per-view prompts)
         pipe(**base, bev_controlnet_kwargs={"use_aug_text": True})
     with pytest.raises(ValueError, match="bboxes_3d_data"):
         pipe(**base, bev_controlnet_kwargs={"use_aug_text": False})
