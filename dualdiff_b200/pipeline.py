@@ -53,23 +53,9 @@ class DualDiffDenoiser:
         View-sharded: every rank passes the full inputs of the call (`scenes_sliced`: only the scenes of its group)."""
         if self.view_shard is not None:
             # every rank passes the FULL inputs of the call and keeps the scenes of its group and its own camera views
-            from .sharding import slice_scenes, slice_views
-            vs = self.view_shard
-            B_all = latents.shape[0]
-            mine = range(B_all) if scenes_sliced else vs.scenes(B_all)
-            full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
-                        cond_fg=images[1], prompt_embeds=prompt_embeds)
-            n_all = latents.shape[1]
-            if prompt_embeds.shape[0] % (B_all * n_all) == 0 and n_all > 1:   # per-view prompts: keep this rank's scenes AND views
-                pe = prompt_embeds.reshape(-1, B_all, n_all, *prompt_embeds.shape[1:])[:, mine.start:mine.stop][:, :, vs.views]
-                full["prompt_embeds"] = None
-            loc = slice_views(full, vs.views, n_all, scenes=mine)
-            latents, camera_param = loc["latents"], loc["camera_param"]
-            prompt_embeds = loc["prompt_embeds"] if loc["prompt_embeds"] is not None else pe.reshape(-1, *pe.shape[3:]).contiguous()
-            fg_boxes = bboxes_3d_data[1]            # map vectors are view-shared: only the scene selection applies
-            fg_boxes = None if fg_boxes is None else slice_scenes(fg_boxes, mine, B_all, vs.n_cam)
-            bboxes_3d_data = [loc["boxes_bg"], fg_boxes]
-            images = [loc["cond_bg"], loc["cond_fg"]]
+            from .sharding import slice_step_inputs
+            latents, prompt_embeds, camera_param, bboxes_3d_data, images = slice_step_inputs(
+                self.view_shard, latents, prompt_embeds, camera_param, bboxes_3d_data, images, scenes_sliced)
         dev = latents.device
         if dev.type != "cuda":
             raise RuntimeError("dualdiff_b200 has no CPU path: inputs must be CUDA tensors")

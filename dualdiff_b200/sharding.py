@@ -294,6 +294,27 @@ def slice_views(inputs: dict, views, n_cam: int = 6, scenes: range = None) -> di
     return out
 
 
+def slice_step_inputs(vs: "ViewShard", latents, prompt_embeds, camera_param, bboxes_3d_data, images, scenes_sliced: bool = False):
+    """what `DualDiffDenoiser.prepare` keeps on a view-sharded rank: the scenes of the rank's group (all of them when the
+    caller already passed only those) and the rank's camera views of latents, camera parameters, box tokens and both
+    condition inputs.  Prompt embeddings (uncond rows first) follow the scenes -- and the views when there is one prompt
+    per view (use_aug_text); the view-shared map vectors only follow the scenes."""
+    B_all, n_all = latents.shape[0], latents.shape[1]
+    mine = range(B_all) if scenes_sliced else vs.scenes(B_all)
+    full = dict(latents=latents, camera_param=camera_param, boxes_bg=bboxes_3d_data[0], cond_bg=images[0],
+                cond_fg=images[1], prompt_embeds=prompt_embeds)
+    pe = None
+    if prompt_embeds.shape[0] % (B_all * n_all) == 0 and n_all > 1:   # one prompt per view: keep this rank's scenes AND views
+        pe = prompt_embeds.reshape(-1, B_all, n_all, *prompt_embeds.shape[1:])[:, mine.start:mine.stop][:, :, vs.views]
+        pe = pe.reshape(-1, *pe.shape[3:]).contiguous()
+        full["prompt_embeds"] = None
+    loc = slice_views(full, vs.views, n_all, scenes=mine)
+    fg_boxes = bboxes_3d_data[1]
+    fg_boxes = None if fg_boxes is None else slice_scenes(fg_boxes, mine, B_all, vs.n_cam)
+    return (loc["latents"], pe if pe is not None else loc["prompt_embeds"], loc["camera_param"], [loc["boxes_bg"], fg_boxes],
+            [loc["cond_bg"], loc["cond_fg"]])
+
+
 def gathered_kv_image(clip: int, frame: int, view: int, n_clip: int, f_loc: int, n_view: int = 6) -> int:
     """image index of (clip, global frame, view) inside FrameShard.gather's rank-major buffer -- the address arithmetic
     of csrc/dd_temporal.cu (kv_rank_stride = n_clip * f_loc * n_view images)"""

@@ -7,20 +7,27 @@ from dualdiff_b200 import ops
 n = int(os.environ.get("N_IMG", "96"))
 L = int(os.environ.get("TOKENS", "1400"))
 d, dp = 40, 48
-qkv = (torch.randn(n * L, 16 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
-txt = (torch.randn(n * 106, 8 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
+ones = os.environ.get("V_ONES", "0") == "1"      # the shipped layout: V heads padded to 48 columns, column 40 = 1.0
+dv = dp if ones else d
+qkv = (torch.randn(n * L, 16 * dp + 8 * dv, device="cuda") * 0.5).to(torch.bfloat16)
+txt = (torch.randn(n * 106, 8 * dp + 8 * dv, device="cuda") * 0.5).to(torch.bfloat16)
+if ones:
+    for t, rows, k0 in ((qkv, n * L, 16), (txt, n * 106, 8)):
+        v = t.view(rows, -1, dp)
+        v[:, k0:, d:] = 0
+        v[:, k0:, d] = 1.0
 kv_map = torch.tensor([[(i // 6) * 6 + (i + 5) % 6, (i // 6) * 6 + (i + 1) % 6] for i in range(n)], dtype=torch.int32, device="cuda")
 
 
 def run(kind, variant):
     if kind == "self":
         return ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp,
-                             variant=variant)
+                             variant=variant, v_ones=ones)
     if kind == "xview":
         return ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp,
-                             kv_map=kv_map, n_src=2, variant=variant)
+                             kv_map=kv_map, n_src=2, variant=variant, v_ones=ones)
     return ops.attention(qkv, txt, txt, n_img=n, lq=L, lk=106, heads=8, head_dim=d, q_col0=0, k_col0=0, v_col0=8 * dp,
-                         q_cols=8 * dp, variant=variant)
+                         q_cols=8 * dp, variant=variant, v_ones=ones)
 
 
 def timed(kind, variant, reps=8):

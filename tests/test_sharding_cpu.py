@@ -219,6 +219,34 @@ def test_view_shard_groups_four_ranks_gloo():
         assert peers == (rank ^ 1, rank ^ 1)          # exchanges stay inside the group
 
 
+def test_view_sharded_step_inputs_follow_scenes_and_views():
+    """what a rank of a 4-GPU job (2 groups x 2 ranks) keeps of a 4-scene call: its group's scenes, its 3 views; prompts per
+    scene and per view (use_aug_text)"""
+    from dualdiff_b200.sharding import ViewShard, slice_step_inputs
+    from dualdiff_b200 import synthetic as S
+    B, h, w = 4, 4, 6
+    inp = S.make_inputs(B, h, w, seed=3, L_bg=3, L_fg=4, same_noise_across_views=False)
+    vs = ViewShard(3, 4)                               # group 1 (scenes 2, 3), second half of the views
+    assert list(vs.scenes(B)) == [2, 3] and vs.views == [3, 4, 5]
+    args = (inp["latents"], inp["prompt_embeds"], inp["camera_param"], [inp["boxes_bg"], inp["boxes_fg"]], [inp["cond_bg"], inp["cond_fg"]])
+    lat, pe, cam, boxes, images = slice_step_inputs(vs, *args)
+    assert torch.equal(lat, inp["latents"][2:4, 3:6]) and torch.equal(cam, inp["camera_param"][2:4, 3:6])
+    assert torch.equal(pe, torch.cat([inp["prompt_embeds"][2:4], inp["prompt_embeds"][B + 2:B + 4]]))       # uncond rows, then cond rows
+    assert torch.equal(boxes[0]["bboxes"], inp["boxes_bg"]["bboxes"][2:4, 3:6]) and torch.equal(boxes[1]["bboxes"], inp["boxes_fg"]["bboxes"][2:4])
+    assert torch.equal(images[0], inp["cond_bg"][2:4][..., 3 * 48:6 * 48])
+    assert torch.equal(images[1], inp["cond_fg"].reshape(B, 6, 320, h, w)[2:4, 3:6].reshape(6, 320, h, w))
+    # one prompt per view: rows are (cfg half, scene, view)
+    pv = torch.arange(2 * B * 6, dtype=torch.float32).view(-1, 1, 1).expand(2 * B * 6, 2, 3).contiguous()
+    _, pe2, _, _, _ = slice_step_inputs(vs, inp["latents"], pv, *args[2:])
+    want = [half * B * 6 + s * 6 + v for half in range(2) for s in (2, 3) for v in (3, 4, 5)]
+    assert pe2[:, 0, 0].tolist() == [float(x) for x in want]
+    # the caller already cut the scenes of the group
+    lat3, _, _, _, _ = slice_step_inputs(vs, inp["latents"][2:4], inp["prompt_embeds"][[2, 3, 6, 7]], inp["camera_param"][2:4],
+                                         [{k: v[2:4] for k, v in inp["boxes_bg"].items()}, {k: v[2:4] for k, v in inp["boxes_fg"].items()}],
+                                         [inp["cond_bg"][2:4], inp["cond_fg"][12:24]], scenes_sliced=True)
+    assert torch.equal(lat3, lat)
+
+
 def test_view_shard_world_sizes():
     from dualdiff_b200.sharding import ViewShard, default_ranks_per_scene
     import pytest
