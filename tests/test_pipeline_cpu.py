@@ -83,7 +83,7 @@ def test_call_checks_before_touching_the_gpu():
     base = dict(prompt=["a"], image=[torch.zeros(1), torch.zeros(1)], camera_param=None, height=64, width=96)
     with pytest.raises(NotImplementedError, match="guess_mode"):
         pipe(**base, guess_mode=True)
-    with pytest.raises(NotImplementedError, match="use_aug_text"):
+    with pytest.raises(ValueError, match="bboxes_3d_data"):      # per-view prompts are supported: the next check fires
         pipe(**base, bev_controlnet_kwargs={"use_aug_text": True})
     with pytest.raises(ValueError, match="bboxes_3d_data"):
         pipe(**base, bev_controlnet_kwargs={"use_aug_text": False})
