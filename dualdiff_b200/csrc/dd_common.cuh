@@ -157,6 +157,7 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -345,6 +346,12 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
   return d;
 }
 
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // Shared-memory matrix descriptor (sm_100 UMMA). Fields, following the public CUTLASS
 // cute::UMMA::SmemDescriptor bit layout: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
@@ -401,6 +408,33 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   y = y * t * e;                                        // 1 - erf(|z|)
   const float phi = x >= 0.f ? fmaf(-0.5f, y, 1.f) : 0.5f * y;   // Phi(x) = 0.5 (1 + erf(x / sqrt 2))
   return x * phi;
+}
+// GEGLU on a pair of columns: (v0 * gelu(g0), v1 * gelu(g1)) with the same A&S 7.1.26 erf, the polynomial and the products as
+// packed FFMA2 / FMUL2 (the GEGLU epilogue is issue-bound: 64 gelus per thread and chunk): 17 FMA-pipe + 4 MUFU instructions
+// per PAIR against 2 x (19 + 2).  Phi(x) = 0.5 + copysign(0.5 - 0.5 y, x) with y = 1 - erf(|x| / sqrt 2).
+__device__ __forceinline__ uint64_t geglu_pair(uint64_t V, uint64_t G) {
+  float g0, g1;
+  unpack_f32x2(G, g0, g1);
+  const uint64_t Z = pack_f32x2(fabsf(g0) * 0.70710678118654752f, fabsf(g1) * 0.70710678118654752f);
+  float d0, d1, q0, q1, t0, t1, e0, e1;
+  unpack_f32x2(fma_f32x2(Z, pack_f32x2(0.3275911f, 0.3275911f), pack_f32x2(1.f, 1.f)), d0, d1);
+  unpack_f32x2(mul_f32x2(mul_f32x2(Z, Z), pack_f32x2(-1.4426950408889634f, -1.4426950408889634f)), q0, q1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+  const uint64_t T = pack_f32x2(t0, t1);
+  uint64_t Y = fma_f32x2(T, pack_f32x2(1.061405429f, 1.061405429f), pack_f32x2(-1.453152027f, -1.453152027f));
+  Y = fma_f32x2(Y, T, pack_f32x2(1.421413741f, 1.421413741f));
+  Y = fma_f32x2(Y, T, pack_f32x2(-0.284496736f, -0.284496736f));
+  Y = fma_f32x2(Y, T, pack_f32x2(0.254829592f, 0.254829592f));
+  Y = mul_f32x2(mul_f32x2(Y, T), pack_f32x2(e0, e1));                        // 1 - erf(|z|)
+  float h0, h1;
+  unpack_f32x2(fma_f32x2(Y, pack_f32x2(-0.5f, -0.5f), pack_f32x2(0.5f, 0.5f)), h0, h1);   // 0.5 erf(|z|) >= 0
+  h0 = __uint_as_float(__float_as_uint(h0) | (__float_as_uint(g0) & 0x80000000u));
+  h1 = __uint_as_float(__float_as_uint(h1) | (__float_as_uint(g1) & 0x80000000u));
+  const uint64_t PHI = add_f32x2(pack_f32x2(h0, h1), pack_f32x2(0.5f, 0.5f));
+  return mul_f32x2(V, mul_f32x2(G, PHI));
 }
 #endif  // __CUDACC__
 

@@ -31,6 +31,46 @@
 
 namespace dd {
 
+// A/B hooks of profiles/ab (the shipped library is built without -D overrides)
+#ifndef DD_GEMM_AREUSE
+#define DD_GEMM_AREUSE 1
+#endif
+#ifndef DD_CONV_MERGED
+#define DD_CONV_MERGED 1
+#endif
+
+// Timeline instrumentation for profiles/gemm_trace.py: only in a -DDD_GEMM_TRACE build (never in the shipped library).  Lane 0
+// of every warp of ONE CTA records (event, warp, tile, SM clock).
+#ifdef DD_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[10 * 2 * 2048];
+#define DD_GT_DECL unsigned int gt_n_ = 0;
+#define DD_GT(ev, tile)                                                                                       \
+  do {                                                                                                        \
+    if (blockIdx.x == 6 && (threadIdx.x & 31) == 0 && gt_n_ < 2048u) {                                        \
+      unsigned long long* e_ = g_gemm_trace + ((threadIdx.x >> 5) * 2048u + gt_n_) * 2u;                      \
+      e_[0] = ((unsigned long long)(ev) << 48) | ((unsigned long long)(threadIdx.x >> 5) << 32) | (unsigned)(tile); \
+      e_[1] = clock64();                                                                                      \
+      ++gt_n_;                                                                                                \
+    }                                                                                                         \
+  } while (0)
+// accumulate the cycles of one statement (barrier waits of the issuing warp) / record an accumulated value as an event
+#define DD_GT_TIMED(acc, stmt) do { const long long t_ = clock64(); stmt; acc += clock64() - t_; } while (0)
+#define DD_GT_VAL(ev, tile, val)                                                                              \
+  do {                                                                                                        \
+    if (blockIdx.x == 6 && (threadIdx.x & 31) == 0 && gt_n_ < 2048u) {                                        \
+      unsigned long long* e_ = g_gemm_trace + ((threadIdx.x >> 5) * 2048u + gt_n_) * 2u;                      \
+      e_[0] = ((unsigned long long)(ev) << 48) | ((unsigned long long)(threadIdx.x >> 5) << 32) | (unsigned)(tile); \
+      e_[1] = (unsigned long long)(val) | (1ull << 62);                                                       \
+      ++gt_n_;                                                                                                \
+    }                                                                                                         \
+  } while (0)
+#else
+#define DD_GT_DECL
+#define DD_GT(ev, tile) do { } while (0)
+#define DD_GT_TIMED(acc, stmt) stmt
+#define DD_GT_VAL(ev, tile, val) do { } while (0)
+#endif
+
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 static constexpr int GEMM_THREADS_MAX = 320;  // TMA warp + UMMA warp + 8 epilogue warps
@@ -69,6 +109,11 @@ struct GemmDev {
   // sums the contributors in fixed order and applies the epilogue (bit-reproducible, no atomics).
   int sk_chunk, sk_maxc;
   float* ws;
+  // areuse = 1 (short K: the ring has exactly one slot per 64-wide k-block, so slot s always holds k-block s): every worker
+  // takes a CONTIGUOUS range of the (m-major, n-fastest) tile order and keeps the A blocks of an m-tile in the ring for all
+  // of its n-tiles -- only the B half of a stage is reloaded.  The activation then crosses the L2 -> SM fabric once instead
+  // of n_tiles times (ncu: the K = 320 GEMMs move 5500 B/clk through a fabric that caps near 6300).
+  int areuse;
 };
 
 // Work iterator shared by the three roles of the GEMM kernel.  Classic: tiles worker, worker + n_workers, ... with all
@@ -77,11 +122,17 @@ struct GemmDev {
 struct WorkIter {
   int tile, it0, it1;
   int pos, end, iters, step, total_tiles, sk;
-  __device__ __forceinline__ WorkIter(int worker, int n_workers, int total_tiles_, int iters_, int sk_chunk)
+  // contiguous = 1: the worker owns tiles [worker * T / W, (worker + 1) * T / W) (GemmDev::areuse)
+  __device__ __forceinline__ WorkIter(int worker, int n_workers, int total_tiles_, int iters_, int sk_chunk, int contiguous = 0)
       : tile(worker - n_workers), it0(0), it1(iters_), pos(worker * sk_chunk), iters(iters_), step(n_workers),
         total_tiles(total_tiles_), sk(sk_chunk) {
     const int total = total_tiles_ * iters_;
     end = pos + sk_chunk < total ? pos + sk_chunk : total;
+    if (contiguous) {
+      tile = (int)(((long long)worker * total_tiles_) / n_workers) - 1;
+      total_tiles = (int)(((long long)(worker + 1) * total_tiles_) / n_workers);
+      step = 1;
+    }
   }
   __device__ __forceinline__ bool next() {
     if (sk == 0) {
@@ -110,17 +161,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;   // per CTA: the whole B tile, or its half of the pair's tile
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int TILE_M = BM * CG;
+  // 3x3 conv on tiles up to 192 wide: ONE ring whose slot holds everything an iteration (kernel row kh, 64 channels) needs --
+  // the activation box and the weight boxes of its three taps -- behind one full / one empty barrier.  The timeline of the
+  // issuing warp (profiles/gemm_trace.py conv) showed every barrier wait costing ~90 cycles even when the data is there
+  // and every UMMA / commit ~50: with a wait + commit per tap (4 UMMAs) a stage took 383 cycles against the 320 tensor
+  // cycles of its four 160-wide UMMAs -- the issuing thread, not the tensor core, set the pace.  One wait + one commit per
+  // twelve UMMAs is ~740 cycles of issue against 960 of tensor work.  (256-wide tiles: a UMMA is 128 tensor cycles, the
+  // issuer keeps up, and only two such slots would fit: they keep the separate activation / weight rings.)
+  constexpr bool MERGED = CONV && BN <= 192 && DD_CONV_MERGED;
+  constexpr int CONV_SLOT_BYTES = A_CONV_BYTES + 3 * B_STAGE_BYTES;
   constexpr int ACC_COLS = (BN < 32) ? 32 : BN;      // columns per accumulator buffer
   constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
   constexpr uint32_t IDESC = umma_idesc_bf16(BM * CG, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 8];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4 + 16];
   __shared__ uint32_t tmem_ptr_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  DD_GT_DECL
   const int stages = p.stages;
   const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;          // 0 = leader of the CTA pair
   const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -152,7 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_init(smem_u32(&bars[24 + s]), 1);   //                  empty
       }
     } else {
-      for (int s = 0; s < 8; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per-epilogue-warp residual tile landed
+      for (int s = 0; s < 16; ++s) mbar_init(smem_u32(&bars[20 + s]), 1);  // per epilogue warp: residual landed in staging tile 0 / 1
     }
     fence_mbar_init();
   }
@@ -179,7 +240,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t afull_bar = smem_u32(&bars[20]);
   const uint32_t aempty_bar = smem_u32(&bars[24]);
   const uint32_t ring_b = CONV ? smem_base + (uint32_t)p.a_stages * A_CONV_BYTES : smem_base;   // weight ring (conv)
-  const uint32_t epi_base = CONV ? ring_b + (uint32_t)stages * B_STAGE_BYTES : smem_base + (uint32_t)stages * STAGE_BYTES;
+  const uint32_t epi_base = MERGED ? smem_base + (uint32_t)stages * CONV_SLOT_BYTES
+                            : CONV ? ring_b + (uint32_t)stages * B_STAGE_BYTES : smem_base + (uint32_t)stages * STAGE_BYTES;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int pitch = p.conv_W + 1;
 
@@ -191,12 +253,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
       // ring positions are carried as (slot, parity) counters: no integer division in the steady-state loops
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk, p.areuse);
+      int prev_m0 = -1;
       while (wi.next()) {
         const int tile = wi.tile;
         const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
         const int n0 = (tile % p.n_tiles) * BN;
-        if constexpr (CONV) {
+        if constexpr (MERGED) {
+          int kh = wi.it0 / kchunks;
+          int kc = (wi.it0 - kh * kchunks) * BK;
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            mbar_wait(empty_bar + 8 * sb, pb ^ 1);
+            const int arow = m0 + (kh - 1) * pitch - 1;   // box rows [arow, arow + 130): taps kw = 0, 1, 2 start at row kw
+            const uint32_t sA = smem_base + sb * CONV_SLOT_BYTES;
+            const uint32_t sB = sA + A_CONV_BYTES;
+            const int bcol = kh * 3 * p.K + kc;           // weight columns of tap (kh, kw): (kh * 3 + kw) * K + kc
+            if constexpr (CG == 1) {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(full_bar + 8 * sb, A_CONV_TX + 3 * B_STAGE_BYTES);
+                if (kc < p.K1) tma_load_2d(sA, &tmA, full_bar + 8 * sb, kc, arow);
+                else tma_load_2d(sA, &tmA2, full_bar + 8 * sb, kc - p.K1, arow);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) tma_load_2d(sB + kw * B_STAGE_BYTES, &tmB, full_bar + 8 * sb, bcol + kw * p.K, n0);
+              }
+            } else {
+              const uint32_t full_leader = mapa_shared(full_bar + 8 * sb, 0);
+              if (elect_one()) {
+                if (kc < p.K1) tma_load_2d_2cta(sA, &tmA, full_leader, kc, arow);
+                else tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, arow);
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                  tma_load_2d_2cta(sB + kw * B_STAGE_BYTES, &tmB, full_leader, bcol + kw * p.K, n0 + (int)crank * (BN / 2));
+                if (crank == 0) mbar_arrive_expect_tx(full_bar + 8 * sb, 2 * (A_CONV_TX + 3 * B_STAGE_BYTES));
+                else mbar_arrive_cluster(full_leader);
+              }
+            }
+            __syncwarp();
+            if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
+            kc += BK;
+            if (kc >= p.K) { kc = 0; ++kh; }
+          }
+        } else if constexpr (CONV) {
           int kh = wi.it0 / kchunks;
           int kc = (wi.it0 - kh * kchunks) * BK;
           for (int it = wi.it0; it < wi.it1; ++it) {
@@ -247,30 +344,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           int tap = wi.it0 / kchunks;
           int kc = (wi.it0 - tap * kchunks) * BK;
+          // A reuse: the ring slots still hold the A blocks of this m-tile (loaded for the previous n-tile of this worker)
+          const bool load_a = !(p.areuse && m0 == prev_m0);
+          prev_m0 = m0;
+          const uint32_t tx = load_a ? (uint32_t)STAGE_BYTES : (uint32_t)B_STAGE_BYTES;
+          DD_GT(20, tile);
           for (int it = wi.it0; it < wi.it1; ++it) {
             mbar_wait(empty_bar + 8 * sb, pb ^ 1);
+            if (it == wi.it0) DD_GT(21, tile);
             const uint32_t sA = smem_base + sb * STAGE_BYTES;
             const uint32_t sB = sA + A_STAGE_BYTES;
             if constexpr (CG == 1) {
               if (elect_one()) {
-                mbar_arrive_expect_tx(full_bar + 8 * sb, STAGE_BYTES);
-                if (kc < p.K1)
-                  tma_load_2d(sA, &tmA, full_bar + 8 * sb, kc, m0);
-                else
-                  tma_load_2d(sA, &tmA2, full_bar + 8 * sb, kc - p.K1, m0);
+                mbar_arrive_expect_tx(full_bar + 8 * sb, tx);
+                if (load_a) {
+                  if (kc < p.K1)
+                    tma_load_2d(sA, &tmA, full_bar + 8 * sb, kc, m0);
+                  else
+                    tma_load_2d(sA, &tmA2, full_bar + 8 * sb, kc - p.K1, m0);
+                }
                 tma_load_2d(sB, &tmB, full_bar + 8 * sb, tap * p.K + kc, n0);
               }
             } else {
               // both CTAs load into their own smem; every byte is credited to the LEADER's full barrier
               const uint32_t full_leader = mapa_shared(full_bar + 8 * sb, 0);
               if (elect_one()) {
-                if (kc < p.K1)
-                  tma_load_2d_2cta(sA, &tmA, full_leader, kc, m0);
-                else
-                  tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, m0);
+                if (load_a) {
+                  if (kc < p.K1)
+                    tma_load_2d_2cta(sA, &tmA, full_leader, kc, m0);
+                  else
+                    tma_load_2d_2cta(sA, &tmA2, full_leader, kc - p.K1, m0);
+                }
                 tma_load_2d_2cta(sB, &tmB, full_leader, tap * p.K + kc, n0 + (int)crank * (BN / 2));
                 if (crank == 0)
-                  mbar_arrive_expect_tx(full_bar + 8 * sb, 2 * STAGE_BYTES);
+                  mbar_arrive_expect_tx(full_bar + 8 * sb, 2 * tx);
                 else
                   mbar_arrive_cluster(full_leader);
               }
@@ -280,6 +387,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             kc += BK;
             if (kc >= p.K) { kc = 0; ++tap; }
           }
+          DD_GT(22, tile);
         }
       }
     }
@@ -290,21 +398,53 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t local_tile = 0;
       // descriptor = constant fields | (address >> 4): shared-memory addresses are < 256 KB, so no masking is needed
       const uint64_t DESC0 = umma_smem_desc(0, 16, 1024, 2);
-      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+      WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk, p.areuse);
       for (; wi.next(); ++local_tile) {
         const uint32_t as = local_tile & 1;
         const uint32_t aph = (local_tile >> 1) & 1;
+        DD_GT(10, wi.tile);
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
+        DD_GT(11, wi.tile);
         const uint32_t tmem_d = tmem_base + as * ACC_COLS;
         uint32_t fresh = 0;                       // becomes 1 after the first UMMA of this segment
-        if constexpr (CONV) {
+        if constexpr (MERGED) {
+          [[maybe_unused]] long long w_b = 0;
           for (int it = wi.it0; it < wi.it1; ++it) {
-            mbar_wait(afull_bar + 8 * sa, pa);
+            DD_GT_TIMED(w_b, mbar_wait(full_bar + 8 * sb, pb));
+            tc_fence_after();
+            if (it == wi.it0) DD_GT(12, wi.tile);
+            const uint32_t sA = smem_base + sb * CONV_SLOT_BYTES;
+            if (elect_one()) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                // tap kw reads box rows [kw, kw + 128): start address kw * 128 B into the (1024-aligned) slot
+                const uint64_t dA = DESC0 + ((sA + kw * 128) >> 4);
+                const uint64_t dB = DESC0 + ((sA + A_CONV_BYTES + kw * B_STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint32_t acc = (k != 0 || kw != 0) ? 1u : fresh;
+                  if constexpr (CG == 2) umma_bf16_2cta(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
+                  else umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, IDESC, acc);
+                }
+              }
+              // the slot (in both CTAs of a pair) is free once the twelve UMMAs retire
+              if constexpr (CG == 2) umma_commit_2cta(empty_bar + 8 * sb, 3); else umma_commit(empty_bar + 8 * sb);
+            }
+            __syncwarp();
+            fresh = 1;
+            if (++sb == (uint32_t)stages) { sb = 0; pb ^= 1; }
+          }
+          DD_GT_VAL(15, wi.tile, w_b);
+        } else if constexpr (CONV) {
+          [[maybe_unused]] long long w_a = 0, w_b = 0;
+          for (int it = wi.it0; it < wi.it1; ++it) {
+            DD_GT_TIMED(w_a, mbar_wait(afull_bar + 8 * sa, pa));
+            if (it == wi.it0) DD_GT(12, wi.tile);
             const uint32_t sA = smem_base + sa * A_CONV_BYTES;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              mbar_wait(full_bar + 8 * sb, pb);
+              DD_GT_TIMED(w_b, mbar_wait(full_bar + 8 * sb, pb));
               tc_fence_after();
               // tap kw reads box rows [kw, kw + 128): start address kw * 128 B into the (1024-aligned) slot
               const uint64_t dA = DESC0 + ((sA + kw * 128) >> 4);
@@ -327,10 +467,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (++sa == (uint32_t)p.a_stages) { sa = 0; pa ^= 1; }
           }
+          DD_GT_VAL(14, wi.tile, w_a);
+          DD_GT_VAL(15, wi.tile, w_b);
         } else {
           for (int it = wi.it0; it < wi.it1; ++it) {
             mbar_wait(full_bar + 8 * sb, pb);
             tc_fence_after();
+            if (it == wi.it0) DD_GT(12, wi.tile);
             const uint32_t sA = smem_base + sb * STAGE_BYTES;
             const uint64_t dA = DESC0 + (sA >> 4);
             const uint64_t dB = DESC0 + ((sA + A_STAGE_BYTES) >> 4);
@@ -355,6 +498,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (CG == 2) umma_commit_2cta(tfull_bar + 8 * as, 3); else umma_commit(tfull_bar + 8 * as);
         }
         __syncwarp();
+        DD_GT(13, wi.tile);
       }
     }
   } else {
@@ -372,63 +516,167 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int OUTW = p.geglu ? BN / 2 : BN;
     if (p.tma_epi) {
       // ---------------- TMA epilogue (plain GEMM, bf16 out): everything stays in the row-per-thread domain ----------
-      // per 64-column chunk: TMEM -> regs, + bias, + residual tile (TMA-loaded into swizzled smem, prefetched one
-      // chunk ahead), activation, bf16 pack -> swizzled smem tile -> TMA store.  No strided global access at all.
+      // Per 64-column chunk: TMEM -> regs (both 32-column halves up front), + bias, + residual, activation, bf16 pack ->
+      // swizzled staging tile -> TMA store.  The timeline of a CTA (profiles/gemm_trace.py, profiles/r02_gemm_trace.txt)
+      // showed the short-K GEMMs bound by this loop, not by their operands (M=134400 N=320 K=320: 41 us, 29 us with the
+      // accumulators merely handed back): a 192-wide tile has three chunks, so the warps of one half did two per tile
+      // while the others idled 40 % of the time; the second tile of N = 320 computed a chunk that lies wholly beyond N;
+      // every bulk-async instruction (wait_group.read, fence.proxy.async, store + commit) costs 200-300 cycles, two
+      // integer divisions per tile another 300.  Hence:
+      //   * a warp owns TWO 4 KB staging tiles used alternately; the residual tile of a chunk is TMA-loaded INTO the tile
+      //     its output will be staged in (the thread reads and overwrites its own 16-byte units), a whole chunk ahead:
+      //     issued right after the store of the previous chunk from that tile has released it;
+      //   * chunks beyond N are skipped, and the odd chunk of a tile alternates between the two halves from tile to tile
+      //     (the two accumulator buffers let one half run a tile ahead of the other);
+      //   * the accumulator goes back to the UMMA warp as soon as the last chunk's TMEM loads have landed;
+      //   * tile coordinates are carried as (m, n) counters.
       if constexpr (BN % 64 == 0 && !CONV) {
-        // TMA mode runs 8 epilogue warps: warps 2-5 take the even 64-column chunks, warps 6-9 the odd ones
-        // (two warps per TMEM lane quarter -> two warps per scheduler, hiding each other's TMEM/smem latency).
-        const int half = (warp - 2) >> 2;
-        const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
-        const uint32_t out_stage = my_stage;           // 32 rows x 128 B, SWIZZLE_128B
-        const uint32_t r1_stage = my_stage + 4096;
-        const uint32_t r1_bar = smem_u32(&bars[20 + (warp - 2)]);
-        const bool has_r1 = p.res1 != nullptr;
+        const int half = (warp - 2) >> 2;     // warps 2-5 / 6-9: two warps per TMEM lane quarter (and per scheduler)
+        const uint32_t my_stage = epi_base + (uint32_t)(warp - 2) * EPI_WARP_BYTES;   // two 32-row x 128 B tiles, SWIZZLE_128B
+        const uint32_t r1_bar = smem_u32(&bars[20 + 2 * (warp - 2)]);                 // [2]: residual landed in tile 0 / 1
         const bool geglu = p.geglu != 0;
+        const bool has_r1 = p.res1 != nullptr && !geglu;     // (the host rejects GEGLU with a residual)
         const int act = p.act;
         const float* __restrict__ bias = p.bias;
         const uint32_t xr = (uint32_t)(lane & 7);
-        uint32_t r1_phase = 0;
         const int nch = geglu ? (BN / 128) : (BN / 64);
-        const int n_epi_halves = (int)(blockDim.x - 64) / 128;   // 2 in TMA mode
-        auto r1_issue = [&](int t, int ch) {
-          const int tm0 = (t / p.n_tiles) * TILE_M + (int)crank * BM + q * 32;
-          const int tn0 = (t % p.n_tiles) * BN + ch * 64;
-          mbar_arrive_expect_tx(r1_bar, 4096);
-          tma_load_2d(r1_stage, &tmR1, r1_bar, tn0, tm0);
+        // this worker's tiles: worker, worker + n_workers, ... or (A reuse) a contiguous range of the tile order
+        const int t_step = p.areuse ? 1 : n_workers;
+        const int t_begin = p.areuse ? (int)(((long long)worker * total_tiles) / n_workers) : worker;
+        const int t_end = p.areuse ? (int)(((long long)(worker + 1) * total_tiles) / n_workers) : total_tiles;
+        const int step_m = t_step / p.n_tiles, step_n = t_step - step_m * p.n_tiles;
+        // chunk cursor: (tile, its (m, n) tile coordinates, index of the tile in this worker's sequence, chunk)
+        struct Cur { int tile, m, n, lt, ch; };
+        auto n_valid = [&](int n_idx) {            // chunks of this n-tile that hold columns < N
+          if (geglu) return nch;
+          const int v = (p.N - n_idx * BN + 63) >> 6;
+          return v < nch ? v : nch;
         };
-        if (has_r1 && lane == 0 && worker < total_tiles && half < nch) r1_issue(worker, half);
-        for (int tile = worker; tile < total_tiles; tile += n_workers, ++local_tile) {
-          const int m0 = (tile / p.n_tiles) * TILE_M + (int)crank * BM;
-          const int n0 = (tile % p.n_tiles) * BN;
-          const int nout0 = geglu ? (n0 / BN) * (BN / 2) : n0;
+        auto next_tile = [&](Cur& c) {
+          c.tile += t_step; ++c.lt;
+          c.m += step_m; c.n += step_n;
+          if (c.n >= p.n_tiles) { c.n -= p.n_tiles; ++c.m; }
+        };
+        auto next_chunk = [&](Cur& c) {            // the next chunk THIS warp processes; false when there is none
+          c.ch += 2;
+          while (c.tile < t_end) {
+            if (c.ch < n_valid(c.n)) return true;
+            next_tile(c);
+            c.ch = (half + c.lt) & 1;              // the halves swap the even / odd chunks from tile to tile
+          }
+          return false;
+        };
+        auto r1_issue = [&](const Cur& c, uint32_t k) {   // residual box of chunk c -> staging tile k & 1 (lane 0)
+          mbar_arrive_expect_tx(r1_bar + 8 * (k & 1u), 4096);
+          tma_load_2d(my_stage + (k & 1u) * 4096u, &tmR1, r1_bar + 8 * (k & 1u), c.n * BN + c.ch * 64,
+                      c.m * TILE_M + (int)crank * BM + q * 32);
+        };
+        // one 32-column half: + bias, + residual (in place), activation, bf16 pack -> 4 x 16 B of this thread's staging row
+        auto finish_half = [&](uint32_t (&a)[32], int ncol0, int h, uint32_t buf) {
+          if (bias) {
+            // columns of the last tile beyond N are never stored, but their bias must not be READ either: the overhang
+            // (e.g. N = 320 on 192-wide tiles) would run past the end of the bias vector
+            const int ncol = p.N - ncol0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (j < ncol) b = __ldg(reinterpret_cast<const float4*>(bias + ncol0 + j));
+              a[j] = __float_as_uint(__uint_as_float(a[j]) + b.x);
+              a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + b.y);
+              a[j + 2] = __float_as_uint(__uint_as_float(a[j + 2]) + b.z);
+              a[j + 3] = __float_as_uint(__uint_as_float(a[j + 3]) + b.w);
+            }
+          }
+          if (has_r1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // 4 x 16 B = 32 bf16 of this row
+              const uint32_t uu = (uint32_t)((h >> 3) + u);
+              uint32_t t0, t1, t2, t3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3)
+                           : "r"(buf + lane * 128 + ((uu ^ xr) << 4)));
+              const uint32_t w[4] = {t0, t1, t2, t3};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16(w[e]);
+                const int j = u * 8 + e * 2;
+                a[j] = __float_as_uint(__uint_as_float(a[j]) + f.x);
+                a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + f.y);
+              }
+            }
+          }
+          if (act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(silu_f(__uint_as_float(a[j])));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t uu = (uint32_t)((h >> 3) + u);
+            const uint32_t addr = buf + lane * 128 + ((uu ^ xr) << 4);
+            const uint32_t k0 = pack_bf16(__uint_as_float(a[8 * u]), __uint_as_float(a[8 * u + 1]));
+            const uint32_t k1 = pack_bf16(__uint_as_float(a[8 * u + 2]), __uint_as_float(a[8 * u + 3]));
+            const uint32_t k2 = pack_bf16(__uint_as_float(a[8 * u + 4]), __uint_as_float(a[8 * u + 5]));
+            const uint32_t k3 = pack_bf16(__uint_as_float(a[8 * u + 6]), __uint_as_float(a[8 * u + 7]));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(k0), "r"(k1), "r"(k2), "r"(k3)
+                         : "memory");
+          }
+        };
+        uint32_t cseq = 0;                          // chunks processed by this warp (staging tile = cseq & 1)
+        Cur pf;                                     // the chunk whose residual is requested next (one ahead of the work)
+        pf.tile = t_begin; pf.lt = 0;
+        pf.m = t_begin / p.n_tiles; pf.n = t_begin - pf.m * p.n_tiles;
+        pf.ch = ((half + 0) & 1) - 2;
+        Cur cur = pf;                               // the tile being drained (cur.ch is set per tile below)
+        bool pf_ok = next_chunk(pf);
+        if (has_r1 && pf_ok) {
+          if (lane == 0) r1_issue(pf, 0);
+          pf_ok = next_chunk(pf);
+        }
+        for (; cur.tile < t_end; next_tile(cur), ++local_tile) {
+          const int tile = cur.tile;
+          const int m0 = cur.m * TILE_M + (int)crank * BM;
+          const int n0 = cur.n * BN;
+          const int nout0 = geglu ? cur.n * (BN / 2) : n0;
           const uint32_t as = local_tile & 1;
           const uint32_t aph = (local_tile >> 1) & 1;
-          // residual boxes of this warp's chunks of the NEXT tile -> L2 now (a whole tile ahead of their TMA loads)
-          if (has_r1 && lane == 0 && tile + n_workers < total_tiles) {
-            const int t2 = tile + n_workers;
-            const int tm2 = (t2 / p.n_tiles) * TILE_M + (int)crank * BM + q * 32;
-            for (int ch = half; ch < nch; ch += n_epi_halves) tma_prefetch_2d(&tmR1, (t2 % p.n_tiles) * BN + ch * 64, tm2);
+          const int nv = n_valid(cur.n);
+          // residual rows of the NEXT tile -> L2 now (a whole tile ahead of their TMA loads)
+          if (has_r1 && lane == 0 && tile + t_step < t_end) {
+            Cur t2 = cur;
+            next_tile(t2);
+            const int nv2 = n_valid(t2.n);
+            for (int ch = (half + t2.lt) & 1; ch < nv2; ch += 2)
+              tma_prefetch_2d(&tmR1, t2.n * BN + ch * 64, t2.m * TILE_M + (int)crank * BM + q * 32);
           }
+          DD_GT(0, tile);
           mbar_wait(tfull_bar + 8 * as, aph);
           tc_fence_after();
+          DD_GT(1, tile);
           const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-          for (int ch = half; ch < nch; ch += n_epi_halves) {
-            const int c = ch * 64;
-            if (lane == 0) bulk_wait_read0();   // the previous TMA store has finished reading the staging tile
+          bool released = false;
+          auto release_acc = [&]() {   // every TMEM load of this warp for this tile has landed
+            tc_fence_before();
             __syncwarp();
-            if (has_r1) {
-              mbar_wait(r1_bar, r1_phase);
-              r1_phase ^= 1;
+            if (lane == 0) {
+              if (crank == 0) mbar_arrive(tempty_bar + 8 * as);
+              else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
             }
+            released = true;
+          };
 #pragma unroll 1
-            for (int h = 0; h < 64; h += 32) {
-              uint32_t a[32];
-              tmem_ld_32x32(tmem_acc + c + h, a);
-              if (geglu) {
-                uint32_t g[32];
+          for (int ch = (half + (int)local_tile) & 1; ch < nv; ch += 2) {
+            const int c = ch * 64;
+            const uint32_t buf = my_stage + (cseq & 1u) * 4096u;
+            const bool last_chunk = ch + 2 >= nv;
+            if (geglu) {
+              if (lane == 0) bulk_wait_read1();   // the store issued two chunks ago has finished reading this staging tile
+              __syncwarp();
+#pragma unroll 1
+              for (int h = 0; h < 64; h += 32) {
+                uint32_t a[32], g[32];
+                tmem_ld_32x32(tmem_acc + c + h, a);
                 tmem_ld_32x32(tmem_acc + BN / 2 + c + h, g);
                 tmem_ld_wait();
+                if (last_chunk && h == 32) release_acc();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
@@ -436,82 +684,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     bv = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
                     bg = __ldg(reinterpret_cast<const float4*>(bias + n0 + BN / 2 + c + h + j));
                   }
-                  a[j] = __float_as_uint((__uint_as_float(a[j]) + bv.x) * gelu_erf_f(__uint_as_float(g[j]) + bg.x));
-                  a[j + 1] = __float_as_uint((__uint_as_float(a[j + 1]) + bv.y) * gelu_erf_f(__uint_as_float(g[j + 1]) + bg.y));
-                  a[j + 2] = __float_as_uint((__uint_as_float(a[j + 2]) + bv.z) * gelu_erf_f(__uint_as_float(g[j + 2]) + bg.z));
-                  a[j + 3] = __float_as_uint((__uint_as_float(a[j + 3]) + bv.w) * gelu_erf_f(__uint_as_float(g[j + 3]) + bg.w));
+                  float r0, r1;
+                  unpack_f32x2(geglu_pair(add_f32x2(pack_f32x2(__uint_as_float(a[j]), __uint_as_float(a[j + 1])), pack_f32x2(bv.x, bv.y)),
+                                          add_f32x2(pack_f32x2(__uint_as_float(g[j]), __uint_as_float(g[j + 1])), pack_f32x2(bg.x, bg.y))), r0, r1);
+                  a[j] = __float_as_uint(r0); a[j + 1] = __float_as_uint(r1);
+                  unpack_f32x2(geglu_pair(add_f32x2(pack_f32x2(__uint_as_float(a[j + 2]), __uint_as_float(a[j + 3])), pack_f32x2(bv.z, bv.w)),
+                                          add_f32x2(pack_f32x2(__uint_as_float(g[j + 2]), __uint_as_float(g[j + 3])), pack_f32x2(bg.z, bg.w))), r0, r1);
+                  a[j + 2] = __float_as_uint(r0); a[j + 3] = __float_as_uint(r1);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t uu = (uint32_t)((h >> 3) + u);
+                  const uint32_t addr = buf + lane * 128 + ((uu ^ xr) << 4);
+                  const uint32_t k0 = pack_bf16(__uint_as_float(a[8 * u]), __uint_as_float(a[8 * u + 1]));
+                  const uint32_t k1 = pack_bf16(__uint_as_float(a[8 * u + 2]), __uint_as_float(a[8 * u + 3]));
+                  const uint32_t k2 = pack_bf16(__uint_as_float(a[8 * u + 4]), __uint_as_float(a[8 * u + 5]));
+                  const uint32_t k3 = pack_bf16(__uint_as_float(a[8 * u + 6]), __uint_as_float(a[8 * u + 7]));
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(k0), "r"(k1), "r"(k2), "r"(k3)
+                               : "memory");
+                }
+              }
+            } else {
+              uint32_t a0[32], a1[32];
+              tmem_ld_32x32(tmem_acc + c, a0);
+              tmem_ld_32x32(tmem_acc + c + 32, a1);
+              if (has_r1) {
+                // the store of the previous chunk has released the OTHER staging tile: the residual of this warp's next
+                // chunk goes there now and has this whole chunk to land
+                if (lane == 0) {
+                  bulk_wait_read0();
+                  if (pf_ok) r1_issue(pf, cseq + 1);
+                }
+                if (pf_ok) pf_ok = next_chunk(pf);
+                __syncwarp();
+                mbar_wait(r1_bar + 8 * (cseq & 1u), (cseq >> 1) & 1u);   // this chunk's residual has landed in `buf`
               } else {
-                tmem_ld_wait();
-                if (bias) {
-                  // columns of the last tile beyond N are never stored, but their bias must not be READ either: the
-                  // overhang (e.g. N = 320 on 192-wide tiles) would run up to 512 B past the end of the bias vector
-                  const int ncol = p.N - (n0 + c + h);
-#pragma unroll
-                  for (int j = 0; j < 32; j += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < ncol) b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + h + j));
-                    a[j] = __float_as_uint(__uint_as_float(a[j]) + b.x);
-                    a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + b.y);
-                    a[j + 2] = __float_as_uint(__uint_as_float(a[j + 2]) + b.z);
-                    a[j + 3] = __float_as_uint(__uint_as_float(a[j + 3]) + b.w);
-                  }
-                }
-                if (has_r1) {
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) {  // 4 x 16 B = 32 bf16 of this row
-                    const uint32_t uu = (uint32_t)((h >> 3) + u);
-                    uint32_t t0, t1, t2, t3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3)
-                                 : "r"(r1_stage + lane * 128 + ((uu ^ xr) << 4)));
-                    const uint32_t w[4] = {t0, t1, t2, t3};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 f = unpack_bf16(w[e]);
-                      const int j = u * 8 + e * 2;
-                      a[j] = __float_as_uint(__uint_as_float(a[j]) + f.x);
-                      a[j + 1] = __float_as_uint(__uint_as_float(a[j + 1]) + f.y);
-                    }
-                  }
-                }
-                if (act == 1) {
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(silu_f(__uint_as_float(a[j])));
-                }
+                if (lane == 0) bulk_wait_read1();   // the store issued two chunks ago has finished reading this staging tile
+                __syncwarp();
               }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t uu = (uint32_t)((h >> 3) + u);
-                const uint32_t addr = out_stage + lane * 128 + ((uu ^ xr) << 4);
-                const uint32_t k0 = pack_bf16(__uint_as_float(a[8 * u]), __uint_as_float(a[8 * u + 1]));
-                const uint32_t k1 = pack_bf16(__uint_as_float(a[8 * u + 2]), __uint_as_float(a[8 * u + 3]));
-                const uint32_t k2 = pack_bf16(__uint_as_float(a[8 * u + 4]), __uint_as_float(a[8 * u + 5]));
-                const uint32_t k3 = pack_bf16(__uint_as_float(a[8 * u + 6]), __uint_as_float(a[8 * u + 7]));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(k0), "r"(k1), "r"(k2), "r"(k3)
-                             : "memory");
-              }
+              DD_GT(2, tile);
+              tmem_ld_wait();
+              DD_GT(3, tile);
+              if (last_chunk) release_acc();
+              finish_half(a0, n0 + c, 0, buf);
+              DD_GT(4, tile);
+              finish_half(a1, n0 + c + 32, 32, buf);
+              DD_GT(5, tile);
             }
-            // residual tile consumed: prefetch this warp's next one (same tile, or its first chunk of the next tile)
-            if (has_r1) {
-              __syncwarp();
-              if (lane == 0) {
-                if (ch + n_epi_halves < nch) r1_issue(tile, ch + n_epi_halves);
-                else if (tile + n_workers < total_tiles && half < nch) r1_issue(tile + n_workers, half);
-              }
-            }
+            ++cseq;
             fence_proxy_async_smem();
             __syncwarp();
+            DD_GT(6, tile);
             if (lane == 0) {
-              tma_store_2d(&tmOut, out_stage, nout0 + c, m0 + q * 32);  // clipped at [M, n_store] by the tensor map
+              tma_store_2d(&tmOut, buf, nout0 + c, m0 + q * 32);  // clipped at [M, n_store] by the tensor map
               bulk_commit();
             }
+            DD_GT(7, tile);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (crank == 0) mbar_arrive(tempty_bar + 8 * as);
-            else mbar_arrive_cluster(mapa_shared(tempty_bar + 8 * as, 0));
-          }
+          if (!released) release_acc();   // no chunk of this tile fell to this warp
         }
         if (lane == 0) bulk_wait0();
       }
@@ -521,7 +751,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // bias / per-image vector / residual / activation -> 16-byte row-segment stores.  Residual rows are pulled into L2
     // one tile ahead (prefetch.global.L2) and into registers one chunk ahead, the first chunk's before the wait on the
     // accumulator, so their HBM latency never sits on the tile's critical path.
-    WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk);
+    WorkIter wi(worker, n_workers, total_tiles, iters, p.sk_chunk, p.areuse);
     const bool sk = p.sk_chunk != 0;
     const int n_store = sk ? BN : p.n_store;
     const int out_ld = sk ? BN : (int)p.out_ld;
@@ -601,8 +831,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + cc));
         }
       }
+      DD_GT(0, tile);
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
+      DD_GT(1, tile);
       const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
@@ -647,6 +879,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         __syncwarp();
+        DD_GT(8, tile);
         // ---- smem -> registers (8 lanes = one row's 64 columns) -> epilogue math -> coalesced global store ----
         if (nout0 + c + width > n_store) {
           // ragged right edge inside this chunk (N not a multiple of 8, e.g. conv_out N = 4): every lane takes a compact
@@ -743,6 +976,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         __syncwarp();
+        DD_GT(9, tile);
         // next chunk of this warp: its residual rows go to registers now
         if (c + 64 * n_ehalves < OUTW) {
           g = chunk_of(nout0, c + 64 * n_ehalves);
@@ -848,7 +1082,15 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   const int kchunks = (p.K + BK - 1) / BK;
   const int iters = CONV ? 3 * kchunks : p.taps * kchunks;
   size_t smem;
-  if constexpr (CONV) {
+  if constexpr (CONV && BN <= 192 && DD_CONV_MERGED) {
+    // merged slots: activation box + the weight boxes of the three taps of a kernel row
+    constexpr int SLOT = A_CONV_BYTES + 3 * B_BYTES;
+    int st = avail / SLOT;
+    st = st > 4 ? 4 : st;
+    p.stages = st;
+    p.a_stages = 0;
+    smem = (size_t)st * SLOT + (size_t)epi_warps * EPI_WARP_BYTES + 1024;
+  } else if constexpr (CONV) {
     int sb = (avail - 3 * A_CONV_BYTES) / B_BYTES;
     sb = sb > 8 ? 8 : sb < 2 ? 2 : sb;
     int sa = (avail - sb * B_BYTES) / A_CONV_BYTES;
@@ -868,6 +1110,8 @@ static int launch_gemm_cg(const CUtensorMap& tmA, const CUtensorMap& tmA2, const
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_tcgen05_kernel<BN, CG, CONV>), 227 * 1024 - 2048)) return rc;
   p.m_tiles = (p.M + BM * CG - 1) / (BM * CG);   // tiles of 128 (one CTA) or 256 (CTA pair) rows
   p.n_tiles = (p.N + BN - 1) / BN;
+  // short K (one ring slot per k-block) and several n-tiles per m-tile: contiguous tile ranges with the A blocks kept in the ring
+  p.areuse = (DD_GEMM_AREUSE && !CONV && p.taps == 1 && p.sk_chunk == 0 && iters >= 2 && p.stages == iters && p.n_tiles >= 2) ? 1 : 0;
   int workers = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
   if (workers > sms / CG) workers = sms / CG;
@@ -957,6 +1201,8 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   }
   if (a->taps == 9) DD_CHECK(a->conv_h > 0 && a->conv_w > 0, -1, "dd_gemm: conv geometry missing");
   if (a->geglu) DD_CHECK(a->N % 256 == 0 && !a->out_f32, -1, "dd_gemm: GEGLU needs N %% 256 == 0 and bf16 out");
+  if (a->geglu) DD_CHECK(a->res1 == nullptr && a->res2 == nullptr && a->rowvec == nullptr && a->act == 0, -1,
+                         "dd_gemm: the GEGLU epilogue takes a bias only");
   const int n_store = a->geglu ? a->N / 2 : a->N;
   DD_CHECK(a->out_ld >= n_store, -1, "dd_gemm: out_ld too small");
   if (n_store % 8 != 0) DD_CHECK(a->res1 == nullptr || true, -1, "unreachable");
@@ -1036,7 +1282,7 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
   p.res1 = reinterpret_cast<const bf16*>(a->res1); p.res1_ld = a->res1_ld;
   p.res2 = reinterpret_cast<const bf16*>(a->res2); p.res2_ld = a->res2_ld;
   p.geglu = a->geglu; p.act = a->act; p.n_store = n_store;
-  p.m_tiles = p.n_tiles = p.stages = 0;
+  p.m_tiles = p.n_tiles = p.stages = 0; p.areuse = 0;
   if (sk_chunk > 0) {
     // pass 1: raw fp32 partial tiles into the workspace; pass 2: ordered sum + the real epilogue
     GemmDev pk = p;
@@ -1073,3 +1319,14 @@ int gemm_run(const dd_gemm_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dd
+
+#ifdef DD_GEMM_TRACE
+// trace builds only (profiles/gemm_trace.py): copy out and clear the per-warp timelines (10 x 2048 events)
+extern "C" __attribute__((visibility("default"))) int dd_gemm_trace_read(unsigned long long* dst) {
+  if (cudaMemcpyFromSymbol(dst, dd::g_gemm_trace, sizeof(dd::g_gemm_trace)) != cudaSuccess) return -1;
+  void* sym = nullptr;
+  if (cudaGetSymbolAddress(&sym, dd::g_gemm_trace) != cudaSuccess) return -1;
+  cudaMemset(sym, 0, sizeof(dd::g_gemm_trace));
+  return 0;
+}
+#endif

@@ -30,6 +30,23 @@ def test_linear(M, N, K, bn):
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K,res,tma", [(40000, 1152, 320, False, True), (40001, 320, 320, True, True), (30000, 320, 192, True, True),
+                                           (40000, 640, 128, True, False), (25000, 704, 256, False, True)])
+def test_short_k_contiguous_tile_ranges(M, N, K, res, tma):
+    """K <= 320 with several n-tiles per m-tile: every worker walks a contiguous range of the tile order and keeps the A
+    blocks of an m-tile in the ring for all of its n-tiles (GemmDev::areuse); several tiles per worker, ragged M / N tails,
+    both epilogues.  Reference = torch fp32 matmul on the GPU over ALL rows."""
+    from dualdiff_b200 import ops
+    a = _mk((M, K), 1); w = _mk((N, K), 2, K ** -0.5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    r1 = _mk((M, N), 4) if res else None
+    out = ops.gemm(a, w, bias=bias, res1=r1, no_tma_epilogue=not tma)
+    ref = a.float() @ w.float().t() + bias + (r1.float() if res else 0)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    again = ops.gemm(a, w, bias=bias, res1=r1, no_tma_epilogue=not tma)
+    assert torch.equal(out, again)
+
+
 def test_epilogue_residual_rowvec_f32():
     from dualdiff_b200 import ops
     n_img, T, K, N = 3, 350, 640, 640
@@ -52,9 +69,9 @@ def test_dual_source_concat():
     assert _rel(out, ref) < 1e-2
 
 
-def test_geglu():
+@pytest.mark.parametrize("M,C", [(500, 320), (30000, 320), (9000, 640)])
+def test_geglu(M, C):
     from dualdiff_b200 import ops, packing
-    M, C = 500, 320
     a = _mk((M, C), 1); w = _mk((8 * C, C), 2, C ** -0.5)
     b = torch.randn(8 * C, generator=torch.Generator().manual_seed(3)).cuda()
     wp, bp = packing.pack_geglu(w, b)
@@ -66,7 +83,8 @@ def test_geglu():
 
 
 @pytest.mark.parametrize("n,H,W,ci,co", [(2, 28, 50, 320, 320), (3, 14, 25, 640, 1280), (2, 7, 13, 1280, 1280),
-                                         (5, 4, 7, 128, 64), (1, 28, 50, 320, 4)])
+                                         (5, 4, 7, 128, 64), (1, 28, 50, 320, 4), (4, 14, 25, 1280, 640), (12, 28, 50, 640, 320),
+                                         (30, 28, 50, 320, 320), (2, 9, 11, 72, 128)])
 def test_conv3x3_implicit_gemm(n, H, W, ci, co):
     from dualdiff_b200 import ops, packing
     x = _mk((n, H, W, ci), 1)
@@ -74,6 +92,23 @@ def test_conv3x3_implicit_gemm(n, H, W, ci, co):
     bias = torch.randn(co, generator=torch.Generator().manual_seed(3)).cuda()
     out = ops.gemm(packing.to_padded(x), packing.pack_conv3x3(w), bias=bias, taps=9, conv_hw=(H, W), n_img=n)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+
+
+def test_conv3x3_dual_source_with_time_vector_and_residual():
+    """the up-block resnets: conv over the channel concat of two padded sources (skip connection) with the per-image time
+    vector and a residual in the epilogue; 160-wide tiles (one ring slot per kernel row and 64 channels)"""
+    from dualdiff_b200 import ops, packing
+    n, H, W, c1, c2, co = 7, 28, 50, 640, 320, 320
+    x1 = _mk((n, H, W, c1), 1); x2 = _mk((n, H, W, c2), 2)
+    w = _mk((co, c1 + c2, 3, 3), 3, (9 * (c1 + c2)) ** -0.5)
+    bias = torch.randn(co, generator=torch.Generator().manual_seed(4)).cuda()
+    rv = torch.randn(n, co, generator=torch.Generator().manual_seed(5)).cuda()
+    r1 = _mk((n * H * W, co), 6)
+    out = ops.gemm(packing.to_padded(x1), packing.pack_conv3x3(w), a2=packing.to_padded(x2), bias=bias, rowvec=rv,
+                   rows_per_img=H * W, res1=r1, taps=9, conv_hw=(H, W), n_img=n)
+    x = torch.cat([x1, x2], -1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(x, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co) + rv.repeat_interleave(H * W, 0) + r1.float()
     assert _rel(out, ref) < 1e-2, _rel(out, ref)
 
 
