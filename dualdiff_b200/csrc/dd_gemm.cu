@@ -760,23 +760,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int rowt = (int)crank * BM + q * 32 + lane;   // row of this thread inside the tile
 
     // padded-pixel row m -> (valid, compact output row)
-    auto map_row = [&](int tile, int& valid, int& orow) {
+    // (also the row of the per-image vector that belongs to it, output row / rows_per_img -- the caller may share one vector
+    // between several images: carried with the row so that the store loop divides nothing; it used to run a 64-bit
+    // division per row segment, a third of its instructions)
+    auto map_row = [&](int tile, int& valid, int& orow, int& img) {
       const int m = (tile / p.n_tiles) * TILE_M + rowt;
       valid = m < p.M;
       orow = m;
+      img = 0;
       if (sk) {
         // raw partial accumulator -> workspace slot of (tile, contributor); every row of the tile is written
         const int slot = tile * p.sk_maxc + (worker - (tile * iters) / p.sk_chunk);
         valid = 1;
         orow = slot * TILE_M + rowt;
       } else if (p.taps == 9) {
-        const int img = m / HW1;
-        const int rem = m - img * HW1;
+        const int im = m / HW1;
+        const int rem = m - im * HW1;
         const int hp = rem / pitch;
         const int wp = rem - hp * pitch;
         valid = valid && (hp < p.conv_H) && (wp < p.conv_W);
-        orow = (img * p.conv_H + hp) * p.conv_W + wp;
+        orow = (im * p.conv_H + hp) * p.conv_W + wp;
       }
+      if (p.rowvec && valid && !sk) img = orow / p.rows_per_img;
     };
     // chunk geometry of this lane: 8 lanes own the 64 columns of one row (4 lanes for a 32-column tail chunk)
     struct Chunk { int lpr, rpi, nit, col; bool vec; };
@@ -790,16 +795,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       g.vec = g.col + 8 <= n_store;
       return g;
     };
-    int orow_j[8];
+    int orow_j[8], img_j[8];
     uint32_t vmask = 0;
     uint4 r1v[8];
-    auto prefetch_chunk = [&](const Chunk& g, int valid, int orow) {
+    auto prefetch_chunk = [&](const Chunk& g, int valid, int orow, int img) {
       vmask = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j < g.nit) {
           const int rr = j * g.rpi + lane / g.lpr;
           orow_j[j] = __shfl_sync(0xffffffffu, orow, rr);
+          img_j[j] = __shfl_sync(0xffffffffu, img, rr);
           const int vj = __shfl_sync(0xffffffffu, valid, rr) && (g.col < n_store);
           vmask |= (uint32_t)vj << j;
           r1v[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -809,25 +815,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
 
     bool have = wi.next();
-    int valid = 0, orow = 0;
-    if (have) map_row(wi.tile, valid, orow);
+    int valid = 0, orow = 0, img = 0;
+    if (have) map_row(wi.tile, valid, orow, img);
     for (; have; ++local_tile) {
       const int tile = wi.tile;
       const int n0 = (tile % p.n_tiles) * BN;
       const int nout0 = sk ? 0 : p.geglu ? (n0 / BN) * (BN / 2) : n0;
       const uint32_t as = local_tile & 1;
       const uint32_t aph = (local_tile >> 1) & 1;
-      Chunk g = chunk_of(nout0, ehalf * 64);
-      if (ehalf * 64 < OUTW) prefetch_chunk(g, valid, orow);          // first chunk's residual rows: before the wait
+      // the two warp halves swap the even / odd 64-column chunks from tile to tile: a 160-wide tile has 64 + 64 + 32
+      // columns, and the two accumulator buffers let one half run a tile ahead of the other
+      const int eh = n_ehalves == 2 ? ((ehalf + (int)local_tile) & 1) : 0;
+      Chunk g = chunk_of(nout0, eh * 64);
+      if (eh * 64 < OUTW) prefetch_chunk(g, valid, orow, img);        // first chunk's residual rows: before the wait
       // next tile: row mapping now, residual rows into L2 (one tile = several microseconds ahead)
       have = wi.next();
-      int valid_n = 0, orow_n = 0;
+      int valid_n = 0, orow_n = 0, img_n = 0;
       if (have) {
-        map_row(wi.tile, valid_n, orow_n);
+        map_row(wi.tile, valid_n, orow_n, img_n);
         if (has_r1 && valid_n) {
           const int nn0 = (wi.tile % p.n_tiles) * BN;
           const bf16* rp = p.res1 + (long long)orow_n * p.res1_ld + nn0;
-          for (int cc = ehalf * 64; cc < OUTW && nn0 + cc < n_store; cc += 64 * n_ehalves)
+          for (int cc = (n_ehalves == 2 ? (eh ^ 1) : 0) * 64; cc < OUTW && nn0 + cc < n_store; cc += 64 * n_ehalves)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + cc));
         }
       }
@@ -838,7 +847,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t tmem_acc = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
 
 #pragma unroll 1
-      for (int c = ehalf * 64; c < OUTW; c += 64 * n_ehalves) {
+      for (int c = eh * 64; c < OUTW; c += 64 * n_ehalves) {
         const int width = (OUTW - c) < 64 ? (OUTW - c) : 64;  // 64, or 32 for the last chunk of BN = 32/160
         const int k = lane % g.lpr;
         const int col = g.col;
@@ -889,6 +898,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int rr = j * g.rpi + lane / g.lpr;
             const long long orow_r = __shfl_sync(0xffffffffu, orow, rr);
             const int vr = __shfl_sync(0xffffffffu, valid, rr);
+            const int img_r = __shfl_sync(0xffffffffu, img, rr);
 #pragma unroll 1
             for (int e = 0; e < 8; ++e) {
               const int ci = k * 8 + e, uu = ci >> 2;
@@ -898,7 +908,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stage_buf + rr * 256 + (pu << 4) + (ci & 3) * 4));
               if (!p.geglu) {
                 if (p.bias) x += p.bias[col + e];
-                if (p.rowvec) x += p.rowvec[(orow_r / p.rows_per_img) * (long long)p.rowvec_ld + col + e];
+                if (p.rowvec) x += p.rowvec[(long long)img_r * p.rowvec_ld + col + e];
                 if (p.res1) x += __bfloat162float(p.res1[orow_r * p.res1_ld + col + e]);
                 if (p.res2) x += __bfloat162float(p.res2[orow_r * p.res2_ld + col + e]);
                 if (p.act == 1) x = silu_f(x);
@@ -933,7 +943,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[0] += bia0.x; v[1] += bia0.y; v[2] += bia0.z; v[3] += bia0.w;
                 v[4] += bia1.x; v[5] += bia1.y; v[6] += bia1.z; v[7] += bia1.w;
                 if (p.rowvec) {
-                  const int im = (int)(orow_r / p.rows_per_img);
+                  const int im = img_j[j];
                   if (im != rv_img) {   // rows ascend: the per-image vector is reloaded only when the image changes
                     const float* rv = p.rowvec + (long long)im * p.rowvec_ld + col;
                     rv0 = *reinterpret_cast<const float4*>(rv);
@@ -980,7 +990,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // next chunk of this warp: its residual rows go to registers now
         if (c + 64 * n_ehalves < OUTW) {
           g = chunk_of(nout0, c + 64 * n_ehalves);
-          prefetch_chunk(g, valid, orow);
+          prefetch_chunk(g, valid, orow, img);
         }
       }
       // release the accumulator buffer back to the MMA warp
@@ -992,6 +1002,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       valid = valid_n;
       orow = orow_n;
+      img = img_n;
     }
     }
   }

@@ -108,8 +108,12 @@ def test_conv3x3_dual_source_with_time_vector_and_residual():
     out = ops.gemm(packing.to_padded(x1), packing.pack_conv3x3(w), a2=packing.to_padded(x2), bias=bias, rowvec=rv,
                    rows_per_img=H * W, res1=r1, taps=9, conv_hw=(H, W), n_img=n)
     x = torch.cat([x1, x2], -1).float().permute(0, 3, 1, 2)
-    ref = F.conv2d(x, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co) + rv.repeat_interleave(H * W, 0) + r1.float()
-    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    conv = F.conv2d(x, w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, co) + r1.float()
+    assert _rel(out, conv + rv.repeat_interleave(H * W, 0)) < 1e-2
+    # ONE time vector shared by all images (every image of a sampler step has the same timestep: rows_per_img = n * H * W)
+    out1 = ops.gemm(packing.to_padded(x1), packing.pack_conv3x3(w), a2=packing.to_padded(x2), bias=bias, rowvec=rv[:1],
+                    rows_per_img=n * H * W, res1=r1, taps=9, conv_hw=(H, W), n_img=n)
+    assert _rel(out1, conv + rv[:1]) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,K,res,act", [(134400 // 8, 320, 320, True, 0), (1000, 1088, 320, False, 0), (4200, 640, 640, True, 1),
