@@ -91,6 +91,9 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, fl
 }
 
 // normalise one O row held in TMEM and store (or, for the second source of the cross-view attention, add) it to global
+// The tcgen05 fence that must separate these TMEM loads from the thread's next barrier arrival is issued right after the LAST
+// load has landed, before the final stores: behind them it waited for the global stores as well (timeline of the text
+// cross-attention, profiles/attn_trace.py 2 text: 1000-1700 cycles per item between the last store and the fence's return).
 template <int DV, int DVP>
 __device__ __forceinline__ void store_o_row(uint32_t tmem_o_row, float inv, bf16* orow, bool valid, bool add) {
 #pragma unroll
@@ -98,6 +101,7 @@ __device__ __forceinline__ void store_o_row(uint32_t tmem_o_row, float inv, bf16
     uint32_t ov[16];
     tmem_ld_32x16(tmem_o_row + c, ov);
     tmem_ld_wait();
+    if (c + 16 >= DVP) tc_fence_before();
     if (valid) {
 #pragma unroll
       for (int hh = 0; hh < 16; hh += 8) {
@@ -514,8 +518,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld_wait();
           l = __uint_as_float(t16[DV % 16]);
         }
-        store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);
-        tc_fence_before();
+        store_o_row<DV, DVP>(tmem_O, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);   // (ends with the tcgen05 fence)
         DD_TR(6, k);
       }
       item += stride;
@@ -834,8 +837,7 @@ attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // already loading the next source / item; its first P V waits for this thread's next p_full arrival.
       mbar_wait(o_full, (g - 1) & 1);
       tc_fence_after();
-      store_o_row<DV, DVP>(tmem_O + lane_sel, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);
-      tc_fence_before();
+      store_o_row<DV, DVP>(tmem_O + lane_sel, 1.f / l, orow, q_row < p.Lq, src > 0 && !p.concat);   // (ends with the tcgen05 fence)
     }
     }
   }

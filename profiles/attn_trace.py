@@ -7,21 +7,32 @@ sys.path.insert(0, ROOT)
 src = os.path.join(ROOT, "dualdiff_b200", "csrc")
 out = "/tmp/libdualdiff_trace.so"
 objs = []
-for f in sorted(os.listdir(src)):
+PREBUILT = os.path.join(ROOT, "profiles", "ab", "lib_attn_trace.so")   # built on the CPU box: saves GPU-box minutes
+if os.path.exists(PREBUILT):
+    out = PREBUILT
+for f in ([] if out == PREBUILT else sorted(os.listdir(src))):
     if f.startswith("dd_") and f.endswith(".cu"):
         o = f"/tmp/trace_{f[:-3]}.o"
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler",
                                "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-DDD_ATTN_TRACE", "-c", os.path.join(src, f), "-o", o])
         objs.append(o)
-subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-shared", "-o", out] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+if out != PREBUILT:
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-shared", "-o", out] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
 from dualdiff_b200 import _lib
 _lib.LIB_PATH = out
 import torch
 from dualdiff_b200 import ops
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+TEXT = len(sys.argv) > 2 and sys.argv[2] == "text"     # text cross-attention: 106 keys (three 48-key tiles per item)
 n, L, d, dp = 96, 1400, 40, 48
-qkv = (torch.randn(n * L, 16 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
-run = lambda: ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp, variant=variant)
+if TEXT:
+    q = (torch.randn(n * L, 8 * dp, device="cuda") * 0.5).to(torch.bfloat16)
+    kv = (torch.randn(n * 106, 16 * dp, device="cuda") * 0.5).to(torch.bfloat16)
+    kv.view(n * 106, 2, 8, dp)[:, 1, :, 40] = 1.0
+    run = lambda: ops.attention(q, kv, kv, n_img=n, lq=L, lk=106, heads=8, head_dim=d, q_col0=0, k_col0=0, v_col0=8 * dp, v_ones=True, variant=variant)
+else:
+    qkv = (torch.randn(n * L, 16 * dp + 8 * d, device="cuda") * 0.5).to(torch.bfloat16)
+    run = lambda: ops.attention(qkv, qkv, qkv, n_img=n, lq=L, lk=L, heads=8, head_dim=d, q_col0=0, k_col0=8 * dp, v_col0=16 * dp, variant=variant)
 lib = _lib.lib()
 buf = (C.c_ulonglong * (2 * 10 * 4096))()
 for _ in range(3):
@@ -34,9 +45,12 @@ lib.dd_attn_trace_read(buf)
 ev = [((buf[2 * i] >> 48) & 0xffff, (buf[2 * i] >> 32) & 0xffff, buf[2 * i] & 0xffffffff, buf[2 * i + 1]) for i in range(10 * 4096) if buf[2 * i + 1]]
 ne = len(ev)
 t0 = min(e[3] for e in ev)
-names = {0: "wait S", 1: "got S", 2: "S in regs", 3: "exp done", 4: "PV(k-1) ok", 5: "P published", 6: "epilogue", 10: "iter", 11: "s_free seen",
+names = {0: "wait S", 1: "got S", 2: "S in regs", 3: "exp done", 4: "PV(k-1) ok", 5: "P published", 6: "epilogue", 7: "last PV ok", 20: "O requested", 21: "O in regs", 22: "1/l", 23: "O stored", 24: "item done", 25: "advanced", 26: "row pointer", 10: "iter", 11: "s_free seen",
          12: "QK(k+1) issued", 13: "p_full seen", 14: "produce start", 15: "produce done", 16: "PV issued"}
 print(f"{ne} events from one CTA; times in SM cycles")
+if TEXT:   # raw hand-over sequence of one softmax warp: the per-item epilogue and the step to the next item
+    seq = sorted([(t - t0, names.get(e, str(e))) for e, w, k, t in ev if w == 0])
+    print("warp 0, first 70 events (cycle, event, +delta): " + " | ".join(f"{c} {nm} +{c - (seq[i - 1][0] if i else 0)}" for i, (c, nm) in enumerate(seq[:70])))
 by = {}
 for e, w, k, t in ev:
     by.setdefault((w, k), {})[e] = t - t0
