@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Same-box A/B builds of the CUDA library (after dualdiff_b200/csrc/build.sh):
-#   profiles/ab/lib_old.so      dd_gemm.cu / dd_attention.cu / dd_common.cuh of git revision $OLD_REV (default HEAD), the rest as built
+#   profiles/ab/lib_old.so      every source of git revision $OLD_REV (default HEAD)
 #   profiles/ab/lib_<tag>.so    the working-tree sources with -D overrides for dd_gemm.cu (DD_GEMM_AREUSE selects the tile
 #                               schedule; DD_PROBE the differential-timing probes, whose results are wrong by construction)
 # Run one of them with  python profiles/bench_with_lib.py profiles/ab/lib_<tag>.so ...  or  profiles/gemm_probe.py <lib>.
@@ -17,13 +17,13 @@ build_one() {  # tag, defines...
   link $tag build/dd_gemm_$tag.o
 }
 mkdir -p build/old
-for f in dd_gemm.cu dd_attention.cu dd_common.cuh dd_api_internal.h; do git show $OLD_REV:dualdiff_b200/csrc/$f > build/old/$f; done
-sed -i 's#"../../include/dualdiff_b200.h"#"../../../../include/dualdiff_b200.h"#' build/old/dd_api_internal.h
-( $NVCC $FLAGS -c build/old/dd_gemm.cu -o build/dd_gemm_old.o &
-  $NVCC $FLAGS -c build/old/dd_attention.cu -o build/old/dd_attention.o &
+rm -f build/old/*
+for f in $(git ls-tree --name-only $OLD_REV ./ | grep -E "\.(cu|cuh|h)$"); do git show $OLD_REV:./$f > build/old/$f; done
+sed -i 's#"../../include/dualdiff_b200.h"#"../../../../include/dualdiff_b200.h"#' build/old/*.cu build/old/*.h build/old/*.cuh
+( for f in build/old/dd_*.cu; do $NVCC $FLAGS -c $f -o ${f%.cu}.o & done
   wait
-  $NVCC -shared -o ../../profiles/ab/lib_old.so build/dd_gemm_old.o build/old/dd_attention.o $(ls build/dd_*.o | grep -v "dd_gemm\|dd_attention") \
-    -lcudart_static -lpthread -ldl -lrt && echo "built profiles/ab/lib_old.so" ) &
+  $NVCC -shared -o ../../profiles/ab/lib_old.so build/old/dd_*.o -lcudart_static -lpthread -ldl -lrt &&
+    python3 -c "import ctypes; ctypes.CDLL('../../profiles/ab/lib_old.so').dd_launch_count" && echo "built profiles/ab/lib_old.so" ) &
 for v in "$@"; do
   case $v in
     noareuse) build_one noareuse -DDD_GEMM_AREUSE=0 & ;;
