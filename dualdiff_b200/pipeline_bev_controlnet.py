@@ -54,6 +54,27 @@ class _NullBar:
         self.n += n
 
 
+def pad_boxes(data, max_len: int, batch: int, n_cam: int, device):
+    """`bbox_max_length` (reference pipeline :358,366 -> `BEVControlNetModel.add_uncond_to_kwargs(max_len=...)`,
+    unet_addon_rawbox.py:683-760): the box / map-vector lists are padded along the token axis with zero boxes, class 0 and mask
+    False up to `max_len` tokens -- masked tokens become the learned null token, so the key count of the text cross-attention
+    follows `max_len`; a missing dict (no visible boxes) becomes an all-masked one.  The unconditional half is built from the
+    padded shapes by `DualDiffDenoiser.prepare` as for unpadded boxes."""
+    if data is None:
+        return {"bboxes": torch.zeros([batch, n_cam, max_len, 8, 3], device=device),
+                "classes": torch.zeros([batch, n_cam, max_len], device=device, dtype=torch.long),
+                "masks": torch.zeros([batch, n_cam, max_len], device=device, dtype=torch.bool)}
+    out = {}
+    for key in ("bboxes", "classes", "masks"):
+        v = data[key]
+        extra = max_len - v.shape[2]
+        assert extra >= 0, f"bbox_max_length={max_len} < {v.shape[2]} {key} tokens"
+        out[key] = torch.cat([v, torch.zeros_like(v[:, :, :1]).expand(-1, -1, extra, *v.shape[3:])], dim=2) if extra else v
+    for key, v in data.items():
+        out.setdefault(key, v)
+    return out
+
+
 class StableDiffusionBEVControlNetPipeline:
     def __init__(self, vae, text_encoder, unet, controlnet, scheduler, tokenizer, safety_checker=None,
                  feature_extractor=None, requires_safety_checker: bool = False):
@@ -279,7 +300,7 @@ class StableDiffusionBEVControlNetPipeline:
         move = lambda d: None if d is None else {k: v.to(device) for k, v in d.items()}
         boxes = [move(b) for b in bboxes_3d_data]
         if bbox_max_length is not None:                                # pad the boxes to max_len (:358,366 -> add_uncond_to_kwargs)
-            raise NotImplementedError("bbox_max_length: pad `bboxes_3d_data` in the collate function instead")
+            boxes = [pad_boxes(b, bbox_max_length, batch_size * num_images_per_prompt, n_cam, device) for b in boxes]
         # 8. denoising loop: one DualDiffDenoiser (CUDA graph per step)
         den = self._denoiser
         if den is None or den.unet is not self.unet or den.nets != nets or den.scheduler is not self.scheduler:

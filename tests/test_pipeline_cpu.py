@@ -91,3 +91,24 @@ def test_call_checks_before_touching_the_gpu():
         pipe(**dict(base, image=torch.zeros(1)), bev_controlnet_kwargs={"use_aug_text": False})
     with pytest.raises(AssertionError):
         type(pipe)(None, None, None, None, None, None, safety_checker=object())
+
+
+def test_bbox_max_length_pads_like_the_reference():
+    """`bbox_max_length` (reference pipeline :358,366 -> add_uncond_to_kwargs(max_len=...), unet_addon_rawbox.py:683-760):
+    zero boxes / class 0 / mask False appended along the token axis, an absent dict becomes an all-masked one; restated
+    inline from the reference for the conditional half (the unconditional half is built from the padded shapes)."""
+    from dualdiff_b200.pipeline_bev_controlnet import pad_boxes
+    g = torch.Generator().manual_seed(0)
+    data = {"bboxes": torch.randn(2, 6, 5, 8, 3, generator=g), "classes": torch.randint(0, 10, (2, 6, 5), generator=g),
+            "masks": torch.rand(2, 6, 5, generator=g) > 0.3}
+    out = pad_boxes(data, 9, 2, 6, torch.device("cpu"))
+    for key in ("bboxes", "classes", "masks"):
+        v = data[key]
+        to_pad = torch.zeros_like(v)[:, :, 1].unsqueeze(2).expand(-1, -1, 4, *v.shape[3:])        # reference :731-736
+        ref = torch.cat([v, to_pad], dim=2)
+        assert out[key].dtype == v.dtype and torch.equal(out[key], ref), key
+    assert pad_boxes(data, 5, 2, 6, torch.device("cpu"))["bboxes"] is data["bboxes"]              # nothing to pad
+    none = pad_boxes(None, 7, 2, 6, torch.device("cpu"))                                            # reference :708-716
+    assert none["bboxes"].shape == (2, 6, 7, 8, 3) and none["classes"].dtype == torch.long and not none["masks"].any()
+    with pytest.raises(AssertionError):
+        pad_boxes(data, 4, 2, 6, torch.device("cpu"))

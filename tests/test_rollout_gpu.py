@@ -161,6 +161,15 @@ def test_pipeline_call_matches_oracle(world):
     assert d.max() <= 0.1 and d.mean() <= 0.02
     pil = pipe(**kwargs, generator=torch.Generator().manual_seed(7), num_images_per_prompt=1).images
     assert len(pil) == 2 and len(pil[0]) == 6 and pil[0][0].size == (96, 64)
+    # ---- bbox_max_length (reference :358,366): the call pads the box lists with masked tokens; it must equal the same call on
+    # hand-padded lists bit for bit, and differ from the unpadded one (the null tokens join the keys of the text cross-attention)
+    from dualdiff_b200.pipeline_bev_controlnet import pad_boxes
+    padded = [pad_boxes(b, 9, 2, 6, torch.device("cpu")) for b in (inp["boxes_bg"], inp["boxes_fg"])]
+    assert padded[0]["bboxes"].shape[2] == 9 and padded[1]["bboxes"].shape[2] == 9
+    kw_pad = dict(kwargs, bev_controlnet_kwargs={"bboxes_3d_data": padded, "use_aug_text": False})
+    a = pipe(**kwargs, generator=torch.Generator().manual_seed(7), output_type="latent", bbox_max_length=9).images
+    b = pipe(**kw_pad, generator=torch.Generator().manual_seed(7), output_type="latent").images
+    assert torch.isfinite(a).all() and torch.equal(a, b) and not torch.equal(a.float().cpu(), lat)
 
 
 def test_pipeline_rejects_unbuilt_options(world):
