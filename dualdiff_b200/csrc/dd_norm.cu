@@ -424,8 +424,11 @@ gn_slab_kernel(const GnSlabDev p) {
 
 // groups per CTA of the single-pass kernel (0 = the two-kernel form must be used): the channel range must start on a
 // multiple of 8 channels, an octet may straddle at most two groups, and the [rows x channels] slab must leave room for two
-// CTAs per SM; among the admissible sizes the largest one of at most 64 KB is taken as long as it still yields two waves
-// of CTAs, else the smallest.
+// CTAs per SM; among the admissible sizes the largest one of at most 64 KB is taken as long as the grid still has
+// DD_GN_MIN_CTAS_PER_SM CTAs per SM, else the smallest.
+#ifndef DD_GN_MIN_CTAS_PER_SM
+#define DD_GN_MIN_CTAS_PER_SM 2      // CTAs per SM the plan keeps when it widens the slabs (A/B hook; 1 / 2 / 3 / 4 / 6 / 8 measured: profiles/r02_groupnorm_slab_width.txt)
+#endif
 static int gn_slab_plan(int C, int groups, int HW, int n_img, size_t* smem_bytes) {
   const int cpg = C / groups;
   if (cpg < 8 || groups > 64 * 64) return 0;
@@ -441,7 +444,7 @@ static int gn_slab_plan(int C, int groups, int HW, int n_img, size_t* smem_bytes
     const size_t need = hdr + (size_t)HW * width * 2;
     if (need > limit) break;
     const long long ctas = (long long)n_img * ((groups + g - 1) / g);
-    if (best == 0 || (need <= 64 * 1024 + hdr && ctas >= 2LL * 2 * num_sms())) best = g;
+    if (best == 0 || (need <= 64 * 1024 + hdr && ctas >= (long long)DD_GN_MIN_CTAS_PER_SM * num_sms())) best = g;
   }
   if (best == 0) return 0;
   *smem_bytes = hdr + (size_t)HW * best * cpg * 2;
