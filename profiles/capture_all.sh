@@ -16,3 +16,11 @@ DD_EXPERIMENTAL=1 python -m pytest tests/test_experimental.py -m gpu -q > gpurun
 DD_CONV_IN_PATCH=1 python bench.py --steps 10 --warmup 3 > gpurun_out/ab_conv_in_patch.json 2>/dev/null
 DD_SMALL_CONV_IM2COL=28 python bench.py --steps 10 --warmup 3 > gpurun_out/ab_small_conv_im2col.json 2>/dev/null
 ls -la gpurun_out | tail -20
+
+# ---- round 2 (final state): the driver's sequence + evidence behind profiles/r02_*; see r02_call39.sh / r02_call40.sh for the runs as made
+bash profiles/r02_call39.sh          # GPU suite, smoke, reference arm, default bench, ncu launch list + ncu --set full (L0 conv, K = 320 GEMM), pipeline timing
+bash profiles/r02_call40.sh          # compute-sanitizer memcheck (full latent) + synccheck
+# same-box A/B and timelines (CPU box first: bash dualdiff_b200/csrc/build.sh && bash profiles/ab/build_variants.sh [noareuse nomerged], then
+#  nvcc -DDD_GEMM_TRACE / -DDD_ATTN_TRACE builds linked to profiles/ab/lib_trace.so / lib_attn_trace.so as in profiles/README.md):
+#   python profiles/gemm_probe.py <lib> check ; python profiles/conv_probe.py <lib> ; python profiles/attn_probe.py <lib> ; python profiles/gn_probe.py <lib>
+#   python profiles/gemm_trace.py [conv] ; python profiles/attn_trace.py 2 text ; bash profiles/ab/ab_bench.sh ; bash profiles/ab/ab_streams.sh
